@@ -1,0 +1,237 @@
+/* pgmm_oracle.c -- plain-C CPU restatement of the reference's alignment hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the checker for the CUDA path: only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline leg may load it.  Nothing under pangraph_b200/ links or calls it, and it must never be
+ * the thing that is measured or shipped.
+ *
+ * Parity status: PINNED.  Every function here is checked (tests/test_oracle_vs_ref.py) against the unmodified
+ * vendored minimap2 C of the reference, compiled from /root/reference by oracle/Makefile into
+ * oracle/_ref/libmm2ref.so, which itself reproduces the reference's only boundary golden vector
+ * (packages/pangraph/src/align/minimap2_lib/align_with_minimap2_lib.rs:135-204).
+ *
+ * Citations use C/ = packages/minimap2-sys/minimap2/ of the reference.
+ * The code is scalar and written per cell / per element on purpose: it states WHAT the reference's SSE and
+ * macro-generated code computes, one value at a time, so that a data-parallel kernel can be compared with it.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_NEG_INF (-0x40000000) /* C/ksw2.h:6 */
+/* flag bits, C/ksw2.h:8-14 */
+#define ORC_EZ_RIGHT 0x02
+#define ORC_EZ_APPROX_MAX 0x08
+#define ORC_EZ_EXTZ_ONLY 0x40
+#define ORC_EZ_REV_CIGAR 0x80
+
+typedef struct {
+	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
+} orc_ez_t;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ksw_extd2: dual-affine banded extension/global DP with traceback.  C/ksw2_extd2_sse.c:34-401.
+ *
+ * State per target position t (one signed byte each, wrap-around arithmetic): u,v,x,y,x2,y2 are the
+ * Suzuki-Kasahara difference values of the previous anti-diagonal, s the substitution score last written for t.
+ * The reference computes 16 positions at a time, so on every anti-diagonal r it evaluates the padded range
+ * [st,en] (st rounded down, en rounded up to 16) although only [st0,en0] is inside the band; the padded cells
+ * use whatever s[t] holds.  Those cells are observable (band edges, traceback), so they are restated too.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+static inline int8_t w8(int v) { return (int8_t)(uint8_t)v; } /* wrap to int8 like _mm_add_epi8/_mm_sub_epi8 */
+
+/* push one op of length 1 with run-length merging, C/ksw2.h:111-121 */
+static void orc_push(uint32_t *cigar, int *n, uint32_t op, int len)
+{
+	if (*n == 0 || op != (cigar[*n - 1] & 0xf)) cigar[(*n)++] = (uint32_t)len << 4 | op;
+	else cigar[*n - 1] += (uint32_t)len << 4;
+}
+
+int orc_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                  int q, int e, int q2, int e2, int w, int zdrop, int end_bonus, int flag,
+                  orc_ez_t *ez, uint32_t *cigar /* capacity >= qlen+tlen+2 */)
+{
+	const int m = 5;
+	int r, t, approx_max = !!(flag & ORC_EZ_APPROX_MAX);
+	/* ksw_reset_extz, C/ksw2.h:161-166 */
+	ez->max_q = ez->max_t = ez->mqe_t = ez->mte_q = -1;
+	ez->max = 0, ez->score = ez->mqe = ez->mte = ORC_NEG_INF;
+	ez->n_cigar = 0, ez->zdropped = 0, ez->reach_end = 0;
+	if (qlen <= 0 || tlen <= 0) return 0;
+	if (q2 + e2 < q + e) { t = q, q = q2, q2 = t, t = e, e = e2, e2 = t; } /* :73 */
+	int8_t sc_mch = mat[0], sc_mis = mat[1], sc_N = mat[m * m - 1] == 0 ? w8(-e2) : mat[m * m - 1]; /* :81-83 */
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int tlen_ = (tlen + 15) / 16, qlen_ = (qlen + 15) / 16;
+	int n_col = qlen < tlen ? qlen : tlen;
+	n_col = ((n_col < w + 1 ? n_col : w + 1) + 15) / 16 + 1; /* :89-91 */
+	{ /* :93-97 */
+		int min_sc = mat[1];
+		for (t = 1; t < m * m; ++t) min_sc = min_sc < mat[t] ? min_sc : mat[t];
+		if (-min_sc > 2 * (q + e)) return 0;
+	}
+	int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0; /* :99-102 */
+	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+	int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+
+	int T = tlen_ * 16, Q = (qlen_ + 1) * 16;
+	/* one allocation laid out like the reference's (:104-107): ... s | sf | qr, so that reads past the end of the
+	 * target copy land in the reversed query, and reads past the reversed query land in zeros */
+	int8_t *u = malloc((size_t)T * 7 + T + Q + 16), *v = u + T, *x = v + T, *y = x + T, *x2 = y + T, *y2 = x2 + T, *s = y2 + T;
+	uint8_t *sf = (uint8_t*)(s + T), *qr = sf + T;
+	memset(u, w8(-q - e), (size_t)T * 4);
+	memset(x2, w8(-q2 - e2), (size_t)T * 2);
+	memset(s, 0, (size_t)T + T + Q + 16);
+	int32_t *H = 0;
+	if (!approx_max) {
+		H = malloc(sizeof(int32_t) * T);
+		for (t = 0; t < T; ++t) H[t] = ORC_NEG_INF;
+	}
+	int n_row = qlen + tlen - 1, stride = n_col * 16;
+	uint8_t *p = malloc((size_t)n_row * stride + 16);
+	int *off = malloc(sizeof(int) * 2 * n_row), *off_end = off + n_row;
+	for (t = 0; t < qlen; ++t) qr[t] = query[qlen - 1 - t];
+	memcpy(sf, target, tlen);
+
+	int last_st = -1, last_en = -1, H0 = 0, last_H0_t = 0, qe = q + e, qe2 = q2 + e2;
+	for (r = 0; r < n_row; ++r) {
+		int st = 0, en = tlen - 1, st0, en0;
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+		if (en > (r + w) >> 1) en = (r + w) >> 1;
+		if (st > en) { ez->zdropped = 1; break; } /* :142-145 */
+		st0 = st, en0 = en;
+		st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
+		/* values standing in for position st-1 of the previous anti-diagonal, :149-159 */
+		int8_t x1, x21, v1;
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = x[st - 1], x21 = x2[st - 1], v1 = v[st - 1];
+			else x1 = w8(-q - e), x21 = w8(-q2 - e2), v1 = w8(-q - e);
+		} else {
+			x1 = w8(-q - e), x21 = w8(-q2 - e2);
+			v1 = r == 0 ? w8(-q - e) : r < long_thres ? w8(-e) : r == long_thres ? w8(long_diff) : w8(-e2);
+		}
+		if (en >= r) { /* first row of the matrix, :160-163 */
+			y[r] = w8(-q - e), y2[r] = w8(-q2 - e2);
+			u[r] = r == 0 ? w8(-q - e) : r < long_thres ? w8(-e) : r == long_thres ? w8(long_diff) : w8(-e2);
+		}
+		/* substitution scores: written in runs of 16 starting at st0, :165-180 (the run may pass en0 and, when
+		 * tlen is a multiple of 16, the end of s[] -- it then lands in sf[0..], which is never read again) */
+		const uint8_t *qrr = qr + (qlen - 1 - r);
+		for (t = st0; t <= en0; t += 16) {
+			int k;
+			for (k = 0; k < 16; ++k) {
+				uint8_t a = sf[t + k], b = qrr[t + k];
+				s[t + k] = (a == m - 1 || b == m - 1) ? sc_N : a == b ? sc_mch : sc_mis;
+			}
+		}
+		/* the recurrence, one cell at a time; xp/vp/x2p carry the previous anti-diagonal's value at t-1 */
+		int8_t xp = x1, vp = v1, x2p = x21;
+		uint8_t *pr = p + (size_t)r * stride - st;
+		off[r] = st, off_end[r] = en;
+		for (t = st; t <= en; ++t) {
+			int8_t z = s[t], xt1 = xp, vt1 = vp, x2t1 = x2p, ut = u[t], d;
+			xp = x[t], vp = v[t], x2p = x2[t];
+			int8_t a = w8(xt1 + vt1), b = w8(y[t] + ut), a2 = w8(x2t1 + vt1), b2 = w8(y2[t] + ut);
+			if (!(flag & ORC_EZ_RIGHT)) { /* gap left-alignment, :228-275 */
+				d = a > z ? 1 : 0;  z = z > a ? z : a;
+				d = b > z ? 2 : d;  z = z > b ? z : b;
+				d = a2 > z ? 3 : d; z = z > a2 ? z : a2;
+				d = b2 > z ? 4 : d; z = z > b2 ? z : b2;
+			} else { /* gap right-alignment, :276-322 */
+				d = z > a ? 0 : 1;  z = z > a ? z : a;
+				d = z > b ? d : 2;  z = z > b ? z : b;
+				d = z > a2 ? d : 3; z = z > a2 ? z : a2;
+				d = z > b2 ? d : 4; z = z > b2 ? z : b2;
+			}
+			z = z < sc_mch ? z : sc_mch;
+			u[t] = w8(z - vt1), v[t] = w8(z - ut);
+			int8_t tmp = w8(z - q), tmp2 = w8(z - q2);
+			a = w8(a - tmp), b = w8(b - tmp), a2 = w8(a2 - tmp2), b2 = w8(b2 - tmp2);
+			if (!(flag & ORC_EZ_RIGHT)) {
+				x[t]  = w8((a  > 0 ? a  : 0) - qe);  if (a  > 0) d |= 0x08;
+				y[t]  = w8((b  > 0 ? b  : 0) - qe);  if (b  > 0) d |= 0x10;
+				x2[t] = w8((a2 > 0 ? a2 : 0) - qe2); if (a2 > 0) d |= 0x20;
+				y2[t] = w8((b2 > 0 ? b2 : 0) - qe2); if (b2 > 0) d |= 0x40;
+			} else {
+				x[t]  = w8((a  >= 0 ? a  : 0) - qe);  if (a  >= 0) d |= 0x08;
+				y[t]  = w8((b  >= 0 ? b  : 0) - qe);  if (b  >= 0) d |= 0x10;
+				x2[t] = w8((a2 >= 0 ? a2 : 0) - qe2); if (a2 >= 0) d |= 0x20;
+				y2[t] = w8((b2 >= 0 ? b2 : 0) - qe2); if (b2 >= 0) d |= 0x40;
+			}
+			pr[t] = (uint8_t)d;
+		}
+		if (!approx_max) { /* exact max with a 32-bit score per position, :323-366 */
+			int32_t max_H, max_t;
+			if (r > 0) {
+				int en1 = st0 + (en0 - st0) / 4 * 4, i;
+				int32_t HH[4], tt[4];
+				max_H = H[en0] = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
+				max_t = en0;
+				for (i = 0; i < 4; ++i) HH[i] = max_H, tt[i] = max_t;
+				for (t = st0; t < en1; t += 4) /* four interleaved running maxima, first strict maximum wins per lane */
+					for (i = 0; i < 4; ++i) {
+						H[t + i] += v[t + i];
+						if (H[t + i] > HH[i]) HH[i] = H[t + i], tt[i] = t;
+					}
+				for (i = 0; i < 4; ++i)
+					if (max_H < HH[i]) max_H = HH[i], max_t = tt[i] + i;
+				for (; t < en0; ++t) {
+					H[t] += v[t];
+					if (H[t] > max_H) max_H = H[t], max_t = t;
+				}
+			} else H[0] = v[0] - qe, max_H = H[0], max_t = 0;
+			if (en0 == tlen - 1 && H[en0] > ez->mte) ez->mte = H[en0], ez->mte_q = r - en0;
+			if (r - st0 == qlen - 1 && H[st0] > ez->mqe) ez->mqe = H[st0], ez->mqe_t = st0;
+			/* ksw_apply_zdrop, C/ksw2.h:168-184, with e2 */
+			if (max_H > ez->max) ez->max = max_H, ez->max_t = max_t, ez->max_q = r - max_t;
+			else if (max_t >= ez->max_t && r - max_t >= ez->max_q) {
+				int tl = max_t - ez->max_t, ql = (r - max_t) - ez->max_q, l = tl > ql ? tl - ql : ql - tl;
+				if (zdrop >= 0 && ez->max - max_H > zdrop + l * e2) { ez->zdropped = 1; break; }
+			}
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H[tlen - 1];
+		} else { /* one tracked cell, :367-383 (KSW_EZ_APPROX_DROP is never set on pangraph's path) */
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					int d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += v[last_H0_t];
+				else ++last_H0_t, H0 += u[last_H0_t];
+			} else H0 = v[0] - qe, last_H0_t = 0;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+	/* traceback, C/ksw2.h:127-159 and C/ksw2_extd2_sse.c:388-399 */
+	{
+		int i = -1, j = -1, n = 0, state = 0, go = 1;
+		if (!ez->zdropped && !(flag & ORC_EZ_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
+		else if (!ez->zdropped && (flag & ORC_EZ_EXTZ_ONLY) && ez->mqe + end_bonus > ez->max) ez->reach_end = 1, i = ez->mqe_t, j = qlen - 1;
+		else if (ez->max_t >= 0 && ez->max_q >= 0) i = ez->max_t, j = ez->max_q;
+		else go = 0;
+		if (go) {
+			while (i >= 0 && j >= 0) {
+				int force = -1, tmp;
+				r = i + j;
+				if (i < off[r]) force = 2;
+				if (i > off_end[r]) force = 1;
+				tmp = force < 0 ? p[(size_t)r * stride + i - off[r]] : 0;
+				if (state == 0) state = tmp & 7;
+				else if (!(tmp >> (state + 2) & 1)) state = 0;
+				if (state == 0) state = tmp & 7;
+				if (force >= 0) state = force;
+				if (state == 0) orc_push(cigar, &n, 0, 1), --i, --j;
+				else if (state == 1 || state == 3) orc_push(cigar, &n, 2, 1), --i;
+				else orc_push(cigar, &n, 1, 1), --j;
+			}
+			if (i >= 0) orc_push(cigar, &n, 2, i + 1);
+			if (j >= 0) orc_push(cigar, &n, 1, j + 1);
+			if (!(flag & ORC_EZ_REV_CIGAR))
+				for (i = 0; i < n >> 1; ++i) { uint32_t c = cigar[i]; cigar[i] = cigar[n - 1 - i]; cigar[n - 1 - i] = c; }
+			ez->n_cigar = n;
+		}
+	}
+	free(u); free(H); free(p); free(off);
+	return 0;
+}
