@@ -1,0 +1,279 @@
+/* pgmm_b200.h -- C-ABI of libpgmm_b200.so, the B200-native replacement for pangraph's alignment hot path.
+ *
+ * Part 1 is the boundary the reference's FFI crate binds today: packages/minimap2-sys/minimap2.h (bindgen over
+ * minimap2/minimap.h + mmpriv.h) -- the ten symbols and five struct layouts that packages/minimap2 (the safe Rust
+ * wrapper) actually touches.  A build of pangraph that links this library instead of the vendored C sees the same
+ * names, argument meaning, ownership rules and struct offsets (verified by tests/test_abi.py with offsetof()).
+ * Part 2 adds the batched entry point a GPU needs, and the host half of the path (find_matches -> split -> filter).
+ * Part 3 are stage-level entry points used by the parity tests and by bench.py.
+ *
+ * All entry points are plain C: pointers and sizes only.  CUDA failures abort() with a message, like the reference's
+ * C, which has no error channel either.  There is no CPU fallback behind any of them.
+ */
+#ifndef PGMM_B200_H
+#define PGMM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PGMM_API __attribute__((visibility("default")))
+#else
+#define PGMM_API
+#endif
+
+/* ===================== Part 1: the minimap2-sys boundary ===================== */
+
+/* mapping flags used on pangraph's path -- reference: minimap2/minimap.h:10-47 */
+#define MM_F_NO_DIAG    (0x001LL)
+#define MM_F_NO_DUAL    (0x002LL)
+#define MM_F_CIGAR      (0x004LL)
+#define MM_F_OUT_SAM    (0x008LL)
+#define MM_F_NO_QUAL    (0x010LL)
+#define MM_F_OUT_CG     (0x020LL)
+#define MM_F_OUT_CS     (0x040LL)
+#define MM_F_SPLICE     (0x080LL)
+#define MM_F_SPLICE_FOR (0x100LL)
+#define MM_F_SPLICE_REV (0x200LL)
+#define MM_F_NO_LJOIN   (0x400LL)
+#define MM_F_OUT_CS_LONG (0x800LL)
+#define MM_F_SR         (0x1000LL)
+#define MM_F_FRAG_MODE  (0x2000LL)
+#define MM_F_NO_PRINT_2ND (0x4000LL)
+#define MM_F_2_IO_THREADS (0x8000LL)
+#define MM_F_LONG_CIGAR (0x10000LL)
+#define MM_F_INDEPEND_SEG (0x20000LL)
+#define MM_F_SPLICE_FLANK (0x40000LL)
+#define MM_F_SOFTCLIP   (0x80000LL)
+#define MM_F_FOR_ONLY   (0x100000LL)
+#define MM_F_REV_ONLY   (0x200000LL)
+#define MM_F_HEAP_SORT  (0x400000LL)
+#define MM_F_ALL_CHAINS (0x800000LL)
+#define MM_F_OUT_MD     (0x1000000LL)
+#define MM_F_COPY_COMMENT (0x2000000LL)
+#define MM_F_EQX        (0x4000000LL)
+#define MM_F_PAF_NO_HIT (0x8000000LL)
+#define MM_F_NO_END_FLT (0x10000000LL)
+#define MM_F_HARD_MLEVEL (0x20000000LL)
+#define MM_F_SAM_HIT_ONLY (0x40000000LL)
+#define MM_F_RMQ        (0x80000000LL)
+#define MM_F_QSTRAND    (0x100000000LL)
+#define MM_F_NO_INV     (0x200000000LL)
+#define MM_F_NO_HASH_NAME (0x400000000LL)
+#define MM_F_SPLICE_OLD (0x800000000LL)
+#define MM_F_SECONDARY_SEQ (0x1000000000LL)
+
+#define MM_I_HPC     0x1
+#define MM_I_NO_SEQ  0x2
+#define MM_I_NO_NAME 0x4
+
+#define MM_CIGAR_MATCH 0
+#define MM_CIGAR_INS   1
+#define MM_CIGAR_DEL   2
+#define MM_CIGAR_STR   "MIDNSHP=XB"
+
+/* reference: minimap.h:75-80 (24 bytes) */
+typedef struct {
+	char *name;
+	uint64_t offset;
+	uint32_t len;
+	uint32_t is_alt;
+} mm_idx_seq_t;
+
+/* reference: minimap.h:82-92 (80 bytes).  The caller reads b,w,k,flag,n_seq and seq[] directly
+ * (packages/minimap2/src/map.rs:278-291); S/B/I/km/h are private to the implementation -- here `h` points at the
+ * device-resident index object and the others stay NULL. */
+typedef struct {
+	int32_t b, w, k, flag;
+	uint32_t n_seq;
+	int32_t index;
+	int32_t n_alt;
+	mm_idx_seq_t *seq;
+	uint32_t *S;
+	struct mm_idx_bucket_s *B;
+	struct mm_idx_intv_s *I;
+	void *km, *h;
+} mm_idx_t;
+
+/* reference: minimap.h:95-101 (24 bytes + flexible array); cigar[i] = len<<4 | op */
+typedef struct {
+	uint32_t capacity;
+	int32_t dp_score, dp_max, dp_max2;
+	uint32_t n_ambi:30, trans_strand:2;
+	uint32_t n_cigar;
+	uint32_t cigar[];
+} mm_extra_t;
+
+/* reference: minimap.h:103-117 (80 bytes) */
+typedef struct {
+	int32_t id;
+	int32_t cnt;
+	int32_t rid;
+	int32_t score;
+	int32_t qs, qe, rs, re;
+	int32_t parent, subsc;
+	int32_t as;
+	int32_t mlen, blen;
+	int32_t n_sub;
+	int32_t score0;
+	uint32_t mapq:8, split:2, rev:1, inv:1, sam_pri:1, proper_frag:1, pe_thru:1, seg_split:1, seg_id:8, split_inv:1, is_alt:1, strand_retained:1, dummy:5;
+	uint32_t hash;
+	float div;
+	mm_extra_t *p;
+} mm_reg1_t;
+
+/* reference: minimap.h:119-123 (24 bytes) */
+typedef struct {
+	short k, w, flag, bucket_bits;
+	int64_t mini_batch_size;
+	uint64_t batch_size;
+} mm_idxopt_t;
+
+/* reference: minimap.h:125-181 (248 bytes); the Rust wrapper writes fields in place
+ * (packages/minimap2/src/options_args.rs:273-551) */
+typedef struct {
+	int64_t flag;
+	int seed;
+	int sdust_thres;
+	int max_qlen;
+	int bw, bw_long;
+	int max_gap, max_gap_ref;
+	int max_frag_len;
+	int max_chain_skip, max_chain_iter;
+	int min_cnt;
+	int min_chain_score;
+	float chain_gap_scale;
+	float chain_skip_scale;
+	int rmq_size_cap, rmq_inner_dist;
+	int rmq_rescue_size;
+	float rmq_rescue_ratio;
+	float mask_level;
+	int mask_len;
+	float pri_ratio;
+	int best_n;
+	float alt_drop;
+	int a, b, q, e, q2, e2;
+	int sc_ambi;
+	int noncan;
+	int junc_bonus;
+	int zdrop, zdrop_inv;
+	int end_bonus;
+	int min_dp_max;
+	int min_ksw_len;
+	int anchor_ext_len, anchor_ext_shift;
+	float max_clip_ratio;
+	int rank_min_len;
+	float rank_frac;
+	int pe_ori, pe_bonus;
+	float mid_occ_frac;
+	float q_occ_frac;
+	int32_t min_mid_occ, max_mid_occ;
+	int32_t mid_occ;
+	int32_t max_occ, max_max_occ, occ_dist;
+	int64_t mini_batch_size;
+	int64_t max_sw_mat;
+	int64_t cap_kalloc;
+	const char *split_prefix;
+} mm_mapopt_t;
+
+/* reference: minimap.h:196-199; opaque to the caller (packages/minimap2/src/buf.rs) */
+typedef struct mm_tbuf_s mm_tbuf_t;
+
+/* replaces options.c:88-162.  preset==NULL initialises both structs to the defaults; returns 0, or -1 for an unknown
+ * preset (packages/minimap2/src/options.rs:89-112 turns non-zero into an error) */
+PGMM_API int mm_set_opt(const char *preset, mm_idxopt_t *io, mm_mapopt_t *mo);
+/* replaces options.c:164-234; 0 when valid, the same negative codes otherwise (options.rs:123) */
+PGMM_API int mm_check_opt(const mm_idxopt_t *io, const mm_mapopt_t *mo);
+/* replace options.c:5-12 and :14-64 (used by the Default impls, minimap2-sys/src/lib.rs:13-31) */
+PGMM_API void mm_idxopt_init(mm_idxopt_t *opt);
+PGMM_API void mm_mapopt_init(mm_mapopt_t *opt);
+/* replaces index.c:408-456: builds the minimizer index of n in-memory sequences ON THE GPU.  Copies names and
+ * sequences (the caller frees its strings right after, packages/minimap2/src/index.rs:40-52).  NULL when n<=0. */
+PGMM_API mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const char **seq, const char **name);
+/* replaces options.c:66-80: computes mid_occ from the index (index.rs:47) */
+PGMM_API void mm_mapopt_update(mm_mapopt_t *opt, const mm_idx_t *mi);
+/* replaces index.c:56-79 (index.rs:71-77) */
+PGMM_API void mm_idx_destroy(mm_idx_t *mi);
+/* replace map.c:13-26 (buf.rs:17,36).  One per concurrent mm_map call. */
+PGMM_API mm_tbuf_t *mm_tbuf_init(void);
+PGMM_API void mm_tbuf_destroy(mm_tbuf_t *b);
+/* replaces map.c:376-381 (packages/minimap2/src/map.rs:390).  Returns a malloc() array of *n_regs hits, each with a
+ * separately malloc()ed ->p; the caller frees every ->p and then the array with free() (minimap.h:353-366,
+ * map.rs:407-421).  Re-entrant for distinct tbufs. */
+PGMM_API mm_reg1_t *mm_map(const mm_idx_t *mi, int l_seq, const char *seq, int *n_regs, mm_tbuf_t *b, const mm_mapopt_t *opt, const char *name);
+/* replaces align.c:911-917 (map.rs:323) */
+PGMM_API double mm_event_identity(const mm_reg1_t *r);
+
+/* ===================== Part 2: batched mapping and the host half of the path ===================== */
+
+/* All queries of one find_matches round at once (what mm_map does per query, packages/pangraph/src/align/
+ * minimap2_lib/align_with_minimap2_lib.rs:64-74, done for the whole batch so the GPU sees every DP problem of the
+ * round together).  n_regs[i]/regs[i] follow mm_map's ownership rules; results are independent of batch composition. */
+PGMM_API void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *const *seqs, const char *const *names,
+                             const mm_mapopt_t *opt, int *n_regs, mm_reg1_t **regs);
+
+/* One alignment record, the C image of pangraph's `Alignment` (packages/pangraph/src/align/alignment.rs:13-59).
+ * Block names are the decimal BlockId values; cigar is malloc()ed (len<<4|op) and owned by the caller. */
+typedef struct {
+	uint64_t qry_name, ref_name;
+	uint64_t qry_len, ref_len;
+	uint64_t qry_start, qry_end, ref_start, ref_end;
+	uint64_t matches, length, quality;
+	int32_t reverse;      /* Strand::Reverse */
+	int32_t has_divergence;
+	double divergence;    /* PAF de */
+	double align;         /* PAF AS */
+	uint32_t n_cigar;
+	uint32_t *cigar;
+} pgmm_alignment_t;
+
+/* AlignmentArgs of the reference (packages/pangraph/src/align/alignment_args.rs:6-37) */
+typedef struct {
+	uint64_t indel_len_threshold; /* -l, default 100 */
+	double alpha;                 /* -a, default 100 */
+	double beta;                  /* -b, default 10 */
+	uint64_t sensitivity;         /* -s, 5|10|20 */
+	int64_t kmer_length;          /* -K, <=0: preset default */
+} pgmm_alignment_args_t;
+
+PGMM_API void pgmm_alignment_args_default(pgmm_alignment_args_t *args);
+
+/* align_with_minimap2_lib (align_with_minimap2_lib.rs:15-121): block ids + consensus sequences -> Alignment list in
+ * query-index order.  Returns 0, or a negative code (-1 unknown sensitivity, -2 size mismatch / bad input).
+ * *out is one malloc() array of *n_out records; free with pgmm_alignments_free. */
+PGMM_API int pgmm_align_with_minimap2_lib(int n_blocks, const uint64_t *block_ids, const char *const *consensus,
+                                          const pgmm_alignment_args_t *args, pgmm_alignment_t **out, size_t *n_out);
+/* split_matches (packages/pangraph/src/pangraph/split_matches.rs:13-24) on one record */
+PGMM_API int pgmm_split_matches(const pgmm_alignment_t *aln, const pgmm_alignment_args_t *args, pgmm_alignment_t **out, size_t *n_out);
+/* alignment_energy2 (packages/pangraph/src/align/energy.rs:37-54) */
+PGMM_API double pgmm_alignment_energy2(const pgmm_alignment_t *aln, const pgmm_alignment_args_t *args);
+/* filter_matches (packages/pangraph/src/pangraph/graph_merging.rs:187-216) */
+PGMM_API int pgmm_filter_matches(const pgmm_alignment_t *alns, size_t n, const pgmm_alignment_args_t *args, pgmm_alignment_t **out, size_t *n_out);
+/* the alignment half of self_merge (graph_merging.rs:95-121): find_matches, drop self hits, split, filter */
+PGMM_API int pgmm_find_filtered_matches(int n_blocks, const uint64_t *block_ids, const char *const *consensus,
+                                        const pgmm_alignment_args_t *args, pgmm_alignment_t **out, size_t *n_out);
+PGMM_API void pgmm_alignments_free(pgmm_alignment_t *alns, size_t n);
+
+/* ===================== Part 3: stage-level entry points (tests, bench) ===================== */
+
+PGMM_API int pgmm_device_count(void);
+
+/* K5 alone: n DP problems over windows of two host code buffers (bases coded 0..4).  flag = KSW_EZ_* of the
+ * reference (ksw2.h:8-14) | 0x10000 to read both windows back to front.  out_ez: 11 int32 per problem
+ * (max,zdropped,max_q,max_t,mqe,mqe_t,mte,mte_q,score,reach_end,n_cigar); problem i's CIGAR is
+ * out_cigar[out_cig_start[i] .. +n_cigar).  Returns 0, -1 if cigar_cap is too small. */
+PGMM_API int pgmm_ksw_extd2_batch(int n, const int32_t *qlen, const int32_t *tlen, const uint64_t *q_off,
+                                  const uint64_t *t_off, const uint8_t *qcodes, uint64_t q_total,
+                                  const uint8_t *tcodes, uint64_t t_total, const int32_t *w, const int32_t *zdrop,
+                                  const int32_t *end_bonus, const int32_t *flag, int a, int b, int sc_ambi, int q,
+                                  int e, int q2, int e2, int32_t *out_ez, uint32_t *out_cigar, uint64_t cigar_cap,
+                                  uint64_t *out_cig_start, double *out_kernel_ms, uint64_t arena_budget_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,550 @@
+// K5: ksw_extd2 on the GPU -- dual-affine banded DP (Suzuki-Kasahara difference recurrence, int8) with traceback.
+//
+// Behavioural contract: bit-identical ksw_extz_t and CIGAR to the reference's ksw_extd2_sse
+// (packages/minimap2-sys/minimap2/ksw2_extd2_sse.c:34-401, ksw2.h:127-184) for the four flag combinations that occur
+// on pangraph's path (align.c:714,755,759,798).  That includes the reference's 16-lane artefacts: on every
+// anti-diagonal the padded range [st,en] is evaluated, padded cells read whatever substitution score was last written
+// for their target position, and band edges / traceback see those cells.
+//
+// Mapping: one CTA per DP problem.  All per-target-position state (u,y,y2,s in place; v,x,x2 ping-ponged between
+// anti-diagonals so that a single barrier separates them) lives in shared memory -- or in a global scratch slab when a
+// problem is too long -- as packed int8x4 words; a thread advances one word (4 cells) per step with the byte-wise SIMD
+// integer instructions.  The traceback matrix streams to HBM with 32-bit stores (one row per anti-diagonal); the
+// traceback walk runs on thread 0 after the wavefront.  No tensor cores: this is integer add/compare/select work.
+#include "ksw_extd2.h"
+#include "pgmm_cuda.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace pgmm {
+
+namespace {
+
+constexpr int kMiscWords = 96;  // per-CTA scratch: warp partial keys (64 words) + scalars
+
+__host__ __device__ inline int round16_up(int x) { return (x + 15) / 16 * 16; }
+
+struct Geom {
+  int T, Qp, n_col16, n_row;
+  size_t state_bytes, p_bytes;
+};
+
+__host__ __device__ inline Geom make_geom(int qlen, int tlen, int w, int flag) {
+  Geom g;
+  if (w < 0) w = tlen > qlen ? tlen : qlen;
+  g.T = round16_up(tlen);
+  g.Qp = (qlen + 3) / 4 * 4 + 24;  // 4 leading + >=16 trailing zero bytes around the reversed query
+  int n_col = qlen < tlen ? qlen : tlen;
+  n_col = ((n_col < w + 1 ? n_col : w + 1) + 15) / 16 + 1;  // ksw2_extd2_sse.c:89-91
+  g.n_col16 = n_col * 16;
+  g.n_row = qlen + tlen - 1;
+  g.p_bytes = (size_t)g.n_row * g.n_col16;
+  g.state_bytes = (size_t)g.T * 11 + ((flag & KSW_APPROX_MAX) ? 0 : (size_t)g.T * 4) + g.Qp;
+  return g;
+}
+
+__device__ __forceinline__ uint32_t rep4(int v) { return (uint32_t)(uint8_t)v * 0x01010101u; }
+__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
+// 0xff in byte k iff lo <= t0+k <= hi
+__device__ __forceinline__ uint32_t range_mask(int t0, int lo, int hi) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (t0 + k >= lo && t0 + k <= hi) m |= 0xffu << (8 * k);
+  return m;
+}
+__device__ __forceinline__ int8_t byte_of(uint32_t w, int k) { return (int8_t)(w >> (8 * k)); }
+__device__ __forceinline__ uint32_t set_byte(uint32_t w, int k, int v) {
+  return (w & ~(0xffu << (8 * k))) | ((uint32_t)(uint8_t)v << (8 * k));
+}
+
+// band of anti-diagonal r (ksw2_extd2_sse.c:137-147); returns false when the band is empty
+__device__ __forceinline__ bool band(int r, int qlen, int tlen, int w, int &st0, int &en0) {
+  int st = 0, en = tlen - 1;
+  if (st < r - qlen + 1) st = r - qlen + 1;
+  if (en > r) en = r;
+  if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+  if (en > (r + w) >> 1) en = (r + w) >> 1;
+  st0 = st, en0 = en;
+  return st <= en;
+}
+
+struct EzState {
+  int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end;
+};
+
+template <int NT>
+__device__ __forceinline__ void cta_bar() {
+  if (NT == 32) __syncwarp();
+  else __syncthreads();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
+                                                       const uint8_t *__restrict__ qcodes,
+                                                       const uint8_t *__restrict__ tcodes, KswScoring sc,
+                                                       uint8_t *__restrict__ p_arena, uint32_t *__restrict__ cig_arena,
+                                                       uint8_t *__restrict__ scratch, KswOut *__restrict__ outs) {
+  extern __shared__ uint32_t dyn_smem[];
+  __shared__ __align__(16) uint32_t misc[kMiscWords];
+  const int tid = threadIdx.x;
+  const int jid = job_ids[blockIdx.x];
+  const KswJob job = jobs[jid];
+  const int qlen = job.qlen, tlen = job.tlen, flag = job.flag;
+  int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
+  if (q2 + e2 < q + e) {  // ksw2_extd2_sse.c:73
+    int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t;
+  }
+  const int w = job.w < 0 ? (tlen > qlen ? tlen : qlen) : job.w;
+  const bool approx = flag & KSW_APPROX_MAX, right = flag & KSW_RIGHT;
+  const Geom g = make_geom(qlen, tlen, w, flag);
+  const int T = g.T;
+
+  // ---- carve the per-problem state ----
+  uint8_t *base = job.scr_off == ~0ull ? (uint8_t *)dyn_smem : scratch + job.scr_off;
+  uint32_t *U32 = (uint32_t *)base, *Y32 = U32 + T / 4, *Y232 = Y32 + T / 4, *S32 = Y232 + T / 4;
+  // v, x, x2 are read at t-1 by the neighbouring cell: two copies, swapped every anti-diagonal
+  uint32_t *Vc32 = S32 + T / 4, *Vn32 = S32 + 2 * (T / 4);
+  uint32_t *Xc32 = S32 + 3 * (T / 4), *Xn32 = S32 + 4 * (T / 4);
+  uint32_t *X2c32 = S32 + 5 * (T / 4), *X2n32 = S32 + 6 * (T / 4);
+  uint32_t *TQ32 = S32 + 7 * (T / 4);
+  uint32_t *QR32 = TQ32 + T / 4;
+  int32_t *H = (int32_t *)(QR32 + g.Qp / 4);
+  int8_t *U8 = (int8_t *)U32;
+
+  const uint32_t NQE = rep4(-q - e), NQE2 = rep4(-q2 - e2);
+  for (int i = tid; i < T / 4; i += NT) {
+    U32[i] = NQE, Y32[i] = NQE, Y232[i] = NQE2, S32[i] = 0;
+    Vc32[i] = Vn32[i] = NQE;
+    Xc32[i] = Xn32[i] = NQE;
+    X2c32[i] = X2n32[i] = NQE2;
+    TQ32[i] = 0;
+    if (!approx) H[4 * i] = H[4 * i + 1] = H[4 * i + 2] = H[4 * i + 3] = KSW_NEG_INF;
+  }
+  for (int i = tid; i < g.Qp / 4; i += NT) QR32[i] = 0;
+  cta_bar<NT>();
+  {
+    const bool rev = flag & KSW_JOB_REVSEQ;
+    const uint8_t *tb = tcodes + job.t_off, *qb = qcodes + job.q_off;
+    uint8_t *TQ8 = (uint8_t *)TQ32, *QR8 = (uint8_t *)QR32 + 4;
+    for (int i = tid; i < tlen; i += NT) TQ8[i] = rev ? tb[tlen - 1 - i] : tb[i];
+    for (int i = tid; i < qlen; i += NT) QR8[i] = rev ? qb[i] : qb[qlen - 1 - i];  // qr[i] = query[qlen-1-i]
+  }
+  cta_bar<NT>();
+
+  const int long_thres0 = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;  // :99-102
+  const int long_thres = (q2 + e2 + long_thres0 * e2 > q + e + long_thres0 * e) ? long_thres0 + 1 : long_thres0;
+  const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+  const uint32_t MCH = rep4(sc.sc_mch), MIS = rep4(sc.sc_mis);
+  const uint32_t SCN = rep4(sc.sc_ambi == 0 ? -e2 : -(sc.sc_ambi < 0 ? -sc.sc_ambi : sc.sc_ambi));
+  const uint32_t Q4 = rep4(q), Q24 = rep4(q2), QE4 = rep4(q + e), QE24 = rep4(q2 + e2), N4 = rep4(4);
+  const int qe = q + e;
+  uint8_t *P = p_arena + job.p_off;
+  const int stride = g.n_col16, n_row = g.n_row;
+
+  EzState ez;
+  ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+  ez.max = 0, ez.score = ez.mqe = ez.mte = KSW_NEG_INF;
+  ez.zdropped = 0, ez.reach_end = 0;
+  int32_t H0 = 0, last_H0_t = 0;  // thread 0 only
+  int last_st = -1, last_en = -1;
+  long long *wpart = (long long *)misc;     // [NT/32] warp partial keys
+  int32_t *hsave = (int32_t *)&misc[64];    // H[en0-1] of the previous anti-diagonal
+  volatile int32_t *stop = (int32_t *)&misc[65];
+  if (tid == 0) *stop = 0;
+
+  for (int r = 0; r < n_row; ++r) {
+    int st0, en0;
+    if (!band(r, qlen, tlen, w, st0, en0)) {  // :142-145
+      ez.zdropped = 1;
+      break;
+    }
+    const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+    const int8_t *Xc8 = (const int8_t *)Xc32, *Vc8 = (const int8_t *)Vc32, *X2c8 = (const int8_t *)X2c32;
+    // stand-ins for position st-1 of the previous anti-diagonal, :149-159
+    const int ufirst = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+    int x1, x21, v1;
+    if (st > 0) {
+      if (st - 1 >= last_st && st - 1 <= last_en) x1 = Xc8[st - 1], x21 = X2c8[st - 1], v1 = Vc8[st - 1];
+      else x1 = -q - e, x21 = -q2 - e2, v1 = -q - e;
+    } else x1 = -q - e, x21 = -q2 - e2, v1 = ufirst;
+    // substitution scores are (re)written for [st0, s_hi] in runs of 16 from st0, :165-180
+    const int s_hi = min(st0 + ((en0 - st0) / 16 + 1) * 16 - 1, T - 1);
+    const int whi = max(en, s_hi) >> 2;
+    const int en1 = st0 + (en0 - st0) / 4 * 4, NB = (en1 - st0) >> 2;
+    long long best = LLONG_MIN;
+    uint8_t *prow = P + (size_t)r * stride;
+
+    for (int wi = (st >> 2) + tid; wi <= whi; wi += NT) {
+      const int t0 = wi << 2;
+      uint32_t S = S32[wi];
+      if (t0 + 3 >= st0 && t0 <= s_hi) {
+        const uint32_t tw = TQ32[wi];
+        const int i = qlen - 1 - r + t0 + 4;  // byte index into QR8-4 (>= 1 because t0 >= st0-3)
+        const uint32_t lo = QR32[i >> 2], hi = QR32[(i >> 2) + 1];
+        const uint32_t qw = __funnelshift_r(lo, hi, (i & 3) * 8);
+        const uint32_t eq = __vcmpeq4(tw, qw), nm = __vcmpeq4(tw, N4) | __vcmpeq4(qw, N4);
+        const uint32_t scw = sel4(nm, SCN, sel4(eq, MCH, MIS));
+        S = sel4(range_mask(t0, st0, s_hi), scw, S);
+        S32[wi] = S;
+      }
+      if (t0 > en) continue;
+      uint32_t Uo = U32[wi], Yo = Y32[wi], Y2o = Y232[wi];
+      const uint32_t Vc = Vc32[wi], Xc = Xc32[wi], X2c = X2c32[wi];
+      int xl, vl, x2l;
+      if (t0 == st) xl = x1, vl = v1, x2l = x21;
+      else xl = Xc8[t0 - 1], vl = Vc8[t0 - 1], x2l = X2c8[t0 - 1];
+      const uint32_t XT1 = (Xc << 8) | (uint8_t)xl, VT1 = (Vc << 8) | (uint8_t)vl, X2T1 = (X2c << 8) | (uint8_t)x2l;
+      if (en >= r && (r >> 2) == wi) {  // first row of the matrix, :160-163
+        const int k = r & 3;
+        Yo = set_byte(Yo, k, -q - e), Y2o = set_byte(Y2o, k, -q2 - e2), Uo = set_byte(Uo, k, ufirst);
+      }
+      uint32_t Z = S, A = __vadd4(XT1, VT1), B = __vadd4(Yo, Uo), A2 = __vadd4(X2T1, VT1), B2 = __vadd4(Y2o, Uo), D, m;
+      if (!right) {  // :228-275
+        m = __vcmpgts4(A, Z);  D = m & 0x01010101u;             Z = __vmaxs4(Z, A);
+        m = __vcmpgts4(B, Z);  D = sel4(m, 0x02020202u, D);      Z = __vmaxs4(Z, B);
+        m = __vcmpgts4(A2, Z); D = sel4(m, 0x03030303u, D);      Z = __vmaxs4(Z, A2);
+        m = __vcmpgts4(B2, Z); D = sel4(m, 0x04040404u, D);      Z = __vmaxs4(Z, B2);
+      } else {  // :276-322
+        m = __vcmpgts4(Z, A);  D = ~m & 0x01010101u;             Z = __vmaxs4(Z, A);
+        m = __vcmpgts4(Z, B);  D = sel4(m, D, 0x02020202u);      Z = __vmaxs4(Z, B);
+        m = __vcmpgts4(Z, A2); D = sel4(m, D, 0x03030303u);      Z = __vmaxs4(Z, A2);
+        m = __vcmpgts4(Z, B2); D = sel4(m, D, 0x04040404u);      Z = __vmaxs4(Z, B2);
+      }
+      Z = __vmins4(Z, MCH);
+      const uint32_t Un = __vsub4(Z, VT1), Vn = __vsub4(Z, Uo);
+      uint32_t tmp = __vsub4(Z, Q4);
+      A = __vsub4(A, tmp), B = __vsub4(B, tmp);
+      tmp = __vsub4(Z, Q24);
+      A2 = __vsub4(A2, tmp), B2 = __vsub4(B2, tmp);
+      uint32_t Xn, Yn, X2n, Y2n;
+      if (!right) {
+        m = __vcmpgts4(A, 0);  Xn = __vsub4(A & m, QE4);    D |= m & 0x08080808u;
+        m = __vcmpgts4(B, 0);  Yn = __vsub4(B & m, QE4);    D |= m & 0x10101010u;
+        m = __vcmpgts4(A2, 0); X2n = __vsub4(A2 & m, QE24); D |= m & 0x20202020u;
+        m = __vcmpgts4(B2, 0); Y2n = __vsub4(B2 & m, QE24); D |= m & 0x40404040u;
+      } else {
+        m = ~__vcmpgts4(0, A);  Xn = __vsub4(A & m, QE4);    D |= m & 0x08080808u;
+        m = ~__vcmpgts4(0, B);  Yn = __vsub4(B & m, QE4);    D |= m & 0x10101010u;
+        m = ~__vcmpgts4(0, A2); X2n = __vsub4(A2 & m, QE24); D |= m & 0x20202020u;
+        m = ~__vcmpgts4(0, B2); Y2n = __vsub4(B2 & m, QE24); D |= m & 0x40404040u;
+      }
+      U32[wi] = Un, Y32[wi] = Yn, Y232[wi] = Y2n;
+      Vn32[wi] = Vn, Xn32[wi] = Xn, X2n32[wi] = X2n;
+      *(uint32_t *)(prow + (t0 - st)) = D;
+      if (!approx && r > 0) {  // H[t] += v[t] for st0 <= t < en0, :333-357
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int t = t0 + k;
+          if (t >= st0 && t < en0) {
+            int32_t h = H[t];
+            if (t == en0 - 1) *hsave = h;
+            h += byte_of(Vn, k);
+            H[t] = h;
+            // tie order of the reference: en0 first, then 4 interleaved lanes (first block wins inside a lane, lower
+            // lane wins across lanes), then the scalar tail in increasing t
+            const int d = t - st0;
+            const int rank = t < en1 ? 1 + (d & 3) * NB + (d >> 2) : 1 + 4 * NB + (t - en1);
+            const long long key = (long long)h * 4294967296LL + (long long)(0x7fffffff - rank);
+            best = best > key ? best : key;
+          }
+        }
+      }
+    }
+    if (!approx) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = best > other ? best : other;
+      }
+      if ((tid & 31) == 0) wpart[tid >> 5] = best;
+    }
+    cta_bar<NT>();
+    if (tid == 0) {
+      const int8_t *Vn8 = (const int8_t *)Vn32;
+      if (!approx) {  // :323-366
+        int32_t max_H, max_t;
+        if (r > 0) {
+          int32_t hen;
+          if (en0 > 0) hen = (en0 - 1 >= st0 ? *hsave : H[en0 - 1]) + U8[en0];
+          else hen = H[0] + Vn8[0];
+          H[en0] = hen;
+          max_H = hen, max_t = en0;
+          long long b = wpart[0];
+          for (int k = 1; k < NT / 32; ++k) b = b > wpart[k] ? b : wpart[k];
+          if (b != LLONG_MIN && (int32_t)(b >> 32) > max_H) {
+            const int rank = 0x7fffffff - (int)(uint32_t)b;
+            max_H = (int32_t)(b >> 32);
+            if (rank - 1 < 4 * NB) max_t = st0 + 4 * ((rank - 1) % NB) + (rank - 1) / NB;
+            else max_t = en1 + (rank - 1 - 4 * NB);
+          }
+        } else H[0] = Vn8[0] - qe, max_H = H[0], max_t = 0;
+        if (en0 == tlen - 1 && H[en0] > ez.mte) ez.mte = H[en0], ez.mte_q = r - en0;
+        if (r - st0 == qlen - 1 && H[st0] > ez.mqe) ez.mqe = H[st0], ez.mqe_t = st0;
+        bool brk = false;  // ksw_apply_zdrop with e2, ksw2.h:168-184
+        if (max_H > ez.max) ez.max = max_H, ez.max_t = max_t, ez.max_q = r - max_t;
+        else if (max_t >= ez.max_t && r - max_t >= ez.max_q) {
+          const int tl = max_t - ez.max_t, ql = (r - max_t) - ez.max_q, l = tl > ql ? tl - ql : ql - tl;
+          if (job.zdrop >= 0 && ez.max - max_H > job.zdrop + l * e2) ez.zdropped = 1, brk = true;
+        }
+        if (!brk && r == n_row - 1 && en0 == tlen - 1) ez.score = H[tlen - 1];
+        if (brk) *stop = 1;
+      } else {  // one tracked cell, :367-383
+        if (r > 0) {
+          const bool in0 = last_H0_t >= st0 && last_H0_t <= en0, in1 = last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0;
+          if (in0 && in1) {
+            const int d0 = Vn8[last_H0_t], d1 = U8[last_H0_t + 1];
+            if (d0 > d1) H0 += d0;
+            else H0 += d1, ++last_H0_t;
+          } else if (in0) H0 += Vn8[last_H0_t];
+          else {
+            ++last_H0_t;
+            H0 += last_H0_t < T ? U8[last_H0_t] : 0;
+          }
+        } else H0 = Vn8[0] - qe, last_H0_t = 0;
+        if (r == n_row - 1 && en0 == tlen - 1) ez.score = H0;
+      }
+    }
+    cta_bar<NT>();
+    if (*stop) break;
+    last_st = st, last_en = en;
+    uint32_t *sw;
+    sw = Vc32, Vc32 = Vn32, Vn32 = sw;
+    sw = Xc32, Xc32 = Xn32, Xn32 = sw;
+    sw = X2c32, X2c32 = X2n32, X2n32 = sw;
+  }
+
+  // ---- traceback on thread 0, ksw2.h:127-159 and ksw2_extd2_sse.c:388-399 ----
+  if (tid == 0) {
+    int i = -1, j = -1, n = 0, state = 0;
+    bool go = true;
+    if (!ez.zdropped && !(flag & KSW_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
+    else if (!ez.zdropped && (flag & KSW_EXTZ_ONLY) && ez.mqe + job.end_bonus > ez.max) ez.reach_end = 1, i = ez.mqe_t, j = qlen - 1;
+    else if (ez.max_t >= 0 && ez.max_q >= 0) i = ez.max_t, j = ez.max_q;
+    else go = false;
+    uint32_t *cig = cig_arena + job.cig_off;
+    if (go) {
+      uint32_t last = 0;  // run being built: len<<4|op, flushed when the op changes
+      while (i >= 0 && j >= 0) {
+        const int r = i + j;
+        int st0, en0;
+        band(r, qlen, tlen, w, st0, en0);
+        const int off = st0 / 16 * 16, off_end = (en0 + 16) / 16 * 16 - 1;
+        int force = -1;
+        if (i < off) force = 2;
+        if (i > off_end) force = 1;
+        const int tmp = force < 0 ? __ldcg(P + (size_t)r * stride + (i - off)) : 0;
+        if (state == 0) state = tmp & 7;
+        else if (!((tmp >> (state + 2)) & 1)) state = 0;
+        if (state == 0) state = tmp & 7;
+        if (force >= 0) state = force;
+        uint32_t op;
+        if (state == 0) op = 0, --i, --j;
+        else if (state == 1 || state == 3) op = 2, --i;
+        else op = 1, --j;
+        if (last != 0 && (last & 0xf) == op) last += 1u << 4;
+        else {
+          if (last != 0) cig[n++] = last;
+          last = 1u << 4 | op;
+        }
+      }
+      if (i >= 0) {  // leading deletion
+        if (last != 0 && (last & 0xf) == 2) last += (uint32_t)(i + 1) << 4;
+        else {
+          if (last != 0) cig[n++] = last;
+          last = (uint32_t)(i + 1) << 4 | 2;
+        }
+      }
+      if (j >= 0) {  // leading insertion
+        if (last != 0 && (last & 0xf) == 1) last += (uint32_t)(j + 1) << 4;
+        else {
+          if (last != 0) cig[n++] = last;
+          last = (uint32_t)(j + 1) << 4 | 1;
+        }
+      }
+      if (last != 0) cig[n++] = last;
+      if (!(flag & KSW_REV_CIGAR))
+        for (int k = 0; k < n >> 1; ++k) {
+          const uint32_t c = cig[k];
+          cig[k] = cig[n - 1 - k], cig[n - 1 - k] = c;
+        }
+    }
+    KswOut o;
+    o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t, o.mqe = ez.mqe, o.mqe_t = ez.mqe_t;
+    o.mte = ez.mte, o.mte_q = ez.mte_q, o.score = ez.score, o.reach_end = ez.reach_end, o.n_cigar = n;
+    outs[jid] = o;
+  }
+}
+
+// packs the per-job CIGAR scratch runs into one contiguous array (dst offsets precomputed on the host)
+__global__ void gather_cigars_kernel(const KswJob *__restrict__ jobs, const KswOut *__restrict__ outs,
+                                     const uint64_t *__restrict__ dst_off, const uint32_t *__restrict__ cig_arena,
+                                     uint32_t *__restrict__ dst, int njobs) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= njobs) return;
+  const uint32_t *src = cig_arena + jobs[warp].cig_off;
+  uint32_t *d = dst + dst_off[warp];
+  for (int i = lane; i < outs[warp].n_cigar; i += 32) d[i] = src[i];
+}
+
+constexpr size_t kSmemMax = 200 * 1024;
+
+template <int NT>
+void launch_class(const std::vector<int> &ids, size_t smem, const int *d_ids_base, size_t ids_off, const KswJob *d_jobs,
+                  const uint8_t *d_q, const uint8_t *d_t, const KswScoring &sc, uint8_t *p_arena, uint32_t *cig_arena,
+                  uint8_t *scratch, KswOut *d_outs, cudaStream_t stream) {
+  if (ids.empty()) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PGMM_CUDA(cudaFuncSetAttribute(ksw_extd2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    attr_set = true;
+  }
+  ksw_extd2_kernel<NT><<<(unsigned)ids.size(), NT, smem, stream>>>(d_jobs, d_ids_base + ids_off, d_q, d_t, sc, p_arena,
+                                                                   cig_arena, scratch, d_outs);
+  PGMM_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
+  Geom g = make_geom(qlen, tlen, w, flag);
+  KswGeom o;
+  o.T = g.T, o.n_col16 = g.n_col16, o.p_bytes = (int64_t)g.p_bytes, o.state_bytes = (int64_t)g.state_bytes;
+  return o;
+}
+
+struct KswEngine::Impl {
+  DevBuf<KswJob> d_jobs;
+  DevBuf<int> d_ids;
+  DevBuf<KswOut> d_outs;
+  DevBuf<uint8_t> p_arena, scratch;
+  DevBuf<uint32_t> cig_arena, cig_packed;
+  DevBuf<uint64_t> d_dst_off;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+KswEngine::KswEngine() : impl_(new Impl) {
+  PGMM_CUDA(cudaEventCreate(&impl_->ev0));
+  PGMM_CUDA(cudaEventCreate(&impl_->ev1));
+}
+KswEngine::~KswEngine() {
+  cudaEventDestroy(impl_->ev0);
+  cudaEventDestroy(impl_->ev1);
+  delete impl_;
+}
+
+void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t *d_t, const KswScoring &sc,
+                    KswBatchResult &res, cudaStream_t stream) {
+  const size_t n = jobs.size();
+  res.out.assign(n, KswOut{});
+  res.cig_start.assign(n + 1, 0);
+  res.cigar.clear();
+  res.cells = 0, res.launches = 0, res.kernel_ms = 0.f;
+  if (n == 0) return;
+  Impl &m = *impl_;
+
+  // order by traceback size, largest first, so that waves are filled greedily and long problems start early
+  std::vector<Geom> geo(n);
+  std::vector<int> order;
+  order.reserve(n);
+  for (size_t i = 0; i < n; ++i) {
+    KswJob &j = jobs[i];
+    if (j.qlen <= 0 || j.tlen <= 0) {  // ksw2_extd2_sse.c:71: reset only
+      KswOut &o = res.out[i];
+      o.max_q = o.max_t = o.mqe_t = o.mte_q = -1;
+      o.score = o.mqe = o.mte = KSW_NEG_INF;
+      continue;
+    }
+    geo[i] = make_geom(j.qlen, j.tlen, j.w, j.flag);
+    order.push_back((int)i);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return geo[a].p_bytes > geo[b].p_bytes; });
+
+  std::vector<uint64_t> packed_off(n + 1, 0);
+  size_t pos = 0;
+  while (pos < order.size()) {
+    // ---- carve one wave ----
+    size_t p_used = 0, cig_used = 0, scr_used = 0, end = pos;
+    while (end < order.size()) {
+      const int i = order[end];
+      const size_t pb = (geo[i].p_bytes + 255) / 256 * 256;
+      if (end > pos && p_used + pb > arena_budget_bytes) break;
+      jobs[i].p_off = p_used, p_used += pb;
+      jobs[i].cig_off = cig_used, cig_used += (size_t)jobs[i].qlen + jobs[i].tlen + 2;
+      if (geo[i].state_bytes > kSmemMax) jobs[i].scr_off = scr_used, scr_used += (geo[i].state_bytes + 255) / 256 * 256;
+      else jobs[i].scr_off = ~0ull;
+      ++end;
+    }
+    // ---- size classes (threads per CTA follow the width of the wavefront) ----
+    std::vector<int> cls[5];
+    size_t cls_smem[5] = {0, 0, 0, 0, 0};
+    for (size_t k = pos; k < end; ++k) {
+      const int i = order[k];
+      const size_t sb = geo[i].state_bytes;
+      int c;
+      if (sb > kSmemMax) c = 4;
+      else if (sb <= 6 * 1024) c = 0;
+      else if (sb <= 24 * 1024) c = 1;
+      else if (sb <= 64 * 1024) c = 2;
+      else c = 3;
+      cls[c].push_back(i);
+      if (c < 4) cls_smem[c] = std::max(cls_smem[c], sb);
+      res.cells += (uint64_t)std::min<int64_t>((int64_t)jobs[i].qlen * jobs[i].tlen,
+                                                (int64_t)geo[i].n_row * std::min(geo[i].n_col16, geo[i].T));
+    }
+    std::vector<int> ids;
+    size_t cls_off[5];
+    for (int c = 0; c < 5; ++c) cls_off[c] = ids.size(), ids.insert(ids.end(), cls[c].begin(), cls[c].end());
+
+    m.d_jobs.ensure(n), m.d_outs.ensure(n), m.d_ids.ensure(ids.size());
+    m.p_arena.ensure(p_used + 256), m.cig_arena.ensure(cig_used + 4), m.scratch.ensure(scr_used + 256);
+    PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, jobs.data(), n * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
+    PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    PGMM_CUDA(cudaEventRecord(m.ev0, stream));
+    launch_class<32>(cls[0], cls_smem[0], m.d_ids.p, cls_off[0], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
+    launch_class<64>(cls[1], cls_smem[1], m.d_ids.p, cls_off[1], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
+    launch_class<128>(cls[2], cls_smem[2], m.d_ids.p, cls_off[2], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
+    launch_class<256>(cls[3], cls_smem[3], m.d_ids.p, cls_off[3], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
+    launch_class<256>(cls[4], 0, m.d_ids.p, cls_off[4], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
+    PGMM_CUDA(cudaEventRecord(m.ev1, stream));
+    for (int c = 0; c < 5; ++c) res.launches += !cls[c].empty();
+
+    // ---- results of this wave: ez first, then the CIGARs packed on the device ----
+    std::vector<KswOut> outs(n);
+    PGMM_CUDA(cudaMemcpyAsync(outs.data(), m.d_outs.p, n * sizeof(KswOut), cudaMemcpyDeviceToHost, stream));
+    PGMM_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    PGMM_CUDA(cudaEventElapsedTime(&ms, m.ev0, m.ev1));
+    res.kernel_ms += ms;
+    std::vector<uint64_t> dst(n, 0);
+    uint64_t tot = 0;
+    for (size_t k = pos; k < end; ++k) {
+      const int i = order[k];
+      res.out[i] = outs[i];
+      dst[i] = tot, tot += outs[i].n_cigar;
+    }
+    if (tot > 0) {
+      m.d_dst_off.ensure(n), m.cig_packed.ensure(tot);
+      PGMM_CUDA(cudaMemcpyAsync(m.d_dst_off.p, dst.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+      // jobs outside this wave have stale outs on the device; give them n_cigar = 0 by gathering wave members only
+      std::vector<KswOut> masked(n, KswOut{});
+      for (size_t k = pos; k < end; ++k) masked[order[k]] = outs[order[k]];
+      PGMM_CUDA(cudaMemcpyAsync(m.d_outs.p, masked.data(), n * sizeof(KswOut), cudaMemcpyHostToDevice, stream));
+      const int tpb = 256, blocks = (int)((n * 32 + tpb - 1) / tpb);
+      gather_cigars_kernel<<<blocks, tpb, 0, stream>>>(m.d_jobs.p, m.d_outs.p, m.d_dst_off.p, m.cig_arena.p, m.cig_packed.p, (int)n);
+      PGMM_CUDA(cudaGetLastError());
+      const size_t base = res.cigar.size();
+      res.cigar.resize(base + tot);
+      PGMM_CUDA(cudaMemcpyAsync(res.cigar.data() + base, m.cig_packed.p, tot * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      PGMM_CUDA(cudaStreamSynchronize(stream));
+      for (size_t k = pos; k < end; ++k) packed_off[order[k]] = base + dst[order[k]];
+      ++res.launches;
+    }
+    pos = end;
+  }
+  for (size_t i = 0; i < n; ++i) res.cig_start[i] = packed_off[i];
+  res.cig_start[n] = res.cigar.size();
+}
+
+}  // namespace pgmm

@@ -1,0 +1,112 @@
+"""K5 (CUDA ksw_extd2) through the C-ABI against the reference's ksw_extd2_sse and the plain-C oracle."""
+import numpy as np
+import pytest
+
+import kswref
+from test_oracle_ksw import PRESETS, cases
+
+pytestmark = pytest.mark.gpu
+
+EZ = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end")
+
+
+def run_batch(problems, preset, rev=False, budget=0):
+    from pangraph_b200 import abi
+    a, b, gq, ge, gq2, ge2 = PRESETS[preset]
+    qs, ts, qo, to = [], [], [], []
+    qpos = tpos = 0
+    for q, t, *_ in problems:
+        qs.append(q[::-1] if rev else q), ts.append(t[::-1] if rev else t)
+        qo.append(qpos), to.append(tpos)
+        qpos += len(q) + 3
+        tpos += len(t) + 5
+    qbuf = np.full(qpos + 8, 7, dtype=np.uint8)
+    tbuf = np.full(tpos + 8, 7, dtype=np.uint8)
+    for (q, t, *_), o1, o2, qq, tt in zip(problems, qo, to, qs, ts):
+        qbuf[o1:o1 + len(q)] = qq
+        tbuf[o2:o2 + len(t)] = tt
+    flags = [p[3] | (0x10000 if rev else 0) for p in problems]
+    ez, cigs, ms = abi.ksw_extd2_batch([len(p[0]) for p in problems], [len(p[1]) for p in problems], qo, to, qbuf, tbuf,
+                                       [p[2] for p in problems], [p[4] for p in problems], [p[5] for p in problems], flags,
+                                       a, b, 1, gq, ge, gq2, ge2, arena_budget_bytes=budget)
+    return ez, cigs, ms
+
+
+def check(problems, preset, ref, rev=False, budget=0):
+    a, b, gq, ge, gq2, ge2 = PRESETS[preset]
+    mat = kswref.simple_mat(a, b, 1)
+    ez, cigs, _ = run_batch(problems, preset, rev, budget)
+    bad = []
+    for i, (q, t, w, flag, zdrop, end_bonus) in enumerate(problems):
+        want = kswref.ref_extd2(ref, q, t, mat, gq, ge, gq2, ge2, w, zdrop, end_bonus, flag)
+        got = {k: int(ez[i, j]) for j, k in enumerate(EZ)}
+        got["cigar"] = cigs[i]
+        if got != want:
+            bad.append((i, len(q), len(t), w, hex(flag), zdrop, end_bonus,
+                        {k: (got[k], want[k]) for k in want if got[k] != want[k] and k != "cigar"},
+                        got["cigar"][:6], want["cigar"][:6]))
+    assert not bad, f"{len(bad)} of {len(problems)} differ; first: {bad[:3]}"
+
+
+@pytest.mark.parametrize("preset", ["asm5", "asm10", "asm20"])
+def test_ksw_random_problems_match_reference(ref, preset):
+    probs = [(q, t, w, flag, zd, eb) for q, t, w, flag, p, zd, eb in cases(99, 900) if p == preset]
+    assert len(probs) > 200
+    check(probs, preset, ref)
+
+
+def test_ksw_reversed_windows(ref):
+    probs = [(q, t, w, flag, zd, eb) for q, t, w, flag, p, zd, eb in cases(5, 240) if p == "asm10"]
+    check(probs, "asm10", ref, rev=True)
+
+
+def test_ksw_long_banded_extensions(ref):
+    """The 4k-16k class: band 1501 (align.c:590), z-drop, extension-only, both gap alignments; several CTA sizes."""
+    rng = np.random.default_rng(7)
+    probs = []
+    for i in range(24):
+        ql, tl = int(rng.integers(1500, 7000)), int(rng.integers(1500, 7000))
+        q, t = kswref.random_pair(rng, ql, tl, div=float(rng.choice([0.01, 0.03, 0.2])), indel=0.005,
+                                  big_indel=int(rng.choice([0, 0, 400, 2500])))
+        flag = [kswref.FLAG_LEFT_EXT, kswref.FLAG_RIGHT_EXT, kswref.FLAG_FILL2, kswref.FLAG_FILL1][i % 4]
+        w = 1501 if flag != kswref.FLAG_FILL1 else 150001
+        probs.append((q, t, w, flag, 200, -1))
+    check(probs, "asm10", ref)
+
+
+def test_ksw_global_scratch_and_small_arena(ref):
+    """A target too long for shared memory takes the global-memory state path; a tiny arena forces several waves."""
+    rng = np.random.default_rng(11)
+    probs = []
+    q, t = kswref.random_pair(rng, 900, 21000, div=0.02, indel=0.002)
+    probs.append((q, t, 1501, kswref.FLAG_RIGHT_EXT, 200, -1))
+    q, t = kswref.random_pair(rng, 18000, 17500, div=0.02, indel=0.002)
+    probs.append((q, t, 1501, kswref.FLAG_FILL2, 200, -1))
+    for _ in range(40):
+        q, t = kswref.random_pair(rng, int(rng.integers(100, 400)), int(rng.integers(100, 400)), div=0.05)
+        probs.append((q, t, 150001, kswref.FLAG_FILL1, 200, -1))
+    check(probs, "asm10", ref, budget=8 << 20)
+
+
+def test_ksw_edge_cases(ref):
+    """Empty windows, 1x1, all-N, identical and unrelated sequences."""
+    rng = np.random.default_rng(3)
+    one = np.array([2], dtype=np.uint8)
+    probs = [(one, one, 1501, kswref.FLAG_RIGHT_EXT, 200, -1), (one, np.array([1], dtype=np.uint8), 150001, kswref.FLAG_FILL1, 200, -1)]
+    same = rng.integers(0, 4, size=333).astype(np.uint8)
+    probs.append((same, same.copy(), 150001, kswref.FLAG_FILL1, 200, -1))
+    probs.append((same, rng.integers(0, 4, size=200).astype(np.uint8), 1501, kswref.FLAG_FILL2, 200, -1))
+    probs.append((np.full(64, 4, dtype=np.uint8), np.full(80, 4, dtype=np.uint8), 1501, kswref.FLAG_LEFT_EXT, 200, -1))
+    probs.append((same[:16], same[:160], 3, kswref.FLAG_FILL2, 200, -1))
+    probs.append((same[:160], same[:16], 3, kswref.FLAG_RIGHT_EXT, 50, 5))
+    check(probs, "asm10", ref)
+    from pangraph_b200 import abi
+    ez, cigs, _ = abi.ksw_extd2_batch([0, 5], [7, 0], [0, 0], [0, 0], same, same, [10, 10], [200, 200], [-1, -1], [0, 0],
+                                      1, 9, 1, 16, 2, 41, 1)
+    for i in range(2):  # ksw_reset_extz only (ksw2_extd2_sse.c:70-71)
+        assert list(ez[i]) == [0, 0, -1, -1, kswref_neg(), -1, kswref_neg(), -1, kswref_neg(), 0, 0]
+        assert cigs[i] == ()
+
+
+def kswref_neg():
+    return -0x40000000
