@@ -76,27 +76,31 @@ _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
 
 
-def bind(lib):
-    """Attach prototypes of the ten boundary symbols to a loaded library."""
-    lib.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(mm_idxopt_t), C.POINTER(mm_mapopt_t)]
-    lib.mm_set_opt.restype = C.c_int
-    lib.mm_check_opt.argtypes = [C.POINTER(mm_idxopt_t), C.POINTER(mm_mapopt_t)]
-    lib.mm_check_opt.restype = C.c_int
-    lib.mm_idx_str.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p),
-                               C.POINTER(C.c_char_p)]
-    lib.mm_idx_str.restype = C.POINTER(mm_idx_t)
-    lib.mm_mapopt_update.argtypes = [C.POINTER(mm_mapopt_t), C.POINTER(mm_idx_t)]
-    lib.mm_mapopt_update.restype = None
-    lib.mm_idx_destroy.argtypes = [C.POINTER(mm_idx_t)]
-    lib.mm_idx_destroy.restype = None
-    lib.mm_tbuf_init.restype = C.c_void_p
-    lib.mm_tbuf_destroy.argtypes = [C.c_void_p]
-    lib.mm_tbuf_destroy.restype = None
-    lib.mm_map.argtypes = [C.POINTER(mm_idx_t), C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_void_p,
-                           C.POINTER(mm_mapopt_t), C.c_char_p]
-    lib.mm_map.restype = C.POINTER(mm_reg1_t)
-    lib.mm_event_identity.argtypes = [C.POINTER(mm_reg1_t)]
-    lib.mm_event_identity.restype = C.c_double
+_PROTOS = {
+    "mm_set_opt": ([C.c_char_p, C.POINTER(mm_idxopt_t), C.POINTER(mm_mapopt_t)], C.c_int),
+    "mm_check_opt": ([C.POINTER(mm_idxopt_t), C.POINTER(mm_mapopt_t)], C.c_int),
+    "mm_idxopt_init": ([C.POINTER(mm_idxopt_t)], None),
+    "mm_mapopt_init": ([C.POINTER(mm_mapopt_t)], None),
+    "mm_idx_str": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)],
+                   C.POINTER(mm_idx_t)),
+    "mm_mapopt_update": ([C.POINTER(mm_mapopt_t), C.POINTER(mm_idx_t)], None),
+    "mm_idx_destroy": ([C.POINTER(mm_idx_t)], None),
+    "mm_tbuf_init": ([], C.c_void_p),
+    "mm_tbuf_destroy": ([C.c_void_p], None),
+    "mm_map": ([C.POINTER(mm_idx_t), C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(mm_mapopt_t),
+                C.c_char_p], C.POINTER(mm_reg1_t)),
+    "mm_event_identity": ([C.POINTER(mm_reg1_t)], C.c_double),
+}
+
+
+def bind(lib, only=None):
+    """Attach prototypes of the boundary symbols to a loaded library (`only`: a subset, for the CPU-only
+    host-logic test build, which exports just the option functions and mm_event_identity)."""
+    for name, (argtypes, restype) in _PROTOS.items():
+        if only is not None and name not in only:
+            continue
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, restype
     return lib
 
 
@@ -135,7 +139,7 @@ def reg_to_tuple(lib, r):
     cig_t = C.c_uint32 * p.n_cigar
     cig = tuple(cig_t.from_address(C.addressof(p) + 24))
     de = 1.0 - lib.mm_event_identity(C.byref(r))
-    return base + ((p.dp_score, p.dp_max, p.dp_max2, p.n_ambi_ts, cig, de),)
+    return base + ((p.capacity, p.dp_score, p.dp_max, p.dp_max2, p.n_ambi_ts, cig, de),)
 
 
 def cigar_str(cig):

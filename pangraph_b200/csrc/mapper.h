@@ -1,0 +1,75 @@
+// Host side of the mapping pipeline: what the reference does per query inside mm_map (map.c:227-374), re-organised
+// so that the data-parallel stages (sketch, index probe, anchor expansion, DP) run as whole-batch GPU launches and the
+// inherently sequential ones (anchor sort order, chaining, region bookkeeping, CIGAR stitching) run on host threads.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pgmm_b200.h"
+#include "chain.h"
+#include "flag_sort.h"
+#include "ksw_extd2.h"
+
+namespace pgmm {
+
+constexpr uint64_t SEED_LONG_JOIN = 1ULL << 40, SEED_IGNORE = 1ULL << 41, SEED_TANDEM = 1ULL << 42, SEED_SELF = 1ULL << 43;
+
+// Host view of the indexed (target) sequences.
+struct TargetSet {
+  int k = 0, w = 0;
+  std::vector<std::string> names;
+  std::vector<uint32_t> lens;
+  std::vector<uint64_t> offs;   // offset of each sequence in codes
+  std::vector<uint8_t> codes;   // 0..4 per base, all sequences concatenated
+};
+
+// One batch of queries: ASCII in, coded forward and reverse-complement copies kept on both sides.
+struct QueryBatch {
+  int n = 0;
+  std::vector<const char *> seqs, names;
+  std::vector<int> lens;
+  std::vector<uint64_t> base;  // query i: forward codes at codes[base[i] .. +len), reverse complement right after
+  std::vector<uint8_t> codes;
+};
+
+// What the seeding stage hands to the host for one query (map.c:168-204 minus the final sort).
+struct QuerySeeds {
+  std::vector<U128> a;             // anchors in collection order (seed-major, hits ascending)
+  std::vector<uint64_t> mini_pos;  // q_span<<32 | q_pos of the seeds that were used (seed.c:125)
+  int rep_len = 0;                 // bases covered by filtered, repetitive seeds (seed.c:113-128)
+};
+
+struct DpStats {
+  uint64_t jobs = 0, cells = 0, waves = 0;
+  int launches = 0;
+  double kernel_ms = 0;
+};
+
+// The device stages.  The product has exactly one implementation (CUDA, cuda_backend.cu); a second one exists only in
+// the CPU-only test library, where it forwards to the reference's own C so that the host logic can be checked without
+// a GPU (tests/hostlogic_backend.cpp).
+struct Backend {
+  virtual ~Backend() {}
+  virtual void begin_batch(const TargetSet &ts, const QueryBatch &qb) = 0;
+  virtual void seed_batch(const TargetSet &ts, const QueryBatch &qb, const mm_mapopt_t &opt, std::vector<QuerySeeds> &out) = 0;
+  // q_off indexes qb.codes, t_off indexes ts.codes
+  virtual void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) = 0;
+  virtual void end_batch() {}
+  DpStats stats;
+};
+
+// Maps every query of the batch; n_regs[i]/regs[i] are malloc()-owned like mm_map's result.
+void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt_t &opt, int *n_regs, mm_reg1_t **regs,
+               int n_threads);
+
+// ASCII -> 0..4 (A,C,G,T/U in either case -> 0..3, everything else 4; sketch.c:9-26)
+extern const uint8_t kNt4[256];
+void encode_queries(QueryBatch &qb);
+
+// --- pieces exposed for stage-level tests ---
+int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,
+                   int *qe, int *te);
+
+}  // namespace pgmm
