@@ -273,6 +273,23 @@ PGMM_API int pgmm_ksw_extd2_batch(int n, const int32_t *qlen, const int32_t *tle
                                   int e, int q2, int e2, int32_t *out_ez, uint32_t *out_cigar, uint64_t cigar_cap,
                                   uint64_t *out_cig_start, double *out_kernel_ms, uint64_t arena_budget_bytes);
 
+/* K1 alone: (w,k)-minimizers of n ASCII sequences in the reference's emission order (sketch.c:77-143):
+ * x = hash<<8|span, y = seq<<32 | lastPos<<1 | strand; sequence i's minimizers are out[out_off[i] .. out_off[i+1]).
+ * Returns 0, -1 if cap is too small. */
+PGMM_API int pgmm_sketch(int n, const char *const *seqs, const int *lens, int w, int k, uint64_t *out_x, uint64_t *out_y,
+                         uint64_t cap, uint64_t *out_off);
+
+/* K1+K3 alone: what collect_seed_hits (map.c:168-204) builds for each query BEFORE its sort: anchors (x,y pairs),
+ * the query positions of the seeds used (seed.c:125) and the repeat length (seed.c:113-128).
+ * out_n[3*i..3*i+2] = {n_anchors, n_mini_pos, rep_len}. Returns 0, -1 if a capacity is too small. */
+PGMM_API int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *const *seqs, const char *const *names,
+                                const mm_mapopt_t *opt, uint64_t *out_anchor, uint64_t anchor_cap, uint64_t *out_mini,
+                                uint64_t mini_cap, int64_t *out_n);
+
+/* counters since the last reset: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells
+ * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] DP kernel launches */
+PGMM_API void pgmm_get_stats(double *out, int n, int reset);
+
 #ifdef __cplusplus
 }
 #endif

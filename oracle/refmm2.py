@@ -199,3 +199,28 @@ def ref_map_all(seqs, names, preset="asm10", k=None, min_dp_max=90, threads=1):
         return idx.map_all(threads), idx.mo.mid_occ
     finally:
         idx.close()
+
+
+# ---- stage-level access to the reference (for the K1 / K3 parity tests) ----
+
+class mm128_t(C.Structure):
+    _fields_ = [("x", C.c_uint64), ("y", C.c_uint64)]
+
+
+class mm128_v(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("m", C.c_size_t), ("a", C.POINTER(mm128_t))]
+
+
+def ref_sketch(lib, seq, w, k, rid=0):
+    """mm_sketch (sketch.c:77-143) -> list of (x, y)."""
+    seq = seq if isinstance(seq, bytes) else seq.encode()
+    v = mm128_v(0, 0, None)
+    lib.mm_sketch.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(mm128_v)]
+    lib.mm_sketch.restype = None
+    if len(seq) == 0:
+        return []
+    lib.mm_sketch(None, seq, len(seq), w, k, rid, 0, C.byref(v))
+    out = [(v.a[i].x, v.a[i].y) for i in range(v.n)]
+    if v.a:
+        _libc.free(C.cast(v.a, C.c_void_p))
+    return out

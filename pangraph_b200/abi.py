@@ -8,6 +8,61 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpgmm_b200.so")
 
+# flag constants: include/pgmm_b200.h (reference: minimap2/minimap.h:10-47)
+MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_CIGAR, MM_F_OUT_CG = 0x1, 0x2, 0x4, 0x20
+MM_F_NO_LJOIN, MM_F_ALL_CHAINS, MM_F_RMQ = 0x400, 0x800000, 0x80000000
+
+
+class mm_idxopt_t(C.Structure):
+    _fields_ = [("k", C.c_short), ("w", C.c_short), ("flag", C.c_short), ("bucket_bits", C.c_short),
+                ("mini_batch_size", C.c_int64), ("batch_size", C.c_uint64)]
+
+
+class mm_mapopt_t(C.Structure):
+    _fields_ = [("flag", C.c_int64), ("seed", C.c_int), ("sdust_thres", C.c_int), ("max_qlen", C.c_int),
+                ("bw", C.c_int), ("bw_long", C.c_int), ("max_gap", C.c_int), ("max_gap_ref", C.c_int),
+                ("max_frag_len", C.c_int), ("max_chain_skip", C.c_int), ("max_chain_iter", C.c_int),
+                ("min_cnt", C.c_int), ("min_chain_score", C.c_int), ("chain_gap_scale", C.c_float),
+                ("chain_skip_scale", C.c_float), ("rmq_size_cap", C.c_int), ("rmq_inner_dist", C.c_int),
+                ("rmq_rescue_size", C.c_int), ("rmq_rescue_ratio", C.c_float), ("mask_level", C.c_float),
+                ("mask_len", C.c_int), ("pri_ratio", C.c_float), ("best_n", C.c_int), ("alt_drop", C.c_float),
+                ("a", C.c_int), ("b", C.c_int), ("q", C.c_int), ("e", C.c_int), ("q2", C.c_int), ("e2", C.c_int),
+                ("sc_ambi", C.c_int), ("noncan", C.c_int), ("junc_bonus", C.c_int), ("zdrop", C.c_int),
+                ("zdrop_inv", C.c_int), ("end_bonus", C.c_int), ("min_dp_max", C.c_int), ("min_ksw_len", C.c_int),
+                ("anchor_ext_len", C.c_int), ("anchor_ext_shift", C.c_int), ("max_clip_ratio", C.c_float),
+                ("rank_min_len", C.c_int), ("rank_frac", C.c_float), ("pe_ori", C.c_int), ("pe_bonus", C.c_int),
+                ("mid_occ_frac", C.c_float), ("q_occ_frac", C.c_float), ("min_mid_occ", C.c_int32),
+                ("max_mid_occ", C.c_int32), ("mid_occ", C.c_int32), ("max_occ", C.c_int32),
+                ("max_max_occ", C.c_int32), ("occ_dist", C.c_int32), ("mini_batch_size", C.c_int64),
+                ("max_sw_mat", C.c_int64), ("cap_kalloc", C.c_int64), ("split_prefix", C.c_char_p)]
+
+
+class mm_idx_seq_t(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("offset", C.c_uint64), ("len", C.c_uint32), ("is_alt", C.c_uint32)]
+
+
+class mm_idx_t(C.Structure):
+    _fields_ = [("b", C.c_int32), ("w", C.c_int32), ("k", C.c_int32), ("flag", C.c_int32), ("n_seq", C.c_uint32),
+                ("index", C.c_int32), ("n_alt", C.c_int32), ("seq", C.POINTER(mm_idx_seq_t)),
+                ("S", C.c_void_p), ("B", C.c_void_p), ("I", C.c_void_p), ("km", C.c_void_p), ("h", C.c_void_p)]
+
+
+class mm_extra_t(C.Structure):
+    _fields_ = [("capacity", C.c_uint32), ("dp_score", C.c_int32), ("dp_max", C.c_int32), ("dp_max2", C.c_int32),
+                ("n_ambi_ts", C.c_uint32), ("n_cigar", C.c_uint32)]
+
+
+class mm_reg1_t(C.Structure):
+    _fields_ = [("id", C.c_int32), ("cnt", C.c_int32), ("rid", C.c_int32), ("score", C.c_int32),
+                ("qs", C.c_int32), ("qe", C.c_int32), ("rs", C.c_int32), ("re", C.c_int32),
+                ("parent", C.c_int32), ("subsc", C.c_int32), ("as_", C.c_int32), ("mlen", C.c_int32),
+                ("blen", C.c_int32), ("n_sub", C.c_int32), ("score0", C.c_int32), ("bits", C.c_uint32),
+                ("hash", C.c_uint32), ("div", C.c_float), ("p", C.POINTER(mm_extra_t))]
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
 _lib = None
 
 
@@ -19,6 +74,24 @@ def lib():
                                "pangraph_b200 has no fallback implementation")
         _lib = C.CDLL(LIB_PATH)
         _lib.pgmm_device_count.restype = C.c_int
+        _lib.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(mm_idxopt_t), C.POINTER(mm_mapopt_t)]
+        _lib.mm_check_opt.argtypes = [C.POINTER(mm_idxopt_t), C.POINTER(mm_mapopt_t)]
+        _lib.mm_idx_str.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+        _lib.mm_idx_str.restype = C.POINTER(mm_idx_t)
+        _lib.mm_mapopt_update.argtypes = [C.POINTER(mm_mapopt_t), C.POINTER(mm_idx_t)]
+        _lib.mm_mapopt_update.restype = None
+        _lib.mm_idx_destroy.argtypes = [C.POINTER(mm_idx_t)]
+        _lib.mm_idx_destroy.restype = None
+        _lib.mm_tbuf_init.restype = C.c_void_p
+        _lib.mm_tbuf_destroy.argtypes = [C.c_void_p]
+        _lib.mm_tbuf_destroy.restype = None
+        _lib.mm_map.argtypes = [C.POINTER(mm_idx_t), C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_void_p,
+                                C.POINTER(mm_mapopt_t), C.c_char_p]
+        _lib.mm_map.restype = C.POINTER(mm_reg1_t)
+        _lib.mm_event_identity.argtypes = [C.POINTER(mm_reg1_t)]
+        _lib.mm_event_identity.restype = C.c_double
+        _lib.pgmm_map_batch.restype = None
+        _lib.pgmm_get_stats.restype = None
     return _lib
 
 
@@ -54,3 +127,153 @@ def ksw_extd2_batch(qlen, tlen, q_off, t_off, qcodes, tcodes, w, zdrop, end_bonu
         raise RuntimeError(f"pgmm_ksw_extd2_batch -> {rc}")
     cigs = [tuple(int(c) for c in cig[int(start[i]):int(start[i]) + int(ez[i, 10])]) for i in range(n)]
     return ez, cigs, ms.value
+
+
+STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_cells", "dp_waves", "bases_mapped",
+              "bases_indexed", "batches", "dp_launches")
+
+
+def get_stats(reset=False):
+    out = (C.c_double * len(STAT_NAMES))()
+    lib().pgmm_get_stats(out, len(STAT_NAMES), 1 if reset else 0)
+    return dict(zip(STAT_NAMES, out))
+
+
+def make_options(preset="asm10", k=None, min_dp_max=90):
+    """What the reference's wrapper builds for pangraph: Minimap2Options::new + init_opts with
+    Minimap2Args{x:preset, k, c:true, X:true, s:min_dp_max, bucket_bits:14}
+    (packages/minimap2/src/options.rs:84-138, options_args.rs:273-331; align_with_minimap2_lib.rs:49-57)."""
+    L = lib()
+    io, mo = mm_idxopt_t(), mm_mapopt_t()
+    if L.mm_set_opt(None, C.byref(io), C.byref(mo)) != 0:
+        raise RuntimeError("mm_set_opt(NULL) failed")
+    if L.mm_set_opt(preset.encode(), C.byref(io), C.byref(mo)) != 0:
+        raise ValueError(f"minimap2: mm_set_opt(preset, ...): failed to set options: incorrect preset {preset}")
+    if k is not None:
+        io.k = k
+    mo.flag |= MM_F_OUT_CG | MM_F_CIGAR
+    mo.min_dp_max = min_dp_max
+    mo.flag |= MM_F_ALL_CHAINS | MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_NO_LJOIN
+    io.bucket_bits = 14
+    rc = L.mm_check_opt(C.byref(io), C.byref(mo))
+    if rc != 0:
+        raise ValueError(f"minimap2: mm_check_opt(): options are invalid ({rc})")
+    return io, mo
+
+
+def reg_to_tuple(r):
+    """One mm_reg1_t (+ mm_extra_t + CIGAR + de) as a plain tuple; same field order as oracle.refmm2.reg_to_tuple."""
+    base = (r.id, r.cnt, r.rid, r.score, r.qs, r.qe, r.rs, r.re, r.parent, r.subsc, r.as_, r.mlen, r.blen,
+            r.n_sub, r.score0, r.bits, r.hash, C.c_uint32.from_buffer_copy(C.c_float(r.div)).value)
+    if not r.p:
+        return base + (None,)
+    p = r.p.contents
+    cig = tuple((C.c_uint32 * p.n_cigar).from_address(C.addressof(p) + 24))
+    de = 1.0 - lib().mm_event_identity(C.byref(r))
+    return base + ((p.capacity, p.dp_score, p.dp_max, p.dp_max2, p.n_ambi_ts, cig, de),)
+
+
+def _take_regs(regs, n):
+    out = [reg_to_tuple(regs[j]) for j in range(n)]
+    for j in range(n):
+        if regs[j].p:
+            _libc.free(C.cast(regs[j].p, C.c_void_p))
+    if regs:
+        _libc.free(C.cast(regs, C.c_void_p))
+    return out
+
+
+class Index:
+    """Minimap2Index of the reference wrapper (packages/minimap2/src/index.rs:17-55) over the GPU library."""
+
+    def __init__(self, seqs, names, preset="asm10", k=None, min_dp_max=90):
+        L = lib()
+        self.io, self.mo = make_options(preset, k, min_dp_max)
+        self.seqs = [s if isinstance(s, bytes) else s.encode() for s in seqs]
+        self.names = [s if isinstance(s, bytes) else s.encode() for s in names]
+        n = len(self.seqs)
+        sa = (C.c_char_p * n)(*self.seqs)
+        na = (C.c_char_p * n)(*self.names)
+        self.mi = L.mm_idx_str(self.io.w, self.io.k, self.io.flag & 1, self.io.bucket_bits, n, sa, na)
+        if not self.mi:
+            raise RuntimeError("minimap2: failed to create index")
+        L.mm_mapopt_update(C.byref(self.mo), self.mi)
+
+    def map_one(self, seq, name):
+        """Minimap2Mapper::run_map (packages/minimap2/src/map.rs:26-41): one mm_map call."""
+        L = lib()
+        seq = seq if isinstance(seq, bytes) else seq.encode()
+        name = name if isinstance(name, bytes) else name.encode()
+        tb = L.mm_tbuf_init()
+        n = C.c_int(0)
+        regs = L.mm_map(self.mi, len(seq), seq, C.byref(n), tb, C.byref(self.mo), name)
+        out = _take_regs(regs, n.value)
+        L.mm_tbuf_destroy(tb)
+        return out
+
+    def map_batch(self, seqs=None, names=None):
+        """All queries of one round through pgmm_map_batch (default: the indexed sequences themselves)."""
+        L = lib()
+        seqs = self.seqs if seqs is None else [s if isinstance(s, bytes) else s.encode() for s in seqs]
+        names = self.names if names is None else [s if isinstance(s, bytes) else s.encode() for s in names]
+        n = len(seqs)
+        sa, na = (C.c_char_p * n)(*seqs), (C.c_char_p * n)(*names)
+        lens = (C.c_int * n)(*[len(s) for s in seqs])
+        n_regs = (C.c_int * n)()
+        regs = (C.POINTER(mm_reg1_t) * n)()
+        L.pgmm_map_batch(self.mi, n, lens, sa, na, C.byref(self.mo), n_regs, regs)
+        return [_take_regs(regs[i], n_regs[i]) for i in range(n)]
+
+    def collect_seeds(self, seqs=None, names=None):
+        """Stage K1+K3: per query (anchors[n,2] uint64 before the sort, mini_pos uint64[], rep_len)."""
+        L = lib()
+        seqs = self.seqs if seqs is None else [s if isinstance(s, bytes) else s.encode() for s in seqs]
+        names = self.names if names is None else [s if isinstance(s, bytes) else s.encode() for s in names]
+        n = len(seqs)
+        sa, na = (C.c_char_p * n)(*seqs), (C.c_char_p * n)(*names)
+        lens = (C.c_int * n)(*[len(s) for s in seqs])
+        cap_a = 1 << 22
+        while True:
+            anchors = np.zeros((cap_a, 2), dtype=np.uint64)
+            mini = np.zeros(sum(len(s) for s in seqs) + 16, dtype=np.uint64)
+            counts = np.zeros((n, 3), dtype=np.int64)
+            rc = L.pgmm_collect_seeds(self.mi, n, lens, sa, na, C.byref(self.mo), _p(anchors), C.c_uint64(cap_a), _p(mini),
+                                      C.c_uint64(mini.size), _p(counts))
+            if rc == 0:
+                break
+            cap_a *= 4
+        out, a0, m0 = [], 0, 0
+        for i in range(n):
+            na_, nm_, rep = (int(x) for x in counts[i])
+            out.append((anchors[a0:a0 + na_].copy(), mini[m0:m0 + nm_].copy(), rep))
+            a0 += na_
+            m0 += nm_
+        return out
+
+    def close(self):
+        if self.mi:
+            lib().mm_idx_destroy(self.mi)
+            self.mi = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sketch(seqs, w, k):
+    """Stage K1: list of (x[], y[]) uint64 arrays, one per sequence."""
+    L = lib()
+    seqs = [s if isinstance(s, bytes) else s.encode() for s in seqs]
+    n = len(seqs)
+    sa = (C.c_char_p * n)(*seqs)
+    lens = (C.c_int * n)(*[len(s) for s in seqs])
+    cap = sum(len(s) for s in seqs) + 16
+    x = np.zeros(cap, dtype=np.uint64)
+    y = np.zeros(cap, dtype=np.uint64)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    rc = L.pgmm_sketch(n, sa, lens, w, k, _p(x), _p(y), C.c_uint64(cap), _p(off))
+    if rc != 0:
+        raise RuntimeError(f"pgmm_sketch -> {rc}")
+    return [(x[int(off[i]):int(off[i + 1])].copy(), y[int(off[i]):int(off[i + 1])].copy()) for i in range(n)]

@@ -10,6 +10,9 @@ OUT = os.path.join(HERE, "libpgmm_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CXX = os.environ.get("CXX", "g++")
+HOST_FLAGS = ["-O3", "-std=c++17", "-g", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-Wall", "-Wno-unused-function",
+              "-I/usr/local/cuda/include"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
          "-Xptxas", "-v", "--fmad=false"]
 
@@ -30,7 +33,10 @@ def build(verbose=False, force=False):
         o = os.path.join(OBJ, os.path.basename(s) + ".o")
         objs.append(o)
         if force or _stale(s, o, hdrs):
-            cmd = [NVCC] + ARCH + FLAGS + ["-x", "cu", "-dc" if False else "-c", s, "-o", o]
+            if s.endswith(".cu"):
+                cmd = [NVCC] + ARCH + FLAGS + ["-c", s, "-o", o]
+            else:  # host-only translation units go straight to the host compiler (no fused multiply-add contraction)
+                cmd = [CXX] + HOST_FLAGS + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)

@@ -1,0 +1,300 @@
+// The C-ABI of libpgmm_b200.so, part 1 and 2 of include/pgmm_b200.h: the minimap2-sys boundary (index, map) backed by
+// the CUDA stages, and the batched entry point.  Reference call sites: packages/minimap2/src/index.rs:40-47,
+// map.rs:390, buf.rs:17,36; reference implementations replaced: minimap2/index.c:408-456, map.c:376-381.
+#include "../../include/pgmm_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ksw_extd2.h"
+#include "mapper.h"
+#include "pgmm_cuda.h"
+#include "seeding.h"
+
+using namespace pgmm;
+
+namespace {
+
+struct Stats {
+  double seed_ms = 0, dp_kernel_ms = 0, total_ms = 0, index_ms = 0;
+  uint64_t dp_jobs = 0, dp_cells = 0, dp_waves = 0, bases_mapped = 0, bases_indexed = 0, batches = 0, launches = 0;
+};
+Stats g_stats;
+std::mutex g_stats_mu;
+
+double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// Everything that hangs off mm_idx_t::h
+struct PgmmIndex {
+  TargetSet ts;
+  DeviceIndex didx;
+  DevBuf<uint8_t> d_tcodes;
+  std::vector<std::string> sorted_names;  // distinct target names in strcmp order
+  std::vector<int32_t> t_rank;
+  SeedEngine seeder;
+  KswEngine ksw;
+  DevBuf<uint8_t> d_qcodes;
+  DeviceSeqSet qset;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;  // one batch at a time per index: concurrent mm_map callers queue here
+  ~PgmmIndex() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+int host_threads() {
+  static int n = [] {
+    const char *e = getenv("PGMM_THREADS");
+    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return v > 0 ? v : 1;
+  }();
+  return n;
+}
+
+// strcmp order without strings on the device: targets get odd ranks 2*i+1 (i = index among the distinct sorted target
+// names); a query equal to a target shares its rank, any other query gets the even rank between its neighbours
+int32_t rank_of(const std::vector<std::string> &sorted, const char *name) {
+  const auto it = std::lower_bound(sorted.begin(), sorted.end(), name,
+                                   [](const std::string &a, const char *b) { return strcmp(a.c_str(), b) < 0; });
+  const int32_t i = (int32_t)(it - sorted.begin());
+  if (it != sorted.end() && strcmp(it->c_str(), name) == 0) return 2 * i + 1;
+  return 2 * i;
+}
+
+struct CudaBackend : Backend {
+  PgmmIndex &ix;
+  explicit CudaBackend(PgmmIndex &i) : ix(i) {}
+  double t_seed = 0;
+  void begin_batch(const TargetSet &, const QueryBatch &qb) override {
+    const size_t nbytes = qb.codes.size();
+    ix.d_qcodes.ensure(nbytes + 64);
+    PGMM_CUDA(cudaMemcpyAsync(ix.d_qcodes.p, qb.codes.data(), nbytes, cudaMemcpyHostToDevice, ix.stream));
+  }
+  void seed_batch(const TargetSet &ts, const QueryBatch &qb, const mm_mapopt_t &opt, std::vector<QuerySeeds> &out) override {
+    const double t0 = now_ms();
+    std::vector<uint64_t> starts(qb.base.begin(), qb.base.end());
+    std::vector<int> lens(qb.lens.begin(), qb.lens.end());
+    ix.seeder.sketch(ix.d_qcodes.p, starts, lens, ts.w, ts.k, ix.qset, ix.stream);
+    std::vector<int32_t> q_rank(qb.n);
+    // skip_seed only looks at names when the query has one (map.c:81): INT32_MIN marks "no name"
+    for (int i = 0; i < qb.n; ++i) q_rank[i] = qb.names[i] ? rank_of(ix.sorted_names, qb.names[i]) : INT32_MIN;
+    ix.seeder.collect(ix.didx, ix.qset, q_rank, opt, out, ix.stream);
+    t_seed += now_ms() - t0;
+  }
+  void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) override {
+    ix.ksw.run(jobs, ix.d_qcodes.p, ix.d_tcodes.p, sc, res, ix.stream);
+  }
+};
+
+void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *const *seqs, const char *const *names,
+                    const mm_mapopt_t *opt, int *n_regs, mm_reg1_t **regs) {
+  require_device();
+  PgmmIndex *ix = (PgmmIndex *)mi->h;
+  if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200 (no device index attached)");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  const double t0 = now_ms();
+  QueryBatch qb;
+  qb.n = n;
+  qb.seqs.assign(seqs, seqs + n);
+  if (names) qb.names.assign(names, names + n);
+  else qb.names.assign(n, nullptr);
+  qb.lens.assign(lens, lens + n);
+  CudaBackend be(*ix);
+  map_batch(be, ix->ts, qb, *opt, n_regs, regs, host_threads());
+  std::lock_guard<std::mutex> sl(g_stats_mu);
+  g_stats.total_ms += now_ms() - t0, g_stats.seed_ms += be.t_seed, g_stats.dp_kernel_ms += be.stats.kernel_ms;
+  g_stats.dp_jobs += be.stats.jobs, g_stats.dp_cells += be.stats.cells, g_stats.dp_waves += be.stats.waves;
+  g_stats.launches += be.stats.launches, g_stats.batches += 1;
+  for (int i = 0; i < n; ++i) g_stats.bases_mapped += lens[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const char **seq, const char **name) {
+  if (n <= 0) return nullptr;
+  require_device();
+  if (is_hpc) PGMM_FATAL("homopolymer-compressed minimizers (MM_I_HPC) are outside pangraph's path; no implementation here");
+  const double t0 = now_ms();
+  if (bucket_bits < 0) bucket_bits = 14;
+  if (k * 2 < bucket_bits) bucket_bits = k * 2;
+  if (w < 1) w = 1;
+  mm_idx_t *mi = (mm_idx_t *)calloc(1, sizeof(mm_idx_t));
+  mi->w = w, mi->k = k, mi->b = bucket_bits, mi->flag = name == nullptr ? MM_I_NO_NAME : 0;
+  mi->n_seq = (uint32_t)n;
+  mi->seq = (mm_idx_seq_t *)calloc((size_t)n, sizeof(mm_idx_seq_t));
+  PgmmIndex *ix = new PgmmIndex;
+  mi->h = ix;
+  PGMM_CUDA(cudaStreamCreate(&ix->stream));
+  TargetSet &ts = ix->ts;
+  ts.k = k, ts.w = w;
+  uint64_t sum = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t len = strlen(seq[i]);
+    if (name && name[i]) mi->seq[i].name = strdup(name[i]);
+    mi->seq[i].offset = sum, mi->seq[i].len = (uint32_t)len, mi->seq[i].is_alt = 0;
+    ts.names.push_back(name && name[i] ? name[i] : "");
+    ts.lens.push_back((uint32_t)len);
+    ts.offs.push_back(sum);
+    sum += len;
+  }
+  ts.codes.resize(sum + 64);
+  {
+    std::vector<std::thread> th;
+    const int nt = std::min(host_threads(), n);
+    for (int t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        for (int i = t; i < n; i += nt) {
+          uint8_t *d = ts.codes.data() + ts.offs[i];
+          const uint8_t *s = (const uint8_t *)seq[i];
+          for (uint32_t j = 0; j < ts.lens[i]; ++j) d[j] = kNt4[s[j]];
+        }
+      });
+    for (auto &t : th) t.join();
+  }
+  ix->d_tcodes.ensure(sum + 64);
+  PGMM_CUDA(cudaMemcpyAsync(ix->d_tcodes.p, ts.codes.data(), sum, cudaMemcpyHostToDevice, ix->stream));
+  // name ranks for the all-vs-all skips
+  ix->sorted_names = ts.names;
+  std::sort(ix->sorted_names.begin(), ix->sorted_names.end(), [](const std::string &a, const std::string &b) { return strcmp(a.c_str(), b.c_str()) < 0; });
+  ix->sorted_names.erase(std::unique(ix->sorted_names.begin(), ix->sorted_names.end()), ix->sorted_names.end());
+  ix->t_rank.resize(n);
+  for (int i = 0; i < n; ++i) ix->t_rank[i] = rank_of(ix->sorted_names, ts.names[i].c_str());
+  // K1 + K2
+  std::vector<int> lens(ts.lens.begin(), ts.lens.end());
+  ix->didx.w = w, ix->didx.k = k;
+  ix->seeder.sketch(ix->d_tcodes.p, ts.offs, lens, w, k, ix->didx.seqs, ix->stream);
+  ix->seeder.build_index(ix->didx, ts.lens, ix->t_rank, ix->stream);
+  std::lock_guard<std::mutex> sl(g_stats_mu);
+  g_stats.index_ms += now_ms() - t0, g_stats.bases_indexed += sum;
+  return mi;
+}
+
+void mm_mapopt_update(mm_mapopt_t *opt, const mm_idx_t *mi) {
+  if ((opt->flag & MM_F_SPLICE_FOR) || (opt->flag & MM_F_SPLICE_REV)) opt->flag |= MM_F_SPLICE;
+  if (opt->mid_occ <= 0) {
+    PgmmIndex *ix = (PgmmIndex *)mi->h;
+    if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    opt->mid_occ = SeedEngine::cal_max_occ(ix->didx, opt->mid_occ_frac, ix->stream);
+    if (opt->mid_occ < opt->min_mid_occ) opt->mid_occ = opt->min_mid_occ;
+    if (opt->max_mid_occ > opt->min_mid_occ && opt->mid_occ > opt->max_mid_occ) opt->mid_occ = opt->max_mid_occ;
+  }
+  if (opt->bw_long < opt->bw) opt->bw_long = opt->bw;
+}
+
+void mm_idx_destroy(mm_idx_t *mi) {
+  if (mi == nullptr) return;
+  delete (PgmmIndex *)mi->h;
+  if (mi->seq) {
+    for (uint32_t i = 0; i < mi->n_seq; ++i) free(mi->seq[i].name);
+    free(mi->seq);
+  }
+  free(mi);
+}
+
+struct mm_tbuf_s {
+  void *km;
+  int rep_len, frag_gap;
+};
+
+mm_tbuf_t *mm_tbuf_init(void) { return (mm_tbuf_t *)calloc(1, sizeof(mm_tbuf_s)); }
+void mm_tbuf_destroy(mm_tbuf_t *b) { free(b); }
+
+mm_reg1_t *mm_map(const mm_idx_t *mi, int l_seq, const char *seq, int *n_regs, mm_tbuf_t *, const mm_mapopt_t *opt, const char *name) {
+  mm_reg1_t *regs = nullptr;
+  const char *names[1] = {name};
+  map_with_index(mi, 1, &l_seq, &seq, name ? names : nullptr, opt, n_regs, &regs);
+  return regs;
+}
+
+void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *const *seqs, const char *const *names, const mm_mapopt_t *opt,
+                    int *n_regs, mm_reg1_t **regs) {
+  map_with_index(mi, n, lens, seqs, names, opt, n_regs, regs);
+}
+
+// stats: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells [6] dp_waves [7] bases_mapped
+//        [8] bases_indexed [9] batches [10] kernel launches of the DP engine
+void pgmm_get_stats(double *out, int n, int reset) {
+  std::lock_guard<std::mutex> sl(g_stats_mu);
+  const double v[11] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+                        (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
+                        (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches};
+  for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+  if (reset) g_stats = Stats();
+}
+
+
+// ---- stage-level entry points (include/pgmm_b200.h part 3) ----
+
+// K1 alone: minimizers of n ASCII sequences. out_x/out_y need capacity for all of them (cap entries); out_off[n+1].
+int pgmm_sketch(int n, const char *const *seqs, const int *lens, int w, int k, uint64_t *out_x, uint64_t *out_y, uint64_t cap,
+                uint64_t *out_off) {
+  require_device();
+  std::vector<uint64_t> starts(n);
+  std::vector<int> l(lens, lens + n);
+  uint64_t sum = 0;
+  for (int i = 0; i < n; ++i) starts[i] = sum, sum += (uint64_t)lens[i];
+  std::vector<uint8_t> codes(sum + 64);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < lens[i]; ++j) codes[starts[i] + j] = kNt4[(uint8_t)seqs[i][j]];
+  cudaStream_t st;
+  PGMM_CUDA(cudaStreamCreate(&st));
+  DevBuf<uint8_t> d;
+  d.ensure(sum + 64);
+  PGMM_CUDA(cudaMemcpyAsync(d.p, codes.data(), sum, cudaMemcpyHostToDevice, st));
+  SeedEngine eng;
+  DeviceSeqSet set;
+  eng.sketch(d.p, starts, l, w, k, set, st);
+  int rc = 0;
+  if (set.n_mz > cap) rc = -1;
+  else if (set.n_mz > 0) {
+    PGMM_CUDA(cudaMemcpyAsync(out_x, set.mx.p, set.n_mz * 8, cudaMemcpyDeviceToHost, st));
+    PGMM_CUDA(cudaMemcpyAsync(out_y, set.my.p, set.n_mz * 8, cudaMemcpyDeviceToHost, st));
+  }
+  PGMM_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i <= n; ++i) out_off[i] = set.h_mz_off[i];
+  PGMM_CUDA(cudaStreamDestroy(st));
+  return rc;
+}
+
+// K1+K3 alone: the anchors (before the host's sort), used-seed positions and repeat length of every query against mi.
+// out_anchor: 2 uint64 per anchor; out_n[3*i..] = {n_anchors, n_mini_pos, rep_len} of query i.
+int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *const *seqs, const char *const *names,
+                       const mm_mapopt_t *opt, uint64_t *out_anchor, uint64_t anchor_cap, uint64_t *out_mini, uint64_t mini_cap,
+                       int64_t *out_n) {
+  require_device();
+  PgmmIndex *ix = (PgmmIndex *)mi->h;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  QueryBatch qb;
+  qb.n = n;
+  qb.seqs.assign(seqs, seqs + n);
+  if (names) qb.names.assign(names, names + n);
+  else qb.names.assign(n, nullptr);
+  qb.lens.assign(lens, lens + n);
+  encode_queries(qb);
+  CudaBackend be(*ix);
+  be.begin_batch(ix->ts, qb);
+  std::vector<QuerySeeds> out;
+  be.seed_batch(ix->ts, qb, *opt, out);
+  uint64_t na = 0, nm = 0;
+  for (int i = 0; i < n; ++i) {
+    if (na + out[i].a.size() > anchor_cap || nm + out[i].mini_pos.size() > mini_cap) return -1;
+    memcpy(out_anchor + 2 * na, out[i].a.data(), out[i].a.size() * 16);
+    memcpy(out_mini + nm, out[i].mini_pos.data(), out[i].mini_pos.size() * 8);
+    out_n[3 * i] = (int64_t)out[i].a.size(), out_n[3 * i + 1] = (int64_t)out[i].mini_pos.size(), out_n[3 * i + 2] = out[i].rep_len;
+    na += out[i].a.size(), nm += out[i].mini_pos.size();
+  }
+  return 0;
+}
+
+}  // extern "C"
