@@ -216,6 +216,14 @@ PGMM_API double mm_event_identity(const mm_reg1_t *r);
 PGMM_API void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *const *seqs, const char *const *names,
                              const mm_mapopt_t *opt, int *n_regs, mm_reg1_t **regs);
 
+/* The same round with the inputs kept resident in HBM: pgmm_idx_upload codes the sequences and copies them to the
+ * device once; pgmm_idx_build runs the sketch and index kernels on the resident bases (mm_idx_str = upload + build);
+ * pgmm_map_self maps the indexed sequences against their own index -- pangraph's all-vs-all pattern -- deriving the
+ * query-side buffers on the device, so no sequence crosses the bus again.  n_regs/regs have mi->n_seq entries. */
+PGMM_API mm_idx_t *pgmm_idx_upload(int n, const char **seq, const char **name);
+PGMM_API void pgmm_idx_build(mm_idx_t *mi, int w, int k, int bucket_bits);
+PGMM_API void pgmm_map_self(const mm_idx_t *mi, const mm_mapopt_t *opt, int *n_regs, mm_reg1_t **regs);
+
 /* One alignment record, the C image of pangraph's `Alignment` (packages/pangraph/src/align/alignment.rs:13-59).
  * Block names are the decimal BlockId values; cigar is malloc()ed (len<<4|op) and owned by the caller. */
 typedef struct {
@@ -287,7 +295,9 @@ PGMM_API int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, cons
                                 uint64_t mini_cap, int64_t *out_n);
 
 /* counters since the last reset: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells
- * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] DP kernel launches */
+ * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] kernel launches [11..16] wall ms of the phases of
+ * pgmm_map_batch (encode, seeding, sort+chain+plan, DP waves, stitching between waves, final filters)
+ * [17] host->device bytes [18] device->host bytes [19] bases read by the DP kernels */
 PGMM_API void pgmm_get_stats(double *out, int n, int reset);
 
 #ifdef __cplusplus

@@ -91,6 +91,11 @@ def lib():
         _lib.mm_event_identity.argtypes = [C.POINTER(mm_reg1_t)]
         _lib.mm_event_identity.restype = C.c_double
         _lib.pgmm_map_batch.restype = None
+        _lib.pgmm_map_self.restype = None
+        _lib.pgmm_idx_upload.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+        _lib.pgmm_idx_upload.restype = C.POINTER(mm_idx_t)
+        _lib.pgmm_idx_build.argtypes = [C.POINTER(mm_idx_t), C.c_int, C.c_int, C.c_int]
+        _lib.pgmm_idx_build.restype = None
         _lib.pgmm_get_stats.restype = None
     return _lib
 
@@ -130,7 +135,8 @@ def ksw_extd2_batch(qlen, tlen, q_off, t_off, qcodes, tcodes, w, zdrop, end_bonu
 
 
 STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_cells", "dp_waves", "bases_mapped",
-              "bases_indexed", "batches", "dp_launches")
+              "bases_indexed", "batches", "launches", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch", "t_final",
+              "h2d_bytes", "d2h_bytes", "dp_seq_bytes")
 
 
 def get_stats(reset=False):
@@ -186,7 +192,8 @@ def _take_regs(regs, n):
 class Index:
     """Minimap2Index of the reference wrapper (packages/minimap2/src/index.rs:17-55) over the GPU library."""
 
-    def __init__(self, seqs, names, preset="asm10", k=None, min_dp_max=90):
+    def __init__(self, seqs, names, preset="asm10", k=None, min_dp_max=90, resident_only=False):
+        """resident_only=True stops after pgmm_idx_upload (bases coded and copied to HBM); call build() next."""
         L = lib()
         self.io, self.mo = make_options(preset, k, min_dp_max)
         self.seqs = [s if isinstance(s, bytes) else s.encode() for s in seqs]
@@ -194,10 +201,33 @@ class Index:
         n = len(self.seqs)
         sa = (C.c_char_p * n)(*self.seqs)
         na = (C.c_char_p * n)(*self.names)
+        if resident_only:
+            self.mi = L.pgmm_idx_upload(n, sa, na)
+            if not self.mi:
+                raise RuntimeError("minimap2: failed to create index")
+            return
         self.mi = L.mm_idx_str(self.io.w, self.io.k, self.io.flag & 1, self.io.bucket_bits, n, sa, na)
         if not self.mi:
             raise RuntimeError("minimap2: failed to create index")
         L.mm_mapopt_update(C.byref(self.mo), self.mi)
+
+    def build(self):
+        """K1+K2 on the resident bases, then mm_mapopt_update."""
+        L = lib()
+        L.pgmm_idx_build(self.mi, self.io.w, self.io.k, self.io.bucket_bits)
+        self.mo.mid_occ = 0
+        L.mm_mapopt_update(C.byref(self.mo), self.mi)
+
+    def map_self(self, raw=False):
+        """pgmm_map_self: the indexed sequences against their own index, nothing re-uploaded."""
+        L = lib()
+        n = len(self.seqs)
+        n_regs = (C.c_int * n)()
+        regs = (C.POINTER(mm_reg1_t) * n)()
+        L.pgmm_map_self(self.mi, C.byref(self.mo), n_regs, regs)
+        if raw:
+            return n_regs, regs
+        return [_take_regs(regs[i], n_regs[i]) for i in range(n)]
 
     def map_one(self, seq, name):
         """Minimap2Mapper::run_map (packages/minimap2/src/map.rs:26-41): one mm_map call."""

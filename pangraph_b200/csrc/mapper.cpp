@@ -17,6 +17,7 @@
 #include <cstring>
 #include <functional>
 #include <thread>
+#include <ctime>
 
 namespace pgmm {
 
@@ -31,7 +32,7 @@ const uint8_t kNt4[256] = {
 #undef R4
 };
 
-void encode_queries(QueryBatch &qb) {
+void encode_queries(QueryBatch &qb, const TargetSet &ts) {
   qb.base.resize(qb.n);
   uint64_t tot = 0;
   for (int i = 0; i < qb.n; ++i) qb.base[i] = tot, tot += 2ull * qb.lens[i];
@@ -39,10 +40,18 @@ void encode_queries(QueryBatch &qb) {
   for (int i = 0; i < qb.n; ++i) {  // align.c:969-975
     const int L = qb.lens[i];
     uint8_t *f = qb.codes.data() + qb.base[i], *r = f + L;
-    const uint8_t *s = (const uint8_t *)qb.seqs[i];
-    for (int j = 0; j < L; ++j) {
-      const uint8_t c = kNt4[s[j]];
-      f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
+    if (qb.from_targets) {
+      const uint8_t *s = ts.codes.data() + ts.offs[i];
+      for (int j = 0; j < L; ++j) {
+        const uint8_t c = s[j];
+        f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
+      }
+    } else {
+      const uint8_t *s = (const uint8_t *)qb.seqs[i];
+      for (int j = 0; j < L; ++j) {
+        const uint8_t c = kNt4[s[j]];
+        f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
+      }
     }
   }
 }
@@ -1137,10 +1146,18 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     abort();
   }
   Mapper M(ts, qb, opt);
-  encode_queries(qb);
+  const auto now = []() {
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+  };
+  double t0 = now(), t1;
+  encode_queries(qb, ts);
+  t1 = now(), be.stats.t_encode += t1 - t0, t0 = t1;
   be.begin_batch(ts, qb);
   std::vector<QuerySeeds> seeds;
   be.seed_batch(ts, qb, opt, seeds);
+  t1 = now(), be.stats.t_seed += t1 - t0, t0 = t1;
 
   std::vector<QCtx> Q(qb.n);
   const float pen_gap = (float)(opt.chain_gap_scale * 0.01 * ts.k), pen_skip = (float)(opt.chain_skip_scale * 0.01 * ts.k);
@@ -1169,6 +1186,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     for (auto &R : q.regs) M.plan_region(q, *R);
   });
 
+  t1 = now(), be.stats.t_chain += t1 - t0, t0 = t1;
   // ---- DP waves ----
   KswScoring sc;
   sc.sc_mch = (int8_t)(opt.a < 0 ? -opt.a : opt.a), sc.sc_mis = (int8_t)(opt.b > 0 ? -opt.b : opt.b), sc.sc_ambi = (int8_t)opt.sc_ambi;
@@ -1189,9 +1207,12 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     for (QCtx &q : Q)
       for (auto &R : q.regs) any_waiting |= R->state != Region::DONE;
     if (!any_waiting) break;
+    t1 = now(), be.stats.t_stitch += t1 - t0, t0 = t1;
     if (!jobs.empty()) {
       be.run_dp(jobs, sc, res);
+      t1 = now(), be.stats.t_dp += t1 - t0, t0 = t1;
       be.stats.jobs += jobs.size(), be.stats.cells += res.cells, be.stats.waves += 1;
+      for (const KswJob &j : jobs) be.stats.seq_bytes += (uint64_t)j.qlen + j.tlen;
       be.stats.launches += res.launches, be.stats.kernel_ms += res.kernel_ms;
     } else {
       res.out.clear(), res.cigar.clear(), res.cig_start.clear();
@@ -1240,6 +1261,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     });
   }
   be.end_batch();
+  t1 = now(), be.stats.t_stitch += t1 - t0, t0 = t1;
 
   // ---- final filters, order, mapq, and the malloc()-owned result the boundary promises (minimap.h:353-366) ----
   parallel_for(qb.n, n_threads, [&](int qi) {
@@ -1270,6 +1292,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     }
     n_regs[qi] = n, regs[qi] = out;
   });
+  t1 = now(), be.stats.t_final += t1 - t0;
 }
 
 }  // namespace pgmm

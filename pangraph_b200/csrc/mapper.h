@@ -32,6 +32,8 @@ struct QueryBatch {
   std::vector<int> lens;
   std::vector<uint64_t> base;  // query i: forward codes at codes[base[i] .. +len), reverse complement right after
   std::vector<uint8_t> codes;
+  bool from_targets = false;   // the queries ARE the indexed sequences (pangraph's all-vs-all round): seqs is unused and
+                               // the device builds its query buffer from the resident target codes
 };
 
 // What the seeding stage hands to the host for one query (map.c:168-204 minus the final sort).
@@ -42,9 +44,12 @@ struct QuerySeeds {
 };
 
 struct DpStats {
-  uint64_t jobs = 0, cells = 0, waves = 0;
+  uint64_t jobs = 0, cells = 0, waves = 0, seq_bytes = 0;
   int launches = 0;
   double kernel_ms = 0;
+  // wall-clock phases of map_batch (ms): encode, seeding (GPU), anchor sort + chain + plan (host), DP waves (GPU incl.
+  // copies), host work between waves, final filters + output
+  double t_encode = 0, t_seed = 0, t_chain = 0, t_dp = 0, t_stitch = 0, t_final = 0;
 };
 
 // The device stages.  The product has exactly one implementation (CUDA, cuda_backend.cu); a second one exists only in
@@ -66,7 +71,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
 
 // ASCII -> 0..4 (A,C,G,T/U in either case -> 0..3, everything else 4; sketch.c:9-26)
 extern const uint8_t kNt4[256];
-void encode_queries(QueryBatch &qb);
+void encode_queries(QueryBatch &qb, const TargetSet &ts);
 
 // --- pieces exposed for stage-level tests ---
 int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,

@@ -21,7 +21,8 @@ namespace {
 
 struct Stats {
   double seed_ms = 0, dp_kernel_ms = 0, total_ms = 0, index_ms = 0;
-  uint64_t dp_jobs = 0, dp_cells = 0, dp_waves = 0, bases_mapped = 0, bases_indexed = 0, batches = 0, launches = 0;
+  uint64_t dp_seq_bytes = 0, dp_jobs = 0, dp_cells = 0, dp_waves = 0, bases_mapped = 0, bases_indexed = 0, batches = 0, launches = 0;
+  double t_encode = 0, t_seed = 0, t_chain = 0, t_dp = 0, t_stitch = 0, t_final = 0;
 };
 Stats g_stats;
 std::mutex g_stats_mu;
@@ -69,14 +70,38 @@ int32_t rank_of(const std::vector<std::string> &sorted, const char *name) {
   return 2 * i;
 }
 
+// builds the device query buffer (forward codes, then their reverse complement, per sequence) from resident target codes
+__global__ void self_query_kernel(const uint8_t *__restrict__ tcodes, const uint64_t *__restrict__ t_off, const uint64_t *__restrict__ vstart,
+                                  int n, uint64_t total, uint8_t *__restrict__ qcodes) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (vstart[mid] <= p) lo = mid;
+    else hi = mid;
+  }
+  const uint64_t i = p - vstart[lo], L = vstart[lo + 1] - vstart[lo];
+  const uint8_t c = tcodes[t_off[lo] + i];
+  uint8_t *q = qcodes + 2 * vstart[lo];
+  q[i] = c, q[L + (L - 1 - i)] = c < 4 ? 3 - c : 4;
+}
+
 struct CudaBackend : Backend {
   PgmmIndex &ix;
   explicit CudaBackend(PgmmIndex &i) : ix(i) {}
   double t_seed = 0;
-  void begin_batch(const TargetSet &, const QueryBatch &qb) override {
+  void begin_batch(const TargetSet &ts, const QueryBatch &qb) override {
     const size_t nbytes = qb.codes.size();
     ix.d_qcodes.ensure(nbytes + 64);
-    PGMM_CUDA(cudaMemcpyAsync(ix.d_qcodes.p, qb.codes.data(), nbytes, cudaMemcpyHostToDevice, ix.stream));
+    if (qb.from_targets) {  // nothing crosses the bus: the query buffer is derived from the resident target codes
+      const DeviceSeqSet &s = ix.didx.seqs;
+      if (s.total > 0)
+        self_query_kernel<<<(unsigned)((s.total + 255) / 256), 256, 0, ix.stream>>>(ix.d_tcodes.p, s.starts.p, s.vstart.p, s.n, s.total, ix.d_qcodes.p);
+      PGMM_CUDA(cudaGetLastError());
+      ++g_seed_launches;
+      (void)ts;
+    } else PGMM_CUDA(cudaMemcpyAsync(ix.d_qcodes.p, qb.codes.data(), nbytes, cudaMemcpyHostToDevice, ix.stream));
   }
   void seed_batch(const TargetSet &ts, const QueryBatch &qb, const mm_mapopt_t &opt, std::vector<QuerySeeds> &out) override {
     const double t0 = now_ms();
@@ -102,17 +127,30 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   std::lock_guard<std::mutex> lock(ix->mu);
   const double t0 = now_ms();
   QueryBatch qb;
+  std::vector<int> self_lens;
+  std::vector<const char *> self_names;
+  if (seqs == nullptr) {  // pgmm_map_self: the queries are the indexed sequences
+    n = (int)ix->ts.lens.size();
+    qb.from_targets = true;
+    for (int i = 0; i < n; ++i) self_lens.push_back((int)ix->ts.lens[i]), self_names.push_back(mi->seq[i].name);
+    lens = self_lens.data();
+    qb.seqs.assign(n, nullptr);
+    qb.names = self_names;
+  } else {
+    qb.seqs.assign(seqs, seqs + n);
+    if (names) qb.names.assign(names, names + n);
+    else qb.names.assign(n, nullptr);
+  }
   qb.n = n;
-  qb.seqs.assign(seqs, seqs + n);
-  if (names) qb.names.assign(names, names + n);
-  else qb.names.assign(n, nullptr);
   qb.lens.assign(lens, lens + n);
   CudaBackend be(*ix);
   map_batch(be, ix->ts, qb, *opt, n_regs, regs, host_threads());
   std::lock_guard<std::mutex> sl(g_stats_mu);
   g_stats.total_ms += now_ms() - t0, g_stats.seed_ms += be.t_seed, g_stats.dp_kernel_ms += be.stats.kernel_ms;
   g_stats.dp_jobs += be.stats.jobs, g_stats.dp_cells += be.stats.cells, g_stats.dp_waves += be.stats.waves;
-  g_stats.launches += be.stats.launches, g_stats.batches += 1;
+  g_stats.launches += be.stats.launches, g_stats.batches += 1, g_stats.dp_seq_bytes += be.stats.seq_bytes;
+  g_stats.t_encode += be.stats.t_encode, g_stats.t_seed += be.stats.t_seed, g_stats.t_chain += be.stats.t_chain;
+  g_stats.t_dp += be.stats.t_dp, g_stats.t_stitch += be.stats.t_stitch, g_stats.t_final += be.stats.t_final;
   for (int i = 0; i < n; ++i) g_stats.bases_mapped += lens[i];
 }
 
@@ -120,23 +158,17 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
 
 extern "C" {
 
-mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const char **seq, const char **name) {
+mm_idx_t *pgmm_idx_upload(int n, const char **seq, const char **name) {
   if (n <= 0) return nullptr;
   require_device();
-  if (is_hpc) PGMM_FATAL("homopolymer-compressed minimizers (MM_I_HPC) are outside pangraph's path; no implementation here");
-  const double t0 = now_ms();
-  if (bucket_bits < 0) bucket_bits = 14;
-  if (k * 2 < bucket_bits) bucket_bits = k * 2;
-  if (w < 1) w = 1;
   mm_idx_t *mi = (mm_idx_t *)calloc(1, sizeof(mm_idx_t));
-  mi->w = w, mi->k = k, mi->b = bucket_bits, mi->flag = name == nullptr ? MM_I_NO_NAME : 0;
+  mi->flag = name == nullptr ? MM_I_NO_NAME : 0;
   mi->n_seq = (uint32_t)n;
   mi->seq = (mm_idx_seq_t *)calloc((size_t)n, sizeof(mm_idx_seq_t));
   PgmmIndex *ix = new PgmmIndex;
   mi->h = ix;
   PGMM_CUDA(cudaStreamCreate(&ix->stream));
   TargetSet &ts = ix->ts;
-  ts.k = k, ts.w = w;
   uint64_t sum = 0;
   for (int i = 0; i < n; ++i) {
     const size_t len = strlen(seq[i]);
@@ -169,14 +201,42 @@ mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const cha
   ix->sorted_names.erase(std::unique(ix->sorted_names.begin(), ix->sorted_names.end()), ix->sorted_names.end());
   ix->t_rank.resize(n);
   for (int i = 0; i < n; ++i) ix->t_rank[i] = rank_of(ix->sorted_names, ts.names[i].c_str());
+  PGMM_CUDA(cudaStreamSynchronize(ix->stream));
+  return mi;
+}
+
+void pgmm_idx_build(mm_idx_t *mi, int w, int k, int bucket_bits) {
+  PgmmIndex *ix = (PgmmIndex *)mi->h;
+  if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  const double t0 = now_ms();
+  if (bucket_bits < 0) bucket_bits = 14;
+  if (k * 2 < bucket_bits) bucket_bits = k * 2;
+  if (w < 1) w = 1;
+  mi->w = w, mi->k = k, mi->b = bucket_bits;
+  TargetSet &ts = ix->ts;
+  ts.k = k, ts.w = w;
   // K1 + K2
   std::vector<int> lens(ts.lens.begin(), ts.lens.end());
   ix->didx.w = w, ix->didx.k = k;
   ix->seeder.sketch(ix->d_tcodes.p, ts.offs, lens, w, k, ix->didx.seqs, ix->stream);
   ix->seeder.build_index(ix->didx, ts.lens, ix->t_rank, ix->stream);
+  uint64_t sum = 0;
+  for (uint32_t l : ts.lens) sum += l;
   std::lock_guard<std::mutex> sl(g_stats_mu);
   g_stats.index_ms += now_ms() - t0, g_stats.bases_indexed += sum;
+}
+
+mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const char **seq, const char **name) {
+  if (n <= 0) return nullptr;
+  if (is_hpc) PGMM_FATAL("homopolymer-compressed minimizers (MM_I_HPC) are outside pangraph's path; no implementation here");
+  mm_idx_t *mi = pgmm_idx_upload(n, seq, name);
+  pgmm_idx_build(mi, w, k, bucket_bits);
   return mi;
+}
+
+void pgmm_map_self(const mm_idx_t *mi, const mm_mapopt_t *opt, int *n_regs, mm_reg1_t **regs) {
+  map_with_index(mi, 0, nullptr, nullptr, nullptr, opt, n_regs, regs);
 }
 
 void mm_mapopt_update(mm_mapopt_t *opt, const mm_idx_t *mi) {
@@ -226,10 +286,13 @@ void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *cons
 //        [8] bases_indexed [9] batches [10] kernel launches of the DP engine
 void pgmm_get_stats(double *out, int n, int reset) {
   std::lock_guard<std::mutex> sl(g_stats_mu);
-  const double v[11] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+  const double v[20] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
                         (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
-                        (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches};
-  for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+                        (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches,
+                        g_stats.t_encode, g_stats.t_seed, g_stats.t_chain, g_stats.t_dp, g_stats.t_stitch, g_stats.t_final,
+                        (double)pgmm::h2d_bytes(), (double)pgmm::d2h_bytes(), (double)g_stats.dp_seq_bytes};
+  for (int i = 0; i < n && i < 20; ++i) out[i] = v[i];
+  if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0;
   if (reset) g_stats = Stats();
 }
 
@@ -281,7 +344,7 @@ int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *c
   if (names) qb.names.assign(names, names + n);
   else qb.names.assign(n, nullptr);
   qb.lens.assign(lens, lens + n);
-  encode_queries(qb);
+  encode_queries(qb, ix->ts);
   CudaBackend be(*ix);
   be.begin_batch(ix->ts, qb);
   std::vector<QuerySeeds> out;

@@ -27,6 +27,21 @@
 
 namespace pgmm {
 
+// bytes moved across the bus, counted where they are issued (read by pgmm_get_stats)
+inline uint64_t &h2d_bytes() {
+  static uint64_t v = 0;
+  return v;
+}
+inline uint64_t &d2h_bytes() {
+  static uint64_t v = 0;
+  return v;
+}
+inline cudaError_t counted_memcpy_async(void *dst, const void *src, size_t n, cudaMemcpyKind kind, cudaStream_t st) {
+  if (kind == cudaMemcpyHostToDevice) __atomic_fetch_add(&h2d_bytes(), (uint64_t)n, __ATOMIC_RELAXED);
+  else if (kind == cudaMemcpyDeviceToHost) __atomic_fetch_add(&d2h_bytes(), (uint64_t)n, __ATOMIC_RELAXED);
+  return cudaMemcpyAsync(dst, src, n, kind, st);
+}
+
 // Grow-only device buffer (cudaMallocAsync-free: plain cudaMalloc, reused across calls).
 template <typename T>
 struct DevBuf {
@@ -84,3 +99,6 @@ inline void require_device() {
 }
 
 }  // namespace pgmm
+
+// every copy in the library goes through the counter
+#define cudaMemcpyAsync(dst, src, n, kind, st) pgmm::counted_memcpy_async((dst), (src), (n), (kind), (st))

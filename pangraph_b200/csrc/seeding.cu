@@ -20,6 +20,8 @@
 
 namespace pgmm {
 
+uint64_t g_seed_launches = 0;
+
 namespace {
 
 constexpr uint64_t U64MAX = ~0ull;
@@ -481,7 +483,7 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
   }
   SeqView v{d_codes, set.starts.p, set.vstart.p, n, N};
   m.ev.ensure(N), m.hv.ensure(N), m.rmark.ensure(N), m.rpos.ensure(N), m.ev_incl.ensure(N);
-  kmer_kernel<<<nblk(N), TPB, 0, st>>>(v, k, m.ev.p, m.hv.p, m.rmark.p);
+  ++g_seed_launches, kmer_kernel<<<nblk(N), TPB, 0, st>>>(v, k, m.ev.p, m.hv.p, m.rmark.p);
   m.incl_sum(m.ev.p, m.ev_incl.p, N, st);
   {
     size_t bytes = 0;
@@ -497,15 +499,15 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
     return;
   }
   m.EX.ensure(n_ev), m.EP.ensure(n_ev), m.EL.ensure(n_ev), m.flag.ensure(n_ev), m.fpos.ensure(n_ev);
-  event_kernel<<<nblk(N), TPB, 0, st>>>(v, k, m.ev.p, m.hv.p, m.ev_incl.p, m.rpos.p, m.EX.p, m.EP.p, m.EL.p);
+  ++g_seed_launches, event_kernel<<<nblk(N), TPB, 0, st>>>(v, k, m.ev.p, m.hv.p, m.ev_incl.p, m.rpos.p, m.EX.p, m.EP.p, m.EL.p);
   PGMM_CUDA(cudaMemsetAsync(m.flag.p, 0, (size_t)n_ev * 4, st));
-  select_kernel<<<nblk(n_ev), TPB, 0, st>>>(v, w, k, n_ev, m.ev_incl.p, m.EX.p, m.EP.p, m.EL.p, m.flag.p);
+  ++g_seed_launches, select_kernel<<<nblk(n_ev), TPB, 0, st>>>(v, w, k, n_ev, m.ev_incl.p, m.EX.p, m.EP.p, m.EL.p, m.flag.p);
   PGMM_CUDA(cudaGetLastError());
   const uint64_t n_mz = m.scan_flags(m.flag.p, m.fpos.p, n_ev, st);
   set.n_mz = n_mz;
   set.mx.ensure(n_mz + 1), set.my.ensure(n_mz + 1);
-  scatter_mz_kernel<<<nblk(n_ev), TPB, 0, st>>>(v, n_ev, m.flag.p, m.fpos.p, m.EX.p, m.EP.p, set.mx.p, set.my.p);
-  mz_offsets_kernel<<<nblk(n + 1), TPB, 0, st>>>(v, n_ev, m.ev_incl.p, m.fpos.p, (uint32_t)n_mz, set.mz_off.p);
+  ++g_seed_launches, scatter_mz_kernel<<<nblk(n_ev), TPB, 0, st>>>(v, n_ev, m.flag.p, m.fpos.p, m.EX.p, m.EP.p, set.mx.p, set.my.p);
+  ++g_seed_launches, mz_offsets_kernel<<<nblk(n + 1), TPB, 0, st>>>(v, n_ev, m.ev_incl.p, m.fpos.p, (uint32_t)n_mz, set.mz_off.p);
   PGMM_CUDA(cudaGetLastError());
   PGMM_CUDA(cudaMemcpyAsync(set.h_mz_off.data(), set.mz_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
   PGMM_CUDA(cudaStreamSynchronize(st));
@@ -527,7 +529,7 @@ void SeedEngine::build_index(DeviceIndex &idx, const std::vector<uint32_t> &lens
   // minimizers arrive ordered by (sequence, position); a stable sort on the hash therefore leaves every key's
   // positions ascending, which is the order mm_idx_get hands out (index.c:245-255)
   m.key_in.ensure(n), m.key_out.ensure(n);
-  split_key_kernel<<<nblk(n), TPB, 0, st>>>(n, set.mx.p, m.key_in.p);
+  ++g_seed_launches, split_key_kernel<<<nblk(n), TPB, 0, st>>>(n, set.mx.p, m.key_in.p);
   {
     size_t bytes = 0;
     PGMM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, m.key_in.p, m.key_out.p, set.my.p, idx.pos.p, (int64_t)n, 0, 2 * idx.k, st));
@@ -583,7 +585,7 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     uint32_t *qid2 = m.u32[4].ensure(n), *idx2 = m.u32[5].ensure(n), *head = m.u32[6].ensure(n), *run_incl = m.u32[7].ensure(n);
     uint32_t *keep = m.u32[8].ensure(n), *kpos = m.u32[9].ensure(n);
     uint64_t *sx = m.u64[0].ensure(n), *sx2 = m.u64[1].ensure(n);
-    mzflt_prepare_kernel<<<nblk(n), TPB, 0, st>>>(n, qs.my.p, qid, idxv);
+    ++g_seed_launches, mzflt_prepare_kernel<<<nblk(n), TPB, 0, st>>>(n, qs.my.p, qid, idxv);
     // sort by x, carrying (query id, index); then stable by query id: equal (query, x) become adjacent
     size_t bytes = 0;
     PGMM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, qs.mx.p, sx, idxv, idx2, (int64_t)n, 0, 64, st));
@@ -596,21 +598,21 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     PGMM_CUDA(cub::DeviceRadixSort::SortPairs(m.tmp(bytes), bytes, qid2, sq, idx2, sidx, (int64_t)n, 0, qbits, st));
     PGMM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, qid2, sq, sx, sx2, (int64_t)n, 0, qbits, st));
     PGMM_CUDA(cub::DeviceRadixSort::SortPairs(m.tmp(bytes), bytes, qid2, sq, sx, sx2, (int64_t)n, 0, qbits, st));
-    mzflt_heads_kernel<<<nblk(n), TPB, 0, st>>>(n, sx2, sq, head);
+    ++g_seed_launches, mzflt_heads_kernel<<<nblk(n), TPB, 0, st>>>(n, sx2, sq, head);
     m.incl_sum(head, run_incl, n, st);
     uint32_t n_runs = 0;
     PGMM_CUDA(cudaMemcpyAsync(&n_runs, run_incl + n - 1, 4, cudaMemcpyDeviceToHost, st));
     PGMM_CUDA(cudaStreamSynchronize(st));
     uint32_t *run_start = m.u32[10].ensure((uint64_t)n_runs + 2);
-    mzflt_runstart_kernel<<<nblk(n), TPB, 0, st>>>(n, head, run_incl, run_start, n_runs);
-    fill_u32_kernel<<<nblk(n), TPB, 0, st>>>(n, keep, 1u);
-    mzflt_mark_kernel<<<nblk(n), TPB, 0, st>>>(n, run_incl, run_start, sq, sidx, qs.mz_off.p, opt.mid_occ, opt.q_occ_frac, keep);
+    ++g_seed_launches, mzflt_runstart_kernel<<<nblk(n), TPB, 0, st>>>(n, head, run_incl, run_start, n_runs);
+    ++g_seed_launches, fill_u32_kernel<<<nblk(n), TPB, 0, st>>>(n, keep, 1u);
+    ++g_seed_launches, mzflt_mark_kernel<<<nblk(n), TPB, 0, st>>>(n, run_incl, run_start, sq, sidx, qs.mz_off.p, opt.mid_occ, opt.q_occ_frac, keep);
     PGMM_CUDA(cudaGetLastError());
     const uint64_t n_keep = m.scan_flags(keep, kpos, n, st);
     if (n_keep != n) {
       uint64_t *cx = m.u64[2].ensure(n_keep + 1), *cy = m.u64[3].ensure(n_keep + 1), *c_off = m.u64[4].ensure(nq + 2);
-      compact_mz_kernel<<<nblk(n), TPB, 0, st>>>(n, keep, kpos, qs.mx.p, qs.my.p, cx, cy);
-      remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, qs.mz_off.p, kpos, n, n_keep, c_off);
+      ++g_seed_launches, compact_mz_kernel<<<nblk(n), TPB, 0, st>>>(n, keep, kpos, qs.mx.p, qs.my.p, cx, cy);
+      ++g_seed_launches, remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, qs.mz_off.p, kpos, n, n_keep, c_off);
       fx = cx, fy = cy, f_off = c_off, n = n_keep;
       if (n == 0) return;
     }
@@ -619,20 +621,20 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
   // ---- index probe and seed list (seed.c:30-52) ----
   uint32_t *s_n = m.u32[0].ensure(n), *s_off = m.u32[1].ensure(n), *s_tandem = m.u32[2].ensure(n), *s_has = m.u32[3].ensure(n);
   uint32_t *spos = m.u32[4].ensure(n);
-  lookup_kernel<<<nblk(n), TPB, 0, st>>>(n, fx, fy, f_off, idx.keys.p, idx.n_keys, idx.key_off.p, s_n, s_off, s_tandem, s_has);
+  ++g_seed_launches, lookup_kernel<<<nblk(n), TPB, 0, st>>>(n, fx, fy, f_off, idx.keys.p, idx.n_keys, idx.key_off.p, s_n, s_off, s_tandem, s_has);
   PGMM_CUDA(cudaGetLastError());
   const uint64_t n_seed = m.scan_flags(s_has, spos, n, st);
   if (n_seed == 0) return;
   Seed *seeds = m.seeds.ensure(n_seed);
   uint64_t *sd_off = m.u64[5].ensure(nq + 2);
-  compact_seed_kernel<<<nblk(n), TPB, 0, st>>>(n, s_has, spos, s_n, s_off, s_tandem, fx, fy, seeds);
-  remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, f_off, spos, n, n_seed, sd_off);
+  ++g_seed_launches, compact_seed_kernel<<<nblk(n), TPB, 0, st>>>(n, s_has, spos, s_n, s_off, s_tandem, fx, fy, seeds);
+  ++g_seed_launches, remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, f_off, spos, n, n_seed, sd_off);
 
   // ---- high-occurrence thinning (seed.c:56-96,105-112) ----
   const int streak_mode = opt.occ_dist > 0 && opt.max_max_occ > opt.mid_occ;
-  seed_select_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, sd_off, qs.lens.p, opt.mid_occ, opt.max_max_occ, opt.occ_dist, streak_mode);
+  ++g_seed_launches, seed_select_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, sd_off, qs.lens.p, opt.mid_occ, opt.max_max_occ, opt.occ_dist, streak_mode);
   uint32_t *used = m.u32[5].ensure(n_seed), *flt = m.u32[6].ensure(n_seed), *upos = m.u32[7].ensure(n_seed), *fpos = m.u32[8].ensure(n_seed);
-  seed_flags_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, used, flt);
+  ++g_seed_launches, seed_flags_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, used, flt);
   PGMM_CUDA(cudaGetLastError());
   const uint64_t n_used = m.scan_flags(used, upos, n_seed, st);
   const uint64_t n_flt = m.scan_flags(flt, fpos, n_seed, st);
@@ -642,8 +644,8 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
   PGMM_CUDA(cudaMemsetAsync(rep_len, 0, (nq + 1) * 4, st));
   if (n_flt > 0) {
     Seed *flts = m.flts.ensure(n_flt);
-    compact_flt_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, flt, fpos, flts);
-    rep_len_kernel<<<nblk(n_flt), TPB, 0, st>>>(n_flt, flts, rep_len);
+    ++g_seed_launches, compact_flt_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, flt, fpos, flts);
+    ++g_seed_launches, rep_len_kernel<<<nblk(n_flt), TPB, 0, st>>>(n_flt, flts, rep_len);
   }
   std::vector<int32_t> h_rep(nq + 1, 0);
   PGMM_CUDA(cudaMemcpyAsync(h_rep.data(), rep_len, nq * 4, cudaMemcpyDeviceToHost, st));
@@ -656,8 +658,8 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     Seed *useds = m.useds.ensure(n_used);
     uint64_t *mini_pos = m.u64[6].ensure(n_used), *u_off = m.u64[7].ensure(nq + 2), *a_off = m.u64[8].ensure(n_used + 1);
     uint32_t *u_n = m.u32[9].ensure(n_used + 1);
-    compact_used_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, used, upos, useds, mini_pos, u_n);
-    remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, sd_off, upos, n_seed, n_used, u_off);
+    ++g_seed_launches, compact_used_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, used, upos, useds, mini_pos, u_n);
+    ++g_seed_launches, remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, sd_off, upos, n_seed, n_used, u_off);
     PGMM_CUDA(cudaMemsetAsync(u_n + n_used, 0, 4, st));
     m.excl_sum(u_n, a_off, n_used + 1, st);
     uint64_t n_slots = 0;
@@ -670,17 +672,17 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     if (n_slots > 0) {
       uint64_t *ax = m.u64[0].ensure(n_slots), *ay = m.u64[1].ensure(n_slots), *q_slot = m.u64[9].ensure(nq + 2);
       uint32_t *akeep = m.u32[10].ensure(n_slots), *apos = m.u32[11].ensure(n_slots);
-      anchor_kernel<<<nblk(n_slots), TPB, 0, st>>>(n_slots, n_used, useds, a_off, idx.pos.p, qs.lens.p, m.q_rank.p, idx.name_rank.p,
+      ++g_seed_launches, anchor_kernel<<<nblk(n_slots), TPB, 0, st>>>(n_slots, n_used, useds, a_off, idx.pos.p, qs.lens.p, m.q_rank.p, idx.name_rank.p,
                                                    idx.seq_len.p, opt.flag, ax, ay, akeep);
-      query_slot_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, u_off, a_off, n_used, n_slots, q_slot);
+      ++g_seed_launches, query_slot_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, u_off, a_off, n_used, n_slots, q_slot);
       PGMM_CUDA(cudaGetLastError());
       const uint64_t n_anchor = m.scan_flags(akeep, apos, n_slots, st);
       uint64_t *qa_off = m.u64[2].ensure(nq + 2);
-      remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, q_slot, apos, n_slots, n_anchor, qa_off);
+      ++g_seed_launches, remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, q_slot, apos, n_slots, n_anchor, qa_off);
       PGMM_CUDA(cudaMemcpyAsync(h_a_off.data(), qa_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
       if (n_anchor > 0) {
         U128 *anchors = m.anchors.ensure(n_anchor);
-        compact_anchor_kernel<<<nblk(n_slots), TPB, 0, st>>>(n_slots, akeep, apos, ax, ay, anchors);
+        ++g_seed_launches, compact_anchor_kernel<<<nblk(n_slots), TPB, 0, st>>>(n_slots, akeep, apos, ax, ay, anchors);
         h_anchors.resize(n_anchor);
         PGMM_CUDA(cudaMemcpyAsync(h_anchors.data(), anchors, n_anchor * sizeof(U128), cudaMemcpyDeviceToHost, st));
       }

@@ -14,6 +14,8 @@
 
 namespace pgmm {
 
+extern uint64_t g_seed_launches;  // kernels launched by the sketch / index / seeding stages (ours + CUB)
+
 // A set of sequences whose coded bases (0..4) sit in one device buffer, plus their minimizers.
 struct DeviceSeqSet {
   int n = 0;
