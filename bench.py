@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Benchmark of the alignment hot path of `pangraph build` (BASELINE.json metric: Gbp aligned / s).
 
-One STEP = one find_matches round of a guide-tree leaf merge: two related synthetic 5-Mbp genomes (1 % divergence,
+One ROUND = one find_matches call of a guide-tree leaf merge: two related synthetic 5-Mbp genomes (1 % divergence,
 10 rearrangements each) are indexed and aligned all-vs-all, i.e. mm_idx_str + mm_mapopt_update + one
-mm_map per sequence in the reference, index kernels + pgmm_map_batch here.  bp per step = sum of the two lengths.
+mm_map per sequence in the reference, index kernels + pgmm_map_batch here.
+One STEP = `--rounds-per-step` (default 8) such rounds: sibling leaf merges of the guide tree are independent
+(merge_graphs only reads its two children), so a rank keeps several of them in flight, one host thread and one CUDA
+stream each.  bp per step = total length of the genomes of its rounds.
 
   python bench.py [--gpus N --steps K --warmup W]        our CUDA path (N>1: one rank per GPU under torchrun; every
                                                           rank aligns its own pairs -- leaf merges are independent --
@@ -100,12 +103,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference_round(refmm2, seqs, names, threads):
-    idx = refmm2.Index(refmm2.load_ref(), seqs, names, "asm10", None, 90)
+def run_reference_step(refmm2, rounds, threads):
+    """The reference's path for every round of a step: index, mid_occ, then one mm_map per query; the queries of all
+    rounds share one pool of `threads` host threads (ctypes drops the GIL inside the C calls)."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib = refmm2.load_ref()
+    idxs = [refmm2.Index(lib, seqs, names, "asm10", None, 90) for seqs, names in rounds]
     try:
-        return idx.map_all(threads)
+        work = [(ix, i) for ix in idxs for i in range(len(ix.seqs))]
+        with ThreadPoolExecutor(max(1, threads)) as ex:
+            return list(ex.map(lambda t: len(t[0].map_one(t[1])), work))
     finally:
-        idx.close()
+        for ix in idxs:
+            ix.close()
 
 
 def reference_arm(args):
@@ -117,29 +127,30 @@ def reference_arm(args):
         return 0
     from oracle import refmm2
     cores = os.cpu_count() or 1
-    pairs = make_pairs(min(args.steps + args.warmup, 2), 0, args.genome_len)
+    P = args.rounds_per_step
+    pairs = make_pairs(P, 0, args.genome_len)
     sample = args.ref_sample_len
+    rounds = [([x[:sample] for x in seqs], names) for seqs, names in pairs]
+    threads = min(cores, 2 * P)
     times, bp = [], 0
     for s in range(args.warmup + args.steps):
-        seqs, names = pairs[s % len(pairs)]
-        seqs = [x[:sample] for x in seqs]
         t0 = time.perf_counter()
-        run_reference_round(refmm2, seqs, names, min(cores, len(seqs)))
+        run_reference_step(refmm2, rounds, threads)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             times.append(dt)
-            bp += sum(len(x) for x in seqs)
+            bp += sum(len(x) for seqs, _ in rounds for x in seqs)
     total = sum(times)
     value = bp / total / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8/int32 (SSE2 lanes)", "data": "synthetic",
-        "config": {"workload": f"leaf-merge alignment round, 2 x {args.genome_len} bp synthetic genomes at 1% divergence, "
-                               f"10 rearrangements (asm10, k=19 w=19)", "sample": f"first {sample} bp of each genome"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, 2), "kind": "reference",
-                         "sample": f"first {sample} bp of each genome of the pair; one mm_map per sequence on its own thread "
-                                   f"({cores} host cores available; a leaf round has only 2 queries)"},
+        "config": {"workload": f"{P} leaf-merge alignment rounds per step, each 2 x {args.genome_len} bp synthetic genomes at 1% "
+                               f"divergence, 10 rearrangements (asm10, k=19 w=19)", "sample": f"first {sample} bp of each genome"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": f"first {sample} bp of each genome of the {P} pairs of a step; the {2 * P} mm_map calls of a step "
+                                   f"share {threads} host threads ({cores} cores available)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -183,9 +194,15 @@ def ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = abi.lib()
-    n_pool = min(args.steps + args.warmup, args.pool)
+    from concurrent.futures import ThreadPoolExecutor
+    P = args.rounds_per_step
+    n_pool = max(P, args.pool)
     pairs = make_pairs(n_pool, rank * n_pool, args.genome_len)
-    bp_step = [sum(len(x) for x in seqs) for seqs, _ in pairs]
+    bp_pair = [sum(len(x) for x in seqs) for seqs, _ in pairs]
+    pool = ThreadPoolExecutor(P)
+
+    def pairs_of_step(s):
+        return [(s * P + j) % n_pool for j in range(P)]
 
     def gather_matches(n_regs, regs):
         """NCCL: variable-length match lists of every rank -> rank 0 (sizes first, then padded payloads)."""
@@ -202,24 +219,33 @@ def ours(args):
         dst = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
         dist.gather(buf, dst, dst=0)
 
-    def step_e2e(p):
-        seqs, names = pairs[p % n_pool]
+    def round_e2e(p):
+        seqs, names = pairs[p]
         idx = abi.Index(seqs, names, "asm10", None, 90)  # mm_idx_str + mm_mapopt_update (host buffers)
         n = len(seqs)
         sa, na = (C.c_char_p * n)(*idx.seqs), (C.c_char_p * n)(*idx.names)
         lens = (C.c_int * n)(*[len(s) for s in idx.seqs])
         n_regs, regs = (C.c_int * n)(), (C.POINTER(abi.mm_reg1_t) * n)()
         L.pgmm_map_batch(idx.mi, n, lens, sa, na, C.byref(idx.mo), n_regs, regs)
-        gather_matches(n_regs, regs)
-        hits = free_regs(abi, n_regs, regs)
         idx.close()
+        return n_regs, regs
+
+    def round_resident(idx):
+        idx.build()
+        return idx.map_self(raw=True)
+
+    def finish(results):
+        hits = 0
+        for n_regs, regs in results:  # rank 0 receives the match lists in round order
+            gather_matches(n_regs, regs)
+            hits += free_regs(abi, n_regs, regs)
         return hits
 
-    def step_resident(idx):
-        idx.build()
-        n_regs, regs = idx.map_self(raw=True)
-        gather_matches(n_regs, regs)
-        return free_regs(abi, n_regs, regs)
+    def step_e2e(s):
+        return finish(list(pool.map(round_e2e, pairs_of_step(s))))
+
+    def step_resident(idxs):
+        return finish(list(pool.map(round_resident, idxs)))
 
     def sync():
         torch.cuda.synchronize()
@@ -250,18 +276,20 @@ def ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
 
     # ---- value: inputs resident in HBM ----
-    resident = [abi.Index(*pairs[(args.warmup + s) % n_pool], "asm10", None, 90, resident_only=True) for s in range(args.steps)]
+    resident = [[abi.Index(*pairs[p], "asm10", None, 90, resident_only=True) for p in pairs_of_step(args.warmup + s)]
+                for s in range(args.steps)]
     abi.get_stats(reset=True)
     t_res, hits_res = timed(step_resident, resident)
     st_res = abi.get_stats(reset=True)
-    for idx in resident:
-        idx.close()
+    for idxs in resident:
+        for idx in idxs:
+            idx.close()
     # ---- e2e: host buffers through the C-ABI ----
     t_e2e, hits_e2e = timed(step_e2e, [args.warmup + s for s in range(args.steps)])
     st_e2e = abi.get_stats(reset=True)
     clocks = sampler.stop() if sampler else None
 
-    bp_rank = sum(bp_step[(args.warmup + s) % n_pool] for s in range(args.steps))
+    bp_rank = sum(bp_pair[p] for s in range(args.steps) for p in pairs_of_step(args.warmup + s))
     bp_all = torch.tensor([bp_rank], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(bp_all)
@@ -271,15 +299,16 @@ def ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import refmm2
         if os.path.exists(refmm2.REF_SO):
-            seqs, names = pairs[0]
             sample = args.ref_sample_len
-            sseqs = [x[:sample] for x in seqs]
+            rounds = [([x[:sample] for x in pairs[p][0]], pairs[p][1]) for p in pairs_of_step(0)]
+            threads = min(os.cpu_count() or 1, 2 * P)
             t0 = time.perf_counter()
-            run_reference_round(refmm2, sseqs, names, 2)
+            run_reference_step(refmm2, rounds, threads)
             dt = time.perf_counter() - t0
-            cpu_baseline = {"value": sum(len(x) for x in sseqs) / dt / 1e9, "unit": UNIT, "cores": 2, "kind": "reference",
-                            "sample": f"first {sample} bp of each genome of pair 0 ({dt:.1f} s; one mm_map per sequence on its own "
-                                      f"thread, {os.cpu_count()} host cores available)"}
+            cpu_baseline = {"value": sum(len(x) for r in rounds for x in r[0]) / dt / 1e9, "unit": UNIT, "cores": threads,
+                            "kind": "reference",
+                            "sample": f"one step on the first {sample} bp of each genome ({dt:.1f} s; the {2 * P} mm_map calls share "
+                                      f"{threads} host threads, {os.cpu_count()} cores available)"}
     if rank == 0:
         peak, peak_src = measured_peaks()
         ker_s = st_res["dp_kernel_ms"] / 1e3
@@ -289,10 +318,10 @@ def ours(args):
             "metric": METRIC, "value": bp_total / t_res / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8x4 (DP) / u64 (seeding)", "data": "synthetic",
-            "config": {"workload": f"leaf-merge alignment round, 2 x {args.genome_len} bp synthetic genomes at 1% divergence, "
-                                   f"10 rearrangements (asm10, k=19 w=19); one pair per rank per step",
-                       "l2": "working set > L2: a new genome pair every step, ~1 GB of traceback written per round",
-                       "hits_per_round": hits_res / max(1, args.steps), "host_threads": os.cpu_count()},
+            "config": {"workload": f"{P} leaf-merge alignment rounds per rank per step, each 2 x {args.genome_len} bp synthetic genomes "
+                                   f"at 1% divergence, 10 rearrangements (asm10, k=19 w=19)",
+                       "l2": "working set > L2: distinct genome pairs in every round, > 1 GB of traceback written per round",
+                       "rounds_per_step": P, "hits_per_round": hits_res / max(1, args.steps * P), "host_threads": os.cpu_count()},
             "e2e": {"value": bp_total / t_e2e / 1e9, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
             "gpu_launches": int(st_res["launches"]),
@@ -302,10 +331,10 @@ def ours(args):
                          "note": "integer-issue bound kernel (about 50 int8-lane ops per cell); HBM fraction is small by construction"},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
-            "phases_ms_per_step": {k: st_res[k] / args.steps for k in ("index_ms", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch",
+            "phases_ms_per_round": {k: st_res[k] / (args.steps * P) for k in ("index_ms", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch",
                                                                        "t_final", "dp_kernel_ms", "total_ms")},
-            "dp": {"jobs_per_step": st_res["dp_jobs"] / args.steps, "cells_per_step": st_res["dp_cells"] / args.steps,
-                   "waves_per_step": st_res["dp_waves"] / args.steps},
+            "dp": {"jobs_per_round": st_res["dp_jobs"] / (args.steps * P), "cells_per_round": st_res["dp_cells"] / (args.steps * P),
+                   "waves_per_round": st_res["dp_waves"] / (args.steps * P)},
         }
         print(json.dumps(line))
     if dist is not None:
@@ -316,11 +345,12 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--pool", type=int, default=4, help="distinct genome pairs generated per rank (steps cycle through them)")
+    ap.add_argument("--rounds-per-step", type=int, default=8, help="independent leaf-merge rounds a rank keeps in flight per step")
+    ap.add_argument("--pool", type=int, default=8, help="distinct genome pairs generated per rank (steps cycle through them)")
     ap.add_argument("--ref-sample-len", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -415,6 +415,8 @@ KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
 }
 
 struct KswEngine::Impl {
+  cudaStream_t cls_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, fork = nullptr;
   DevBuf<KswJob> d_jobs;
   DevBuf<int> d_ids;
   DevBuf<KswOut> d_outs;
@@ -427,10 +429,17 @@ struct KswEngine::Impl {
 KswEngine::KswEngine() : impl_(new Impl) {
   PGMM_CUDA(cudaEventCreate(&impl_->ev0));
   PGMM_CUDA(cudaEventCreate(&impl_->ev1));
+  PGMM_CUDA(cudaEventCreateWithFlags(&impl_->fork, cudaEventDisableTiming));
+  for (int c = 0; c < 5; ++c) {
+    PGMM_CUDA(cudaStreamCreateWithFlags(&impl_->cls_stream[c], cudaStreamNonBlocking));
+    PGMM_CUDA(cudaEventCreateWithFlags(&impl_->cls_done[c], cudaEventDisableTiming));
+  }
 }
 KswEngine::~KswEngine() {
   cudaEventDestroy(impl_->ev0);
   cudaEventDestroy(impl_->ev1);
+  cudaEventDestroy(impl_->fork);
+  for (int c = 0; c < 5; ++c) cudaStreamDestroy(impl_->cls_stream[c]), cudaEventDestroy(impl_->cls_done[c]);
   delete impl_;
 }
 
@@ -502,11 +511,23 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, jobs.data(), n * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
     PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     PGMM_CUDA(cudaEventRecord(m.ev0, stream));
-    launch_class<32>(cls[0], cls_smem[0], m.d_ids.p, cls_off[0], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
-    launch_class<64>(cls[1], cls_smem[1], m.d_ids.p, cls_off[1], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
-    launch_class<128>(cls[2], cls_smem[2], m.d_ids.p, cls_off[2], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
-    launch_class<256>(cls[3], cls_smem[3], m.d_ids.p, cls_off[3], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
-    launch_class<256>(cls[4], 0, m.d_ids.p, cls_off[4], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, stream);
+    // the size classes are independent launches: fork them onto their own streams so that the few long problems of the
+    // large classes overlap with the many short ones instead of queueing behind each other
+    PGMM_CUDA(cudaEventRecord(m.fork, stream));
+    for (int c = 0; c < 5; ++c) {
+      if (cls[c].empty()) continue;
+      cudaStream_t cs = m.cls_stream[c];
+      PGMM_CUDA(cudaStreamWaitEvent(cs, m.fork, 0));
+      switch (c) {
+        case 0: launch_class<32>(cls[0], cls_smem[0], m.d_ids.p, cls_off[0], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
+        case 1: launch_class<64>(cls[1], cls_smem[1], m.d_ids.p, cls_off[1], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
+        case 2: launch_class<128>(cls[2], cls_smem[2], m.d_ids.p, cls_off[2], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
+        case 3: launch_class<256>(cls[3], cls_smem[3], m.d_ids.p, cls_off[3], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
+        default: launch_class<256>(cls[4], 0, m.d_ids.p, cls_off[4], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
+      }
+      PGMM_CUDA(cudaEventRecord(m.cls_done[c], cs));
+      PGMM_CUDA(cudaStreamWaitEvent(stream, m.cls_done[c], 0));
+    }
     PGMM_CUDA(cudaEventRecord(m.ev1, stream));
     for (int c = 0; c < 5; ++c) res.launches += !cls[c].empty();
 

@@ -32,28 +32,56 @@ const uint8_t kNt4[256] = {
 #undef R4
 };
 
-void encode_queries(QueryBatch &qb, const TargetSet &ts) {
+static void parallel_chunks(uint64_t total, int n_threads, const std::function<void(uint64_t, uint64_t)> &fn) {
+  const uint64_t kChunk = 1 << 20;
+  const uint64_t n_chunks = (total + kChunk - 1) / kChunk;
+  if (n_threads <= 1 || n_chunks <= 1) {
+    fn(0, total);
+    return;
+  }
+  std::atomic<uint64_t> next(0);
+  std::vector<std::thread> th;
+  const int nt = (int)std::min<uint64_t>(n_chunks, (uint64_t)n_threads);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        const uint64_t c = next.fetch_add(1);
+        if (c >= n_chunks) break;
+        fn(c * kChunk, std::min(total, (c + 1) * kChunk));
+      }
+    });
+  for (auto &t : th) t.join();
+}
+
+void encode_queries(QueryBatch &qb, const TargetSet &ts, int n_threads) {
   qb.base.resize(qb.n);
   uint64_t tot = 0;
-  for (int i = 0; i < qb.n; ++i) qb.base[i] = tot, tot += 2ull * qb.lens[i];
+  std::vector<uint64_t> vstart(qb.n + 1, 0);
+  for (int i = 0; i < qb.n; ++i) qb.base[i] = tot, tot += 2ull * qb.lens[i], vstart[i + 1] = vstart[i] + (uint64_t)qb.lens[i];
   qb.codes.resize(tot + 16);
-  for (int i = 0; i < qb.n; ++i) {  // align.c:969-975
-    const int L = qb.lens[i];
-    uint8_t *f = qb.codes.data() + qb.base[i], *r = f + L;
-    if (qb.from_targets) {
-      const uint8_t *s = ts.codes.data() + ts.offs[i];
-      for (int j = 0; j < L; ++j) {
-        const uint8_t c = s[j];
-        f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
+  // forward codes and their reverse complement per query (align.c:969-975), chunked over all bases of the batch
+  parallel_chunks(vstart[qb.n], n_threads, [&](uint64_t lo, uint64_t hi) {
+    int i = (int)(std::upper_bound(vstart.begin(), vstart.end(), lo) - vstart.begin()) - 1;
+    for (uint64_t p = lo; p < hi;) {
+      while (vstart[i + 1] <= p) ++i;
+      const uint64_t L = (uint64_t)qb.lens[i], j0 = p - vstart[i], j1 = std::min(L, hi - vstart[i]);
+      uint8_t *f = qb.codes.data() + qb.base[i], *r = f + L;
+      if (qb.from_targets) {
+        const uint8_t *s = ts.codes.data() + ts.offs[i];
+        for (uint64_t j = j0; j < j1; ++j) {
+          const uint8_t c = s[j];
+          f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
+        }
+      } else {
+        const uint8_t *s = (const uint8_t *)qb.seqs[i];
+        for (uint64_t j = j0; j < j1; ++j) {
+          const uint8_t c = kNt4[s[j]];
+          f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
+        }
       }
-    } else {
-      const uint8_t *s = (const uint8_t *)qb.seqs[i];
-      for (int j = 0; j < L; ++j) {
-        const uint8_t c = kNt4[s[j]];
-        f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
-      }
+      p = vstart[i] + j1;
     }
-  }
+  });
 }
 
 namespace {
@@ -1152,7 +1180,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
   };
   double t0 = now(), t1;
-  encode_queries(qb, ts);
+  encode_queries(qb, ts, n_threads);
   t1 = now(), be.stats.t_encode += t1 - t0, t0 = t1;
   be.begin_batch(ts, qb);
   std::vector<QuerySeeds> seeds;

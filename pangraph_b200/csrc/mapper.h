@@ -71,7 +71,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
 
 // ASCII -> 0..4 (A,C,G,T/U in either case -> 0..3, everything else 4; sketch.c:9-26)
 extern const uint8_t kNt4[256];
-void encode_queries(QueryBatch &qb, const TargetSet &ts);
+void encode_queries(QueryBatch &qb, const TargetSet &ts, int n_threads);
 
 // --- pieces exposed for stage-level tests ---
 int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -33,22 +34,76 @@ double now_ms() {
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-// Everything that hangs off mm_idx_t::h
+// Everything that hangs off mm_idx_t::h: read-only once built, so any number of mapping calls may share it
 struct PgmmIndex {
   TargetSet ts;
   DeviceIndex didx;
   DevBuf<uint8_t> d_tcodes;
   std::vector<std::string> sorted_names;  // distinct target names in strcmp order
   std::vector<int32_t> t_rank;
+};
+
+// One execution context = one CUDA stream + the engines' workspaces.  Calls check a context out for their duration;
+// concurrent callers (the reference maps queries from a rayon pool, one mm_tbuf_t each) run on different streams.
+struct DeviceCtx {
   SeedEngine seeder;
   KswEngine ksw;
   DevBuf<uint8_t> d_qcodes;
   DeviceSeqSet qset;
   cudaStream_t stream = nullptr;
-  std::mutex mu;  // one batch at a time per index: concurrent mm_map callers queue here
-  ~PgmmIndex() {
-    if (stream) cudaStreamDestroy(stream);
+  DeviceCtx() {
+    PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const char *e = getenv("PGMM_ARENA_GB");
+    const double gb = e ? atof(e) : 8.0;
+    ksw.arena_budget_bytes = (size_t)(gb * (1ull << 30));
   }
+};
+class CtxPool {
+ public:
+  static CtxPool &get() {
+    static CtxPool *p = new CtxPool;
+    return *p;
+  }
+  DeviceCtx *acquire() {
+    std::unique_lock<std::mutex> g(mu_);
+    for (;;) {
+      if (!idle_.empty()) {
+        DeviceCtx *c = idle_.back();
+        idle_.pop_back();
+        return c;
+      }
+      if (n_ < max_) {
+        ++n_;
+        g.unlock();
+        return new DeviceCtx;
+      }
+      cv_.wait(g);
+    }
+  }
+  void release(DeviceCtx *c) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      idle_.push_back(c);
+    }
+    cv_.notify_one();
+  }
+
+ private:
+  CtxPool() {
+    const char *e = getenv("PGMM_CONTEXTS");
+    max_ = e ? atoi(e) : 8;
+    if (max_ < 1) max_ = 1;
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::vector<DeviceCtx *> idle_;
+  int n_ = 0, max_ = 8;
+};
+struct CtxLease {
+  DeviceCtx *c;
+  CtxLease() : c(CtxPool::get().acquire()) {}
+  ~CtxLease() { CtxPool::get().release(c); }
+  DeviceCtx *operator->() { return c; }
 };
 
 int host_threads() {
@@ -89,33 +144,34 @@ __global__ void self_query_kernel(const uint8_t *__restrict__ tcodes, const uint
 
 struct CudaBackend : Backend {
   PgmmIndex &ix;
-  explicit CudaBackend(PgmmIndex &i) : ix(i) {}
+  DeviceCtx &cx;
+  CudaBackend(PgmmIndex &i, DeviceCtx &c) : ix(i), cx(c) {}
   double t_seed = 0;
   void begin_batch(const TargetSet &ts, const QueryBatch &qb) override {
     const size_t nbytes = qb.codes.size();
-    ix.d_qcodes.ensure(nbytes + 64);
+    cx.d_qcodes.ensure(nbytes + 64);
     if (qb.from_targets) {  // nothing crosses the bus: the query buffer is derived from the resident target codes
       const DeviceSeqSet &s = ix.didx.seqs;
       if (s.total > 0)
-        self_query_kernel<<<(unsigned)((s.total + 255) / 256), 256, 0, ix.stream>>>(ix.d_tcodes.p, s.starts.p, s.vstart.p, s.n, s.total, ix.d_qcodes.p);
+        self_query_kernel<<<(unsigned)((s.total + 255) / 256), 256, 0, cx.stream>>>(ix.d_tcodes.p, s.starts.p, s.vstart.p, s.n, s.total, cx.d_qcodes.p);
       PGMM_CUDA(cudaGetLastError());
       ++g_seed_launches;
       (void)ts;
-    } else PGMM_CUDA(cudaMemcpyAsync(ix.d_qcodes.p, qb.codes.data(), nbytes, cudaMemcpyHostToDevice, ix.stream));
+    } else PGMM_CUDA(cudaMemcpyAsync(cx.d_qcodes.p, qb.codes.data(), nbytes, cudaMemcpyHostToDevice, cx.stream));
   }
   void seed_batch(const TargetSet &ts, const QueryBatch &qb, const mm_mapopt_t &opt, std::vector<QuerySeeds> &out) override {
     const double t0 = now_ms();
     std::vector<uint64_t> starts(qb.base.begin(), qb.base.end());
     std::vector<int> lens(qb.lens.begin(), qb.lens.end());
-    ix.seeder.sketch(ix.d_qcodes.p, starts, lens, ts.w, ts.k, ix.qset, ix.stream);
+    cx.seeder.sketch(cx.d_qcodes.p, starts, lens, ts.w, ts.k, cx.qset, cx.stream);
     std::vector<int32_t> q_rank(qb.n);
     // skip_seed only looks at names when the query has one (map.c:81): INT32_MIN marks "no name"
     for (int i = 0; i < qb.n; ++i) q_rank[i] = qb.names[i] ? rank_of(ix.sorted_names, qb.names[i]) : INT32_MIN;
-    ix.seeder.collect(ix.didx, ix.qset, q_rank, opt, out, ix.stream);
+    cx.seeder.collect(ix.didx, cx.qset, q_rank, opt, out, cx.stream);
     t_seed += now_ms() - t0;
   }
   void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) override {
-    ix.ksw.run(jobs, ix.d_qcodes.p, ix.d_tcodes.p, sc, res, ix.stream);
+    cx.ksw.run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res, cx.stream);
   }
 };
 
@@ -124,7 +180,7 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   require_device();
   PgmmIndex *ix = (PgmmIndex *)mi->h;
   if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200 (no device index attached)");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  CtxLease cx;
   const double t0 = now_ms();
   QueryBatch qb;
   std::vector<int> self_lens;
@@ -143,7 +199,7 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   }
   qb.n = n;
   qb.lens.assign(lens, lens + n);
-  CudaBackend be(*ix);
+  CudaBackend be(*ix, *cx.c);
   map_batch(be, ix->ts, qb, *opt, n_regs, regs, host_threads());
   std::lock_guard<std::mutex> sl(g_stats_mu);
   g_stats.total_ms += now_ms() - t0, g_stats.seed_ms += be.t_seed, g_stats.dp_kernel_ms += be.stats.kernel_ms;
@@ -167,7 +223,7 @@ mm_idx_t *pgmm_idx_upload(int n, const char **seq, const char **name) {
   mi->seq = (mm_idx_seq_t *)calloc((size_t)n, sizeof(mm_idx_seq_t));
   PgmmIndex *ix = new PgmmIndex;
   mi->h = ix;
-  PGMM_CUDA(cudaStreamCreate(&ix->stream));
+  CtxLease cx;
   TargetSet &ts = ix->ts;
   uint64_t sum = 0;
   for (int i = 0; i < n; ++i) {
@@ -194,21 +250,21 @@ mm_idx_t *pgmm_idx_upload(int n, const char **seq, const char **name) {
     for (auto &t : th) t.join();
   }
   ix->d_tcodes.ensure(sum + 64);
-  PGMM_CUDA(cudaMemcpyAsync(ix->d_tcodes.p, ts.codes.data(), sum, cudaMemcpyHostToDevice, ix->stream));
+  PGMM_CUDA(cudaMemcpyAsync(ix->d_tcodes.p, ts.codes.data(), sum, cudaMemcpyHostToDevice, cx->stream));
   // name ranks for the all-vs-all skips
   ix->sorted_names = ts.names;
   std::sort(ix->sorted_names.begin(), ix->sorted_names.end(), [](const std::string &a, const std::string &b) { return strcmp(a.c_str(), b.c_str()) < 0; });
   ix->sorted_names.erase(std::unique(ix->sorted_names.begin(), ix->sorted_names.end()), ix->sorted_names.end());
   ix->t_rank.resize(n);
   for (int i = 0; i < n; ++i) ix->t_rank[i] = rank_of(ix->sorted_names, ts.names[i].c_str());
-  PGMM_CUDA(cudaStreamSynchronize(ix->stream));
+  PGMM_CUDA(cudaStreamSynchronize(cx->stream));
   return mi;
 }
 
 void pgmm_idx_build(mm_idx_t *mi, int w, int k, int bucket_bits) {
   PgmmIndex *ix = (PgmmIndex *)mi->h;
   if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  CtxLease cx;
   const double t0 = now_ms();
   if (bucket_bits < 0) bucket_bits = 14;
   if (k * 2 < bucket_bits) bucket_bits = k * 2;
@@ -219,8 +275,8 @@ void pgmm_idx_build(mm_idx_t *mi, int w, int k, int bucket_bits) {
   // K1 + K2
   std::vector<int> lens(ts.lens.begin(), ts.lens.end());
   ix->didx.w = w, ix->didx.k = k;
-  ix->seeder.sketch(ix->d_tcodes.p, ts.offs, lens, w, k, ix->didx.seqs, ix->stream);
-  ix->seeder.build_index(ix->didx, ts.lens, ix->t_rank, ix->stream);
+  cx->seeder.sketch(ix->d_tcodes.p, ts.offs, lens, w, k, ix->didx.seqs, cx->stream);
+  cx->seeder.build_index(ix->didx, ts.lens, ix->t_rank, cx->stream);
   uint64_t sum = 0;
   for (uint32_t l : ts.lens) sum += l;
   std::lock_guard<std::mutex> sl(g_stats_mu);
@@ -244,8 +300,8 @@ void mm_mapopt_update(mm_mapopt_t *opt, const mm_idx_t *mi) {
   if (opt->mid_occ <= 0) {
     PgmmIndex *ix = (PgmmIndex *)mi->h;
     if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200");
-    std::lock_guard<std::mutex> lock(ix->mu);
-    opt->mid_occ = SeedEngine::cal_max_occ(ix->didx, opt->mid_occ_frac, ix->stream);
+    CtxLease cx;
+    opt->mid_occ = SeedEngine::cal_max_occ(ix->didx, opt->mid_occ_frac, cx->stream);
     if (opt->mid_occ < opt->min_mid_occ) opt->mid_occ = opt->min_mid_occ;
     if (opt->max_mid_occ > opt->min_mid_occ && opt->mid_occ > opt->max_mid_occ) opt->mid_occ = opt->max_mid_occ;
   }
@@ -337,15 +393,15 @@ int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *c
                        int64_t *out_n) {
   require_device();
   PgmmIndex *ix = (PgmmIndex *)mi->h;
-  std::lock_guard<std::mutex> lock(ix->mu);
+  CtxLease cx;
   QueryBatch qb;
   qb.n = n;
   qb.seqs.assign(seqs, seqs + n);
   if (names) qb.names.assign(names, names + n);
   else qb.names.assign(n, nullptr);
   qb.lens.assign(lens, lens + n);
-  encode_queries(qb, ix->ts);
-  CudaBackend be(*ix);
+  encode_queries(qb, ix->ts, host_threads());
+  CudaBackend be(*ix, *cx.c);
   be.begin_batch(ix->ts, qb);
   std::vector<QuerySeeds> out;
   be.seed_batch(ix->ts, qb, *opt, out);

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <map>
+#include <mutex>
 #include <vector>
 
 // CUDA failures abort with a message: the reference's C has no error channel either (SURVEY 8b "Errors").
@@ -42,26 +44,79 @@ inline cudaError_t counted_memcpy_async(void *dst, const void *src, size_t n, cu
   return cudaMemcpyAsync(dst, src, n, kind, st);
 }
 
-// Grow-only device buffer (cudaMallocAsync-free: plain cudaMalloc, reused across calls).
+// Process-wide cache of device allocations: freed blocks are kept per size class and handed out again, so that the
+// steady state of a build (index after index, round after round) never calls cudaMalloc/cudaFree.
+class DevicePool {
+ public:
+  static DevicePool &get() {
+    static DevicePool *p = new DevicePool;  // intentionally leaked: outlives every static DevBuf
+    return *p;
+  }
+  // size classes: 8 steps per power of two
+  static size_t size_class(size_t bytes) {
+    if (bytes < 4096) bytes = 4096;
+    size_t p2 = 4096;
+    while (p2 < bytes) p2 <<= 1;
+    const size_t step = p2 >> 4;  // p2/2 .. p2 in 8 steps
+    const size_t base = p2 >> 1;
+    return base + (bytes - base + step - 1) / step * step;
+  }
+  void *alloc(size_t cls) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = free_.find(cls);
+      if (it != free_.end() && !it->second.empty()) {
+        void *p = it->second.back();
+        it->second.pop_back();
+        return p;
+      }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cls);
+    if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
+      trim();
+      e = cudaMalloc(&p, cls);
+    }
+    if (e != cudaSuccess) PGMM_FATAL("cudaMalloc of %zu bytes failed: %s", cls, cudaGetErrorString(e));
+    return p;
+  }
+  void release(void *p, size_t cls) {
+    std::lock_guard<std::mutex> g(mu_);
+    free_[cls].push_back(p);
+  }
+  void trim() {
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto &kv : free_)
+      for (void *p : kv.second) cudaFree(p);
+    free_.clear();
+  }
+
+ private:
+  std::mutex mu_;
+  std::map<size_t, std::vector<void *>> free_;
+};
+
+// Grow-only device buffer backed by the pool.
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
-  size_t cap = 0;
+  size_t cap = 0;   // elements
+  size_t cls = 0;   // bytes of the pool block
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) DevicePool::get().release(p, cls);
     p = nullptr;
-    cap = 0;
+    cap = 0, cls = 0;
   }
   T *ensure(size_t n) {
     if (n > cap) {
       release();
-      size_t want = n + n / 4 + 64;
-      PGMM_CUDA(cudaMalloc((void **)&p, want * sizeof(T)));
-      cap = want;
+      cls = DevicePool::size_class((n + 64) * sizeof(T));
+      p = (T *)DevicePool::get().alloc(cls);
+      cap = cls / sizeof(T);
     }
     return p;
   }
