@@ -307,3 +307,105 @@ def sketch(seqs, w, k):
     if rc != 0:
         raise RuntimeError(f"pgmm_sketch -> {rc}")
     return [(x[int(off[i]):int(off[i + 1])].copy(), y[int(off[i]):int(off[i + 1])].copy()) for i in range(n)]
+
+
+# ---------------- host half of the path (include/pgmm_b200.h part 2) ----------------
+
+class pgmm_alignment_t(C.Structure):
+    _fields_ = [("qry_name", C.c_uint64), ("ref_name", C.c_uint64), ("qry_len", C.c_uint64), ("ref_len", C.c_uint64),
+                ("qry_start", C.c_uint64), ("qry_end", C.c_uint64), ("ref_start", C.c_uint64), ("ref_end", C.c_uint64),
+                ("matches", C.c_uint64), ("length", C.c_uint64), ("quality", C.c_uint64), ("reverse", C.c_int32),
+                ("has_divergence", C.c_int32), ("divergence", C.c_double), ("align", C.c_double), ("n_cigar", C.c_uint32),
+                ("cigar", C.POINTER(C.c_uint32))]
+
+
+class pgmm_alignment_args_t(C.Structure):
+    _fields_ = [("indel_len_threshold", C.c_uint64), ("alpha", C.c_double), ("beta", C.c_double),
+                ("sensitivity", C.c_uint64), ("kmer_length", C.c_int64)]
+
+
+_OPS = "MIDNSHP=XB"
+
+
+def alignment_args(indel_len_threshold=100, alpha=100.0, beta=10.0, sensitivity=10, kmer_length=None):
+    """AlignmentArgs of the reference (packages/pangraph/src/align/alignment_args.rs) with its defaults."""
+    return pgmm_alignment_args_t(indel_len_threshold, alpha, beta, sensitivity, kmer_length or 0)
+
+
+def _aln_to_c(a, keep):
+    cig = (C.c_uint32 * max(1, len(a["cigar"])))(*[(n << 4) | _OPS.index(op) for n, op in a["cigar"]])
+    keep.append(cig)
+    d = a.get("divergence")
+    return pgmm_alignment_t(a["qry"][0], a["ref"][0], a["qry"][1], a["ref"][1], a["qry"][2], a["qry"][3], a["ref"][2], a["ref"][3],
+                            a["matches"], a["length"], a["quality"], 1 if a["reverse"] else 0, 0 if d is None else 1,
+                            0.0 if d is None else d, a.get("align") or 0.0, len(a["cigar"]), C.cast(cig, C.POINTER(C.c_uint32)))
+
+
+def _aln_from_c(c):
+    return dict(qry=(c.qry_name, c.qry_len, c.qry_start, c.qry_end), ref=(c.ref_name, c.ref_len, c.ref_start, c.ref_end),
+                matches=c.matches, length=c.length, quality=c.quality, reverse=bool(c.reverse),
+                cigar=[(c.cigar[i] >> 4, _OPS[c.cigar[i] & 15]) for i in range(c.n_cigar)],
+                divergence=c.divergence if c.has_divergence else None, align=c.align)
+
+
+def _take_alns(out, n):
+    res = [_aln_from_c(out[i]) for i in range(n.value)]
+    lib().pgmm_alignments_free(out, n)
+    return res
+
+
+def split_matches(aln, args):
+    keep = []
+    c = _aln_to_c(aln, keep)
+    out, n = C.POINTER(pgmm_alignment_t)(), C.c_size_t(0)
+    rc = lib().pgmm_split_matches(C.byref(c), C.byref(args), C.byref(out), C.byref(n))
+    if rc != 0:
+        raise ValueError(f"split_matches: unexpected CIGAR operation ({rc})")
+    return _take_alns(out, n)
+
+
+def alignment_energy2(aln, args):
+    keep = []
+    c = _aln_to_c(aln, keep)
+    lib().pgmm_alignment_energy2.restype = C.c_double
+    return lib().pgmm_alignment_energy2(C.byref(c), C.byref(args))
+
+
+def filter_matches(alns, args):
+    keep = []
+    arr = (pgmm_alignment_t * max(1, len(alns)))(*[_aln_to_c(a, keep) for a in alns])
+    out, n = C.POINTER(pgmm_alignment_t)(), C.c_size_t(0)
+    lib().pgmm_filter_matches(arr, C.c_size_t(len(alns)), C.byref(args), C.byref(out), C.byref(n))
+    return _take_alns(out, n)
+
+
+def _blocks(blocks):
+    ids = list(blocks.keys())
+    n = len(ids)
+    seqs = [blocks[i] if isinstance(blocks[i], bytes) else blocks[i].encode() for i in ids]
+    return n, (C.c_uint64 * max(1, n))(*ids), (C.c_char_p * max(1, n))(*seqs), seqs
+
+
+def align_with_minimap2_lib(blocks, args):
+    """blocks: {block_id: consensus}; returns the Alignment list of one round
+    (packages/pangraph/src/align/minimap2_lib/align_with_minimap2_lib.rs:15-27)."""
+    n, ids, sa, keep = _blocks(blocks)
+    out, cnt = C.POINTER(pgmm_alignment_t)(), C.c_size_t(0)
+    rc = lib().pgmm_align_with_minimap2_lib(n, ids, sa, C.byref(args), C.byref(out), C.byref(cnt))
+    if rc == -1:
+        raise ValueError(f"Unknown sensitivity preset: {args.sensitivity}")
+    if rc != 0:
+        raise RuntimeError(f"align_with_minimap2_lib -> {rc}")
+    return _take_alns(out, cnt)
+
+
+def find_filtered_matches(blocks, args):
+    """find_matches + self-hit removal + split_matches + filter_matches (graph_merging.rs:95-121)."""
+    n, ids, sa, keep = _blocks(blocks)
+    out, cnt = C.POINTER(pgmm_alignment_t)(), C.c_size_t(0)
+    rc = lib().pgmm_find_filtered_matches(n, ids, sa, C.byref(args), C.byref(out), C.byref(cnt))
+    if rc == -1:
+        raise ValueError(f"Unknown sensitivity preset: {args.sensitivity}")
+    if rc != 0:
+        raise RuntimeError(f"find_filtered_matches -> {rc}")
+    return _take_alns(out, cnt)

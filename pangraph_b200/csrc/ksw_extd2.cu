@@ -154,8 +154,10 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
   volatile int32_t *stop = (int32_t *)&misc[65];
   if (tid == 0) *stop = 0;
 
+  int r_done = 0;
   for (int r = 0; r < n_row; ++r) {
     int st0, en0;
+    r_done = r;
     if (!band(r, qlen, tlen, w, st0, en0)) {  // :142-145
       ez.zdropped = 1;
       break;
@@ -373,6 +375,7 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
     KswOut o;
     o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t, o.mqe = ez.mqe, o.mqe_t = ez.mqe_t;
     o.mte = ez.mte, o.mte_q = ez.mte_q, o.score = ez.score, o.reach_end = ez.reach_end, o.n_cigar = n;
+    o.n_diag = r_done + 1;
     outs[jid] = o;
   }
 }
@@ -563,6 +566,15 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       ++res.launches;
     }
     pos = end;
+  }
+  if (getenv("PGMM_DUMP_JOBS")) {
+    FILE *fp = fopen(getenv("PGMM_DUMP_JOBS"), "a");
+    if (fp) {
+      for (size_t i = 0; i < n; ++i)
+        fprintf(fp, "%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\n", jobs[i].qlen, jobs[i].tlen, jobs[i].w, jobs[i].flag, res.out[i].n_diag, res.out[i].zdropped, res.out[i].reach_end, res.out[i].n_cigar);
+      fprintf(fp, "#wave\t%f\n", res.kernel_ms);
+      fclose(fp);
+    }
   }
   for (size_t i = 0; i < n; ++i) res.cig_start[i] = packed_off[i];
   res.cig_start[n] = res.cigar.size();

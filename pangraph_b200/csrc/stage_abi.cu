@@ -45,7 +45,7 @@ extern "C" int pgmm_ksw_extd2_batch(int n, const int32_t *qlen, const int32_t *t
   PGMM_CUDA(cudaStreamDestroy(st));
   if (res.cigar.size() > cigar_cap) return -1;
   for (int i = 0; i < n; ++i) {
-    memcpy(out_ez + 11 * (size_t)i, &res.out[i], sizeof(KswOut));
+    memcpy(out_ez + 11 * (size_t)i, &res.out[i], 11 * sizeof(int32_t));
     out_cig_start[i] = res.cig_start[i];
   }
   if (!res.cigar.empty()) memcpy(out_cigar, res.cigar.data(), res.cigar.size() * sizeof(uint32_t));

@@ -172,3 +172,28 @@ extern "C" __attribute__((visibility("default"))) int pgmm_hostlogic_map_all(
   L->idx_destroy(mi);
   return 0;
 }
+
+// ---- host building blocks exposed one at a time (tests/test_host_stages.py) ----
+extern "C" __attribute__((visibility("default"))) void pgmm_test_flag_sort_128x(uint64_t *xy, size_t n) {
+  flag_sort_128x((U128 *)xy, (U128 *)xy + n);
+}
+extern "C" __attribute__((visibility("default"))) void pgmm_test_flag_sort_64(uint64_t *v, size_t n) { flag_sort_64(v, v + n); }
+
+// chains anchors (already sorted); returns n_u, writes u[] and the compacted anchors back into xy (2 words each)
+extern "C" __attribute__((visibility("default"))) int64_t pgmm_test_chain_rmq(uint64_t *xy, int64_t n, int max_dist, int max_dist_inner,
+                                                                              int bw, int max_skip, int cap, int min_cnt, int min_sc,
+                                                                              float pen_gap, float pen_skip, uint64_t *u, int64_t *n_a_out) {
+  std::vector<U128> a((U128 *)xy, (U128 *)xy + n);
+  std::vector<uint64_t> uu;
+  ChainParams cp{max_dist, max_dist_inner, bw, max_skip, cap, min_cnt, min_sc, pen_gap, pen_skip};
+  chain_rmq(cp, a, uu);
+  memcpy(xy, a.data(), a.size() * 16);
+  memcpy(u, uu.data(), uu.size() * 8);
+  *n_a_out = (int64_t)a.size();
+  return (int64_t)uu.size();
+}
+
+extern "C" __attribute__((visibility("default"))) int pgmm_test_ll_score(int qlen, const uint8_t *q, int tlen, const uint8_t *t,
+                                                                         const int8_t *mat, int gapo, int gape, int *qe, int *te) {
+  return ll_local_score(qlen, q, tlen, t, mat, gapo, gape, qe, te);
+}
