@@ -24,13 +24,14 @@ def test_round_matches_oracle(ref, sens, thr):
     from oracle import host_half, refmm2
     from pangraph_b200 import abi, synth
     gs = synth.genomes(6, length=70_000, n_rearr=8, len_lo=300, len_hi=9000)
-    ids = [901, 17, 5, 10442385907364519937, 100, 9]
+    # pangraph hands the blocks over in BTreeMap order, i.e. ascending BlockId (align_with_minimap2_lib.rs:19-22)
+    ids = sorted([901, 17, 5, 10442385907364519937, 100, 9])
     seqs = [g.decode() for _, g in gs]
     names = [str(i) for i in ids]
     preset = {5: "asm5", 10: "asm10", 20: "asm20"}[sens]
     regs, _ = refmm2.ref_map_all(seqs, names, preset, None, max(thr - 10, 5), threads=6)
     args = abi.alignment_args(indel_len_threshold=thr, sensitivity=sens)
-    blocks = dict(zip(ids, seqs))
+    blocks = dict(reversed(list(zip(ids, seqs))))  # caller order must not matter
     # align_with_minimap2_lib: every hit, queries in BlockId order
     order = sorted(range(len(ids)), key=lambda i: ids[i])
     want_all = [host_half.from_reg(r, names[q], len(seqs[q]), names, [len(s) for s in seqs]) for q in order for r in regs[q]]
