@@ -1205,13 +1205,29 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     q.a.swap(seeds[i].a);
     q.mini_pos.swap(seeds[i].mini_pos);
     q.rep_len = seeds[i].rep_len;
+    const bool trace = getenv("PGMM_TRACE") != nullptr;
+    double c0 = now(), c1;
+    const size_t n_anchor = q.a.size();
     flag_sort_128x(q.a.data(), q.a.data() + q.a.size());  // map.c:202
+    c1 = now();
+    const double t_sort = c1 - c0;
+    c0 = c1;
     std::vector<uint64_t> u;
     chain_rmq(cp, q.a, u);
+    c1 = now();
+    const double t_ch = c1 - c0;
+    c0 = c1;
     M.gen_regs(q, u);
     M.est_err(q);
     q.n_a = q.regs.empty() ? 0 : Mapper::squeeze_a(q);
+    c1 = now();
+    const double t_regs = c1 - c0;
+    c0 = c1;
     for (auto &R : q.regs) M.plan_region(q, *R);
+    c1 = now();
+    if (trace)
+      fprintf(stderr, "[pgmm trace] query %d: %zu anchors, sort %.1f ms, chain %.1f ms, regs %.1f ms, plan %.1f ms (%zu hits, %zu jobs)\n", i,
+              n_anchor, t_sort, t_ch, t_regs, c1 - c0, q.regs.size(), q.jobs.size());
   });
 
   t1 = now(), be.stats.t_chain += t1 - t0, t0 = t1;
