@@ -85,11 +85,12 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
                                                        const uint8_t *__restrict__ qcodes,
                                                        const uint8_t *__restrict__ tcodes, KswScoring sc,
                                                        uint8_t *__restrict__ p_arena, uint32_t *__restrict__ cig_arena,
-                                                       uint8_t *__restrict__ scratch, KswOut *__restrict__ outs) {
+                                                       uint8_t *__restrict__ scratch, KswOut *__restrict__ outs,
+                                                       uint32_t *__restrict__ cig_packed, unsigned long long *__restrict__ cig_counter) {
   extern __shared__ uint32_t dyn_smem[];
   __shared__ __align__(16) uint32_t misc[kMiscWords];
   const int tid = threadIdx.x;
-  const int jid = job_ids[blockIdx.x];
+  const int jid = job_ids[blockIdx.x];  // index within this wave
   const KswJob job = jobs[jid];
   const int qlen = job.qlen, tlen = job.tlen, flag = job.flag;
   int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
@@ -366,13 +367,16 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
         }
       }
       if (last != 0) cig[n++] = last;
-      if (!(flag & KSW_REV_CIGAR))
-        for (int k = 0; k < n >> 1; ++k) {
-          const uint32_t c = cig[k];
-          cig[k] = cig[n - 1 - k], cig[n - 1 - k] = c;
-        }
     }
+    // reserve a slot in the packed output and move the run there (the walk produced it back to front)
+    const unsigned long long pos = n > 0 ? atomicAdd(cig_counter, (unsigned long long)n) : 0ull;
+    uint32_t *dst = cig_packed + pos;
+    if (flag & KSW_REV_CIGAR)
+      for (int k = 0; k < n; ++k) dst[k] = cig[k];
+    else
+      for (int k = 0; k < n; ++k) dst[k] = cig[n - 1 - k];
     KswOut o;
+    o.cig_pos = (uint32_t)pos;
     o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t, o.mqe = ez.mqe, o.mqe_t = ez.mqe_t;
     o.mte = ez.mte, o.mte_q = ez.mte_q, o.score = ez.score, o.reach_end = ez.reach_end, o.n_cigar = n;
     o.n_diag = r_done + 1;
@@ -380,23 +384,12 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
   }
 }
 
-// packs the per-job CIGAR scratch runs into one contiguous array (dst offsets precomputed on the host)
-__global__ void gather_cigars_kernel(const KswJob *__restrict__ jobs, const KswOut *__restrict__ outs,
-                                     const uint64_t *__restrict__ dst_off, const uint32_t *__restrict__ cig_arena,
-                                     uint32_t *__restrict__ dst, int njobs) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= njobs) return;
-  const uint32_t *src = cig_arena + jobs[warp].cig_off;
-  uint32_t *d = dst + dst_off[warp];
-  for (int i = lane; i < outs[warp].n_cigar; i += 32) d[i] = src[i];
-}
-
 constexpr size_t kSmemMax = 200 * 1024;
 
 template <int NT>
 void launch_class(const std::vector<int> &ids, size_t smem, const int *d_ids_base, size_t ids_off, const KswJob *d_jobs,
                   const uint8_t *d_q, const uint8_t *d_t, const KswScoring &sc, uint8_t *p_arena, uint32_t *cig_arena,
-                  uint8_t *scratch, KswOut *d_outs, cudaStream_t stream) {
+                  uint8_t *scratch, KswOut *d_outs, uint32_t *cig_packed, unsigned long long *cig_counter, cudaStream_t stream) {
   if (ids.empty()) return;
   static bool attr_set = false;
   if (!attr_set) {
@@ -404,7 +397,7 @@ void launch_class(const std::vector<int> &ids, size_t smem, const int *d_ids_bas
     attr_set = true;
   }
   ksw_extd2_kernel<NT><<<(unsigned)ids.size(), NT, smem, stream>>>(d_jobs, d_ids_base + ids_off, d_q, d_t, sc, p_arena,
-                                                                   cig_arena, scratch, d_outs);
+                                                                   cig_arena, scratch, d_outs, cig_packed, cig_counter);
   PGMM_CUDA(cudaGetLastError());
 }
 
@@ -425,7 +418,13 @@ struct KswEngine::Impl {
   DevBuf<KswOut> d_outs;
   DevBuf<uint8_t> p_arena, scratch;
   DevBuf<uint32_t> cig_arena, cig_packed;
-  DevBuf<uint64_t> d_dst_off;
+  DevBuf<unsigned long long> d_counter;
+  // pinned staging: copies in both directions are asynchronous and need no driver-side bounce buffer
+  PinBuf<KswJob> h_jobs;
+  PinBuf<int> h_ids;
+  PinBuf<KswOut> h_outs;
+  PinBuf<uint32_t> h_cigar;
+  PinBuf<unsigned long long> h_counter;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -473,7 +472,6 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return geo[a].p_bytes > geo[b].p_bytes; });
 
-  std::vector<uint64_t> packed_off(n + 1, 0);
   size_t pos = 0;
   while (pos < order.size()) {
     // ---- carve one wave ----
@@ -488,11 +486,14 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       else jobs[i].scr_off = ~0ull;
       ++end;
     }
+    const size_t nw = end - pos;
     // ---- size classes (threads per CTA follow the width of the wavefront) ----
     std::vector<int> cls[5];
     size_t cls_smem[5] = {0, 0, 0, 0, 0};
-    for (size_t k = pos; k < end; ++k) {
-      const int i = order[k];
+    KswJob *hj = m.h_jobs.ensure(nw);
+    for (size_t k = 0; k < nw; ++k) {  // jobs of this wave are renumbered 0..nw-1 on the device
+      const int i = order[pos + k];
+      hj[k] = jobs[i];
       const size_t sb = geo[i].state_bytes;
       int c;
       if (sb > kSmemMax) c = 4;
@@ -500,19 +501,22 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       else if (sb <= 24 * 1024) c = 1;
       else if (sb <= 64 * 1024) c = 2;
       else c = 3;
-      cls[c].push_back(i);
+      cls[c].push_back((int)k);
       if (c < 4) cls_smem[c] = std::max(cls_smem[c], sb);
       res.cells += (uint64_t)std::min<int64_t>((int64_t)jobs[i].qlen * jobs[i].tlen,
                                                 (int64_t)geo[i].n_row * std::min(geo[i].n_col16, geo[i].T));
     }
-    std::vector<int> ids;
-    size_t cls_off[5];
-    for (int c = 0; c < 5; ++c) cls_off[c] = ids.size(), ids.insert(ids.end(), cls[c].begin(), cls[c].end());
-
-    m.d_jobs.ensure(n), m.d_outs.ensure(n), m.d_ids.ensure(ids.size());
-    m.p_arena.ensure(p_used + 256), m.cig_arena.ensure(cig_used + 4), m.scratch.ensure(scr_used + 256);
-    PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, jobs.data(), n * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
-    PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    int *hid = m.h_ids.ensure(nw);
+    size_t cls_off[5], nid = 0;
+    for (int c = 0; c < 5; ++c) {
+      cls_off[c] = nid;
+      for (int k : cls[c]) hid[nid++] = k;
+    }
+    m.d_jobs.ensure(nw), m.d_outs.ensure(nw), m.d_ids.ensure(nw), m.d_counter.ensure(1);
+    m.p_arena.ensure(p_used + 256), m.cig_arena.ensure(cig_used + 4), m.cig_packed.ensure(cig_used + 4), m.scratch.ensure(scr_used + 256);
+    PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, hj, nw * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
+    PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, hid, nw * sizeof(int), cudaMemcpyHostToDevice, stream));
+    PGMM_CUDA(cudaMemsetAsync(m.d_counter.p, 0, sizeof(unsigned long long), stream));
     PGMM_CUDA(cudaEventRecord(m.ev0, stream));
     // the size classes are independent launches: fork them onto their own streams so that the few long problems of the
     // large classes overlap with the many short ones instead of queueing behind each other
@@ -521,49 +525,43 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       if (cls[c].empty()) continue;
       cudaStream_t cs = m.cls_stream[c];
       PGMM_CUDA(cudaStreamWaitEvent(cs, m.fork, 0));
+#define PGMM_LAUNCH(NT, SMEM)                                                                                                     \
+  launch_class<NT>(cls[c], SMEM, m.d_ids.p, cls_off[c], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, \
+                   m.cig_packed.p, m.d_counter.p, cs)
       switch (c) {
-        case 0: launch_class<32>(cls[0], cls_smem[0], m.d_ids.p, cls_off[0], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
-        case 1: launch_class<64>(cls[1], cls_smem[1], m.d_ids.p, cls_off[1], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
-        case 2: launch_class<128>(cls[2], cls_smem[2], m.d_ids.p, cls_off[2], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
-        case 3: launch_class<256>(cls[3], cls_smem[3], m.d_ids.p, cls_off[3], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
-        default: launch_class<256>(cls[4], 0, m.d_ids.p, cls_off[4], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, cs); break;
+        case 0: PGMM_LAUNCH(32, cls_smem[0]); break;
+        case 1: PGMM_LAUNCH(64, cls_smem[1]); break;
+        case 2: PGMM_LAUNCH(128, cls_smem[2]); break;
+        case 3: PGMM_LAUNCH(256, cls_smem[3]); break;
+        default: PGMM_LAUNCH(256, 0); break;
       }
+#undef PGMM_LAUNCH
       PGMM_CUDA(cudaEventRecord(m.cls_done[c], cs));
       PGMM_CUDA(cudaStreamWaitEvent(stream, m.cls_done[c], 0));
+      ++res.launches;
     }
     PGMM_CUDA(cudaEventRecord(m.ev1, stream));
-    for (int c = 0; c < 5; ++c) res.launches += !cls[c].empty();
 
-    // ---- results of this wave: ez first, then the CIGARs packed on the device ----
-    std::vector<KswOut> outs(n);
-    PGMM_CUDA(cudaMemcpyAsync(outs.data(), m.d_outs.p, n * sizeof(KswOut), cudaMemcpyDeviceToHost, stream));
+    // ---- results of this wave: ez + the number of CIGAR words, then exactly those words ----
+    KswOut *ho = m.h_outs.ensure(nw);
+    unsigned long long *hc = m.h_counter.ensure(1);
+    PGMM_CUDA(cudaMemcpyAsync(ho, m.d_outs.p, nw * sizeof(KswOut), cudaMemcpyDeviceToHost, stream));
+    PGMM_CUDA(cudaMemcpyAsync(hc, m.d_counter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     PGMM_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
     PGMM_CUDA(cudaEventElapsedTime(&ms, m.ev0, m.ev1));
     res.kernel_ms += ms;
-    std::vector<uint64_t> dst(n, 0);
-    uint64_t tot = 0;
-    for (size_t k = pos; k < end; ++k) {
-      const int i = order[k];
-      res.out[i] = outs[i];
-      dst[i] = tot, tot += outs[i].n_cigar;
-    }
+    const size_t tot = (size_t)*hc, base = res.cigar.size();
     if (tot > 0) {
-      m.d_dst_off.ensure(n), m.cig_packed.ensure(tot);
-      PGMM_CUDA(cudaMemcpyAsync(m.d_dst_off.p, dst.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-      // jobs outside this wave have stale outs on the device; give them n_cigar = 0 by gathering wave members only
-      std::vector<KswOut> masked(n, KswOut{});
-      for (size_t k = pos; k < end; ++k) masked[order[k]] = outs[order[k]];
-      PGMM_CUDA(cudaMemcpyAsync(m.d_outs.p, masked.data(), n * sizeof(KswOut), cudaMemcpyHostToDevice, stream));
-      const int tpb = 256, blocks = (int)((n * 32 + tpb - 1) / tpb);
-      gather_cigars_kernel<<<blocks, tpb, 0, stream>>>(m.d_jobs.p, m.d_outs.p, m.d_dst_off.p, m.cig_arena.p, m.cig_packed.p, (int)n);
-      PGMM_CUDA(cudaGetLastError());
-      const size_t base = res.cigar.size();
-      res.cigar.resize(base + tot);
-      PGMM_CUDA(cudaMemcpyAsync(res.cigar.data() + base, m.cig_packed.p, tot * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      uint32_t *hcig = m.h_cigar.ensure(tot);
+      PGMM_CUDA(cudaMemcpyAsync(hcig, m.cig_packed.p, tot * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
       PGMM_CUDA(cudaStreamSynchronize(stream));
-      for (size_t k = pos; k < end; ++k) packed_off[order[k]] = base + dst[order[k]];
-      ++res.launches;
+      res.cigar.insert(res.cigar.end(), hcig, hcig + tot);
+    }
+    for (size_t k = 0; k < nw; ++k) {
+      const int i = order[pos + k];
+      res.out[i] = ho[k];
+      res.cig_start[i] = base + ho[k].cig_pos;
     }
     pos = end;
   }
@@ -576,7 +574,6 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       fclose(fp);
     }
   }
-  for (size_t i = 0; i < n; ++i) res.cig_start[i] = packed_off[i];
   res.cig_start[n] = res.cigar.size();
 }
 

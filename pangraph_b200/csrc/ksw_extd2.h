@@ -31,7 +31,8 @@ struct KswJob {
 
 struct KswOut {  // ksw_extz_t minus the pointers (ksw2.h:31-40)
   int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
-  int32_t n_diag;  // anti-diagonals actually evaluated (profiling aid; not part of the reference's result)
+  int32_t n_diag;    // anti-diagonals actually evaluated (profiling aid; not part of the reference's result)
+  uint32_t cig_pos;  // where the kernel put this problem's CIGAR in the wave's packed output
 };
 
 struct KswScoring {  // mm_mapopt_t a,b,sc_ambi -> ksw_gen_simple_mat (align.c:9-22); q,e,q2,e2

@@ -15,11 +15,21 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <malloc.h>
 #include <functional>
 #include <thread>
 #include <ctime>
 
 namespace pgmm {
+
+// Rounds run concurrently on many host threads; keep large vectors on the heap (no mmap/munmap per wave, whose page
+// faults serialise on the process's memory map) and never hand memory back to the kernel between waves.
+static const bool g_malloc_tuned = [] {
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, INT32_MAX);
+  mallopt(M_TOP_PAD, 64 << 20);
+  return true;
+}();
 
 const uint8_t kNt4[256] = {
 #define R4 4, 4, 4, 4
@@ -141,7 +151,9 @@ inline Ez ez_reset() {
 struct DpCall {   // one DP window and, once its wave has run, its result
   int job = -1;   // index in the query's job list of the current wave; -1 = not submitted
   Ez ez = ez_reset();
-  std::vector<uint32_t> cigar;
+  // the CIGAR stays in the wave's result buffer (kept alive here) instead of being copied per problem
+  std::shared_ptr<const KswBatchResult> keep;
+  const uint32_t *cigar = nullptr;
 };
 
 struct Fill {
@@ -551,7 +563,8 @@ struct Mapper {
   void submit(QCtx &q, DpCall &c, int strand, int32_t qstart, int32_t ql, int rid, int32_t tstart, int32_t tl, int w,
               int zdrop, int end_bonus, int flag) const {
     c.ez = ez_reset();
-    c.cigar.clear();
+    c.cigar = nullptr;
+    c.keep.reset();
     c.job = -1;
     if (opt.max_sw_mat > 0 && (int64_t)tl * ql > opt.max_sw_mat) {
       c.ez.zdropped = 1;
@@ -567,11 +580,12 @@ struct Mapper {
     q.jobs.push_back(j);
     q.pending = true;
   }
-  static void collect(const QCtx &q, DpCall &c, const KswBatchResult &res) {
+  static void collect(const QCtx &q, DpCall &c, const std::shared_ptr<const KswBatchResult> &res) {
     if (c.job < 0) return;
     const size_t g = q.job_base + (size_t)c.job;
-    c.ez = res.out[g];
-    c.cigar.assign(res.cigar.begin() + res.cig_start[g], res.cigar.begin() + res.cig_start[g] + res.out[g].n_cigar);
+    c.ez = res->out[g];
+    c.keep = res;
+    c.cigar = res->cigar.data() + res->cig_start[g];
     c.job = -1;
   }
 
@@ -695,7 +709,7 @@ struct Mapper {
   }
 
   // re-scores the first-pass CIGAR of a fill and decides whether an exact second pass is needed (align.c:33-89)
-  int test_zdrop(const uint8_t *qseq, const uint8_t *tseq, const std::vector<uint32_t> &cigar) const {
+  int test_zdrop(const uint8_t *qseq, const uint8_t *tseq, const uint32_t *cigar, int n_cigar) const {
     int32_t score = 0, max = INT32_MIN, max_i = -1, max_j = -1, i = 0, j = 0, max_zdrop = 0;
     int pos[2][2] = {{-1, -1}, {-1, -1}};
     const auto upd = [&](int32_t sc, int ii, int jj) {
@@ -708,7 +722,8 @@ struct Mapper {
         }
       } else max = sc, max_i = ii, max_j = jj;
     };
-    for (uint32_t c : cigar) {
+    for (int ci = 0; ci < n_cigar; ++ci) {
+      const uint32_t c = cigar[ci];
       const uint32_t op = c & 0xf, len = c >> 4;
       if (op == MM_CIGAR_MATCH) {
         for (uint32_t l = 0; l < len; ++l) {
@@ -739,13 +754,13 @@ struct Mapper {
   }
 
   // after the first wave: collect results, test every fill, queue the exact second passes (align.c:757-759)
-  void after_pass1(QCtx &q, Region &R, const KswBatchResult &res) const {
+  void after_pass1(QCtx &q, Region &R, const std::shared_ptr<const KswBatchResult> &res) const {
     if (R.has_left) collect(q, R.left, res);
     if (R.has_right) collect(q, R.right, res);
     bool any = false;
     for (Fill &f : R.fills) {
       collect(q, f.pass1, res);
-      f.code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.cigar);
+      f.code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.cigar, f.pass1.ez.n_cigar);
       if (f.code != 0) {
         submit(q, f.pass2, R.rev, f.qs, f.qe - f.qs, R.rid, f.rs, f.re - f.rs, f.bw1, f.code == 2 ? opt.zdrop_inv : opt.zdrop, -1, 0);
         any = true;
@@ -777,7 +792,7 @@ struct Mapper {
 
   // mm_align1, second half: stitch the CIGAR in order, truncate and split on z-drop (align.c:715-827).
   // Returns the split-off hit (cnt > 0) if there is one.
-  mm_reg1_t finish_region(QCtx &q, Region &R, const KswBatchResult &res) const {
+  mm_reg1_t finish_region(QCtx &q, Region &R, const std::shared_ptr<const KswBatchResult> &res) const {
     mm_reg1_t &r = R.r;
     mm_reg1_t r2;
     memset(&r2, 0, sizeof(r2));
@@ -789,7 +804,7 @@ struct Mapper {
     if (R.has_left) {
       const Ez &ez = R.left.ez;
       if (ez.n_cigar > 0) {
-        append_cigar(R, R.left.cigar.data(), ez.n_cigar);
+        append_cigar(R, R.left.cigar, ez.n_cigar);
         R.dp_score += ez.max;
       }
       rs1 = R.rs - (ez.reach_end ? ez.mqe_t + 1 : ez.max_t + 1);
@@ -800,7 +815,7 @@ struct Mapper {
     for (Fill &f : R.fills) {
       const DpCall &c = f.code ? f.pass2 : f.pass1;
       const Ez &ez = c.ez;
-      if (ez.n_cigar > 0) append_cigar(R, c.cigar.data(), ez.n_cigar);
+      if (ez.n_cigar > 0) append_cigar(R, c.cigar, ez.n_cigar);
       if (ez.zdropped) {
         if (!R.has_p) R.has_p = true, R.capacity = roundup_pow2(6);
         int j;
@@ -821,7 +836,7 @@ struct Mapper {
     if (!dropped && R.has_right) {
       const Ez &ez = R.right.ez;
       if (ez.n_cigar > 0) {
-        append_cigar(R, R.right.cigar.data(), ez.n_cigar);
+        append_cigar(R, R.right.cigar, ez.n_cigar);
         R.dp_score += ez.max;
       }
       re1 = R.re + (ez.reach_end ? ez.mqe_t + 1 : ez.max_t + 1);
@@ -834,7 +849,7 @@ struct Mapper {
     if (R.has_p) update_extra(R, q.q0[r.rev] + qs1, tseq(R.rid, rs1));
     R.fills.clear();
     R.fills.shrink_to_fit();
-    R.left.cigar.clear(), R.right.cigar.clear();
+    R.left.keep.reset(), R.right.keep.reset();
     return r2;
   }
 
@@ -871,7 +886,7 @@ struct Mapper {
     Rinv.qe0 = r2.qe, Rinv.re0 = r2.qs;  // r2->qe and r2->qs, used for the query coordinates below
     return true;
   }
-  bool finish_inversion(QCtx &q, Region &Rinv, const KswBatchResult &res) const {
+  bool finish_inversion(QCtx &q, Region &Rinv, const std::shared_ptr<const KswBatchResult> &res) const {
     collect(q, Rinv.inv, res);
     const Ez &ez = Rinv.inv.ez;
     if (ez.n_cigar == 0) return false;
@@ -879,7 +894,7 @@ struct Mapper {
     const int32_t rid = ri.rid;
     const uint32_t rev = ri.rev;
     memset(&ri, 0, sizeof(ri));
-    append_cigar(Rinv, Rinv.inv.cigar.data(), ez.n_cigar);
+    append_cigar(Rinv, Rinv.inv.cigar, ez.n_cigar);
     Rinv.dp_score = ez.max;
     ri.id = -1, ri.parent = PARENT_UNSET, ri.inv = 1, ri.rev = rev, ri.rid = rid, ri.div = -1.0f;
     if (ri.rev == 0) {
@@ -892,7 +907,7 @@ struct Mapper {
     ri.rs = Rinv.rs0 + Rinv.inv_t_off;
     ri.re = ri.rs + ez.max_t + 1;
     update_extra(Rinv, q.q0[Rinv.rev] + Rinv.qs0 + Rinv.inv_q_off, tseq(rid, Rinv.rs0 + Rinv.inv_t_off));
-    Rinv.inv.cigar.clear();
+    Rinv.inv.keep.reset();
     return true;
   }
 
@@ -1236,8 +1251,10 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
   sc.sc_mch = (int8_t)(opt.a < 0 ? -opt.a : opt.a), sc.sc_mis = (int8_t)(opt.b > 0 ? -opt.b : opt.b), sc.sc_ambi = (int8_t)opt.sc_ambi;
   sc.q = (int8_t)opt.q, sc.e = (int8_t)opt.e, sc.q2 = (int8_t)opt.q2, sc.e2 = (int8_t)opt.e2;
   std::vector<KswJob> jobs;
-  KswBatchResult res;
   for (;;) {
+    auto res_mut = std::make_shared<KswBatchResult>();
+    KswBatchResult &res = *res_mut;
+    const std::shared_ptr<const KswBatchResult> res_sp = res_mut;
     jobs.clear();
     bool any_pending = false;
     for (QCtx &q : Q) {
@@ -1267,10 +1284,10 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
         Region &R = *q.regs[k];
         switch (R.state) {
           case Region::WAIT1:
-            M.after_pass1(q, R, res);
+            M.after_pass1(q, R, res_sp);
             break;
           case Region::WAIT2: {
-            mm_reg1_t r2 = M.finish_region(q, R, res);
+            mm_reg1_t r2 = M.finish_region(q, R, res_sp);
             R.state = Region::DONE;
             if (r2.cnt > 0) {  // the split-off remainder is aligned next, right after its parent (align.c:1004)
               auto N = std::make_unique<Region>();
@@ -1289,7 +1306,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
             break;
           }
           case Region::WAIT_INV:
-            if (M.finish_inversion(q, R, res)) R.state = Region::DONE;
+            if (M.finish_inversion(q, R, res_sp)) R.state = Region::DONE;
             else {
               q.regs.erase(q.regs.begin() + k);
               --k;

@@ -429,6 +429,8 @@ struct SeedEngine::Impl {
   DevBuf<U128> anchors;
   DevBuf<int32_t> rep_len, q_rank;
   DevBuf<int> qlens;
+  PinBuf<U128> h_anchors;  // pinned landing zones for the two large device->host copies
+  PinBuf<uint64_t> h_mini;
 
   void *tmp(size_t bytes) { return temp.ensure(bytes + 256); }
 
@@ -651,8 +653,8 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
   PGMM_CUDA(cudaMemcpyAsync(h_rep.data(), rep_len, nq * 4, cudaMemcpyDeviceToHost, st));
 
   std::vector<uint64_t> h_u_off(nq + 1, 0), h_q_slot(nq + 1, 0), h_a_off(nq + 1, 0);
-  std::vector<uint64_t> h_mini;
-  std::vector<U128> h_anchors;
+  uint64_t *h_mini = nullptr;
+  U128 *h_anchors = nullptr;
   if (n_used > 0) {
     // ---- used seeds, their query positions (mini_pos) and the anchor slots they expand to ----
     Seed *useds = m.useds.ensure(n_used);
@@ -665,8 +667,8 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     uint64_t n_slots = 0;
     PGMM_CUDA(cudaMemcpyAsync(&n_slots, a_off + n_used, 8, cudaMemcpyDeviceToHost, st));
     PGMM_CUDA(cudaMemcpyAsync(h_u_off.data(), u_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
-    h_mini.resize(n_used);
-    PGMM_CUDA(cudaMemcpyAsync(h_mini.data(), mini_pos, n_used * 8, cudaMemcpyDeviceToHost, st));
+    h_mini = m.h_mini.ensure(n_used);
+    PGMM_CUDA(cudaMemcpyAsync(h_mini, mini_pos, n_used * 8, cudaMemcpyDeviceToHost, st));
     PGMM_CUDA(cudaStreamSynchronize(st));
     if (n_slots >= (1ull << 32)) PGMM_FATAL("%llu anchors in one batch exceed the 2^32 slots of the expansion pass", (unsigned long long)n_slots);
     if (n_slots > 0) {
@@ -683,8 +685,8 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
       if (n_anchor > 0) {
         U128 *anchors = m.anchors.ensure(n_anchor);
         ++g_seed_launches, compact_anchor_kernel<<<nblk(n_slots), TPB, 0, st>>>(n_slots, akeep, apos, ax, ay, anchors);
-        h_anchors.resize(n_anchor);
-        PGMM_CUDA(cudaMemcpyAsync(h_anchors.data(), anchors, n_anchor * sizeof(U128), cudaMemcpyDeviceToHost, st));
+        h_anchors = m.h_anchors.ensure(n_anchor);
+        PGMM_CUDA(cudaMemcpyAsync(h_anchors, anchors, n_anchor * sizeof(U128), cudaMemcpyDeviceToHost, st));
       }
     }
   }
@@ -692,8 +694,8 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
   for (int q = 0; q < nq; ++q) {
     QuerySeeds &o = out[q];
     o.rep_len = h_rep[q];
-    o.mini_pos.assign(h_mini.begin() + h_u_off[q], h_mini.begin() + h_u_off[q + 1]);
-    if (!h_anchors.empty()) o.a.assign(h_anchors.begin() + h_a_off[q], h_anchors.begin() + h_a_off[q + 1]);
+    if (h_mini) o.mini_pos.assign(h_mini + h_u_off[q], h_mini + h_u_off[q + 1]);
+    if (h_anchors) o.a.assign(h_anchors + h_a_off[q], h_anchors + h_a_off[q + 1]);
   }
 }
 
