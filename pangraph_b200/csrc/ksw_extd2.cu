@@ -377,6 +377,40 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
       for (int k = 0; k < n; ++k) dst[k] = cig[n - 1 - k];
     KswOut o;
     o.cig_pos = (uint32_t)pos;
+    o.zd_max = 0, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
+    if ((flag & KSW_APPROX_MAX) && n > 0) {
+      // first-pass fill: re-score the path like mm_test_zdrop (align.c:33-68) while the sequences are still in shared
+      // memory, so that the host only has to look at five numbers per fill
+      const uint8_t *TQ8 = (const uint8_t *)TQ32, *QR8 = (const uint8_t *)QR32 + 4;
+      const int amb = sc.sc_ambi < 0 ? sc.sc_ambi : -sc.sc_ambi;
+      int32_t score = 0, mx = INT32_MIN, mx_i = -1, mx_j = -1, ti = 0, qj = 0, zd = 0;
+      int p00 = -1, p01 = -1, p10 = -1, p11 = -1;
+      for (int k = 0; k < n; ++k) {
+        const uint32_t c = dst[k], op = c & 0xf, len = c >> 4;
+        if (op == 0) {
+          for (uint32_t l = 0; l < len; ++l) {
+            const int ct = TQ8[ti + l], cq = QR8[qlen - 1 - (qj + (int)l)];
+            score += (ct > 3 || cq > 3) ? amb : ct == cq ? sc.sc_mch : sc.sc_mis;
+            if (score < mx) {
+              const int li = ti + (int)l - mx_i, lj = qj + (int)l - mx_j, diff = li > lj ? li - lj : lj - li;
+              const int z = mx - score - diff * sc.e;
+              if (z > zd) zd = z, p00 = mx_i, p01 = ti + (int)l, p10 = mx_j, p11 = qj + (int)l;
+            } else mx = score, mx_i = ti + (int)l, mx_j = qj + (int)l;
+          }
+          ti += len, qj += len;
+        } else {
+          score -= sc.q + sc.e * (int)len;
+          if (op == 1) qj += len;
+          else ti += len;
+          if (score < mx) {
+            const int li = ti - mx_i, lj = qj - mx_j, diff = li > lj ? li - lj : lj - li;
+            const int z = mx - score - diff * sc.e;
+            if (z > zd) zd = z, p00 = mx_i, p01 = ti, p10 = mx_j, p11 = qj;
+          } else mx = score, mx_i = ti, mx_j = qj;
+        }
+      }
+      o.zd_max = zd, o.zd_t0 = p00, o.zd_t1 = p01, o.zd_q0 = p10, o.zd_q1 = p11;
+    }
     o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t, o.mqe = ez.mqe, o.mqe_t = ez.mqe_t;
     o.mte = ez.mte, o.mte_q = ez.mte_q, o.score = ez.score, o.reach_end = ez.reach_end, o.n_cigar = n;
     o.n_diag = r_done + 1;

@@ -33,6 +33,9 @@ struct KswOut {  // ksw_extz_t minus the pointers (ksw2.h:31-40)
   int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
   int32_t n_diag;    // anti-diagonals actually evaluated (profiling aid; not part of the reference's result)
   uint32_t cig_pos;  // where the kernel put this problem's CIGAR in the wave's packed output
+  // mm_test_zdrop's scan of the CIGAR (align.c:47-68), filled for first-pass fills only: the largest score drop along
+  // the path and the window (target from/to, query from/to) where it happens
+  int32_t zd_max, zd_t0, zd_t1, zd_q0, zd_q1;
 };
 
 struct KswScoring {  // mm_mapopt_t a,b,sc_ambi -> ksw_gen_simple_mat (align.c:9-22); q,e,q2,e2

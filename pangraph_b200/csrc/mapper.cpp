@@ -708,8 +708,11 @@ struct Mapper {
     R.state = Region::WAIT1;
   }
 
-  // re-scores the first-pass CIGAR of a fill and decides whether an exact second pass is needed (align.c:33-89)
-  int test_zdrop(const uint8_t *qseq, const uint8_t *tseq, const uint32_t *cigar, int n_cigar) const {
+  // mm_test_zdrop (align.c:33-89) in two halves.  The scan of the first-pass CIGAR (largest score drop along the path
+  // and where it happens) comes back from the DP kernel with the result (KswOut::zd_*); a backend that does not fill it
+  // in (the CPU test seam) sets zd_max < 0 and the scan is done here.  The decision, including the striped local
+  // alignment that looks for an inversion inside the dropped window, is made on the host.
+  void zdrop_scan(const uint8_t *qseq, const uint8_t *tseq, const uint32_t *cigar, int n_cigar, Ez &ez) const {
     int32_t score = 0, max = INT32_MIN, max_i = -1, max_j = -1, i = 0, j = 0, max_zdrop = 0;
     int pos[2][2] = {{-1, -1}, {-1, -1}};
     const auto upd = [&](int32_t sc, int ii, int jj) {
@@ -738,16 +741,20 @@ struct Mapper {
         upd(score, i, j);
       }
     }
-    const int q_len = pos[1][1] - pos[1][0], t_len = pos[0][1] - pos[0][0];
+    ez.zd_max = max_zdrop, ez.zd_t0 = pos[0][0], ez.zd_t1 = pos[0][1], ez.zd_q0 = pos[1][0], ez.zd_q1 = pos[1][1];
+  }
+  int test_zdrop(const uint8_t *qseq, const uint8_t *tseq, const Ez &ez) const {
+    const int max_zdrop = ez.zd_max;
+    const int q_len = ez.zd_q1 - ez.zd_q0, t_len = ez.zd_t1 - ez.zd_t0;
     if (!(opt.flag & (MM_F_SPLICE | MM_F_SR | MM_F_FOR_ONLY | MM_F_REV_ONLY)) && max_zdrop > opt.zdrop_inv && q_len < opt.max_gap &&
         t_len < opt.max_gap) {
       std::vector<uint8_t> q2((size_t)(q_len > 0 ? q_len : 0));
       for (int k = 0; k < q_len; ++k) {
-        const int c = qseq[pos[1][1] - k - 1];
+        const int c = qseq[ez.zd_q1 - k - 1];
         q2[k] = (uint8_t)(c >= 4 ? 4 : 3 - c);
       }
       int q_off, t_off;
-      const int sc = ll_local_score(q_len, q2.data(), t_len, tseq + pos[0][0], mat, opt.q, opt.e, &q_off, &t_off);
+      const int sc = ll_local_score(q_len, q2.data(), t_len, tseq + ez.zd_t0, mat, opt.q, opt.e, &q_off, &t_off);
       if (sc >= opt.min_chain_score * opt.a && sc >= opt.min_dp_max) return 2;
     }
     return max_zdrop > opt.zdrop ? 1 : 0;
@@ -760,7 +767,8 @@ struct Mapper {
     bool any = false;
     for (Fill &f : R.fills) {
       collect(q, f.pass1, res);
-      f.code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.cigar, f.pass1.ez.n_cigar);
+      if (f.pass1.ez.zd_max < 0) zdrop_scan(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.cigar, f.pass1.ez.n_cigar, f.pass1.ez);
+      f.code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.ez);
       if (f.code != 0) {
         submit(q, f.pass2, R.rev, f.qs, f.qe - f.qs, R.rid, f.rs, f.re - f.rs, f.bw1, f.code == 2 ? opt.zdrop_inv : opt.zdrop, -1, 0);
         any = true;
@@ -1280,14 +1288,19 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     }
     parallel_for(qb.n, n_threads, [&](int qi) {
       QCtx &q = Q[qi];
+      double s0 = now(), s1, tr_p1 = 0, tr_fin = 0, tr_plan = 0;
       for (size_t k = 0; k < q.regs.size(); ++k) {
         Region &R = *q.regs[k];
         switch (R.state) {
           case Region::WAIT1:
+            s0 = now();
             M.after_pass1(q, R, res_sp);
+            tr_p1 += now() - s0;
             break;
           case Region::WAIT2: {
+            s0 = now();
             mm_reg1_t r2 = M.finish_region(q, R, res_sp);
+            tr_fin += now() - s0;
             R.state = Region::DONE;
             if (r2.cnt > 0) {  // the split-off remainder is aligned next, right after its parent (align.c:1004)
               auto N = std::make_unique<Region>();
@@ -1317,8 +1330,12 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
         }
       }
       // newly created remainders plan their windows now; they join the next wave
+      s0 = now();
       for (auto &R : q.regs)
         if (R->state == Region::NEW) M.plan_region(q, *R);
+      s1 = now(), tr_plan += s1 - s0;
+      if (getenv("PGMM_TRACE") && tr_p1 + tr_fin + tr_plan > 1.0)
+        fprintf(stderr, "[pgmm trace] query %d wave: test_zdrop+queue %.1f ms, finish %.1f ms, plan %.1f ms\n", qi, tr_p1, tr_fin, tr_plan);
     });
   }
   be.end_batch();

@@ -114,7 +114,7 @@ struct DevBuf {
   T *ensure(size_t n) {
     if (n > cap) {
       release();
-      cls = DevicePool::size_class((n + 64) * sizeof(T));
+      cls = DevicePool::size_class((n + n / 4 + 64) * sizeof(T));  // 25 % headroom: rounds differ slightly in size
       p = (T *)DevicePool::get().alloc(cls);
       cap = cls / sizeof(T);
     }
@@ -136,7 +136,7 @@ struct PinBuf {
   T *ensure(size_t n) {
     if (n > cap) {
       if (p) cudaFreeHost(p);
-      size_t want = n + n / 4 + 64;
+      size_t want = n + n / 2 + 64;
       PGMM_CUDA(cudaMallocHost((void **)&p, want * sizeof(T)));
       cap = want;
     }

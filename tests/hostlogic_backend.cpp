@@ -131,6 +131,7 @@ struct RefBackend : Backend {
       KswOut &o = res.out[i];
       o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t, o.mqe = ez.mqe, o.mqe_t = ez.mqe_t;
       o.mte = ez.mte, o.mte_q = ez.mte_q, o.score = ez.score, o.reach_end = ez.reach_end, o.n_cigar = ez.n_cigar;
+      o.zd_max = -1;  // no device-side mm_test_zdrop scan here: the host does it
       res.cig_start[i] = res.cigar.size();
       res.cigar.insert(res.cigar.end(), ez.cigar, ez.cigar + ez.n_cigar);
       free(ez.cigar);
