@@ -16,6 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <malloc.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <functional>
 #include <thread>
 #include <ctime>
@@ -1058,6 +1061,78 @@ void parallel_for(int n, int n_threads, const std::function<void(int)> &fn);
 
 }  // namespace
 
+// Striped local alignment score with eight 16-bit lanes (Farrar's layout; ksw2_ll_sse.c:37-152).  The result depends
+// on the striping (ties for the end coordinates, saturation), so the layout is kept: vector j, lane l <-> query
+// position j + l*slen.  Written with the SSE2 intrinsics on x86-64 hosts and lane by lane elsewhere.
+#if defined(__SSE2__)
+int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,
+                   int *qe, int *te) {
+  *qe = *te = -1;
+  const int slen = (qlen + 7) / 8;
+  if (slen == 0) {
+    if (tlen > 0) *te = tlen - 1;
+    return 0;
+  }
+  std::vector<uint64_t> buf((size_t)slen * 9 * 2 + 2);
+  __m128i *prof = (__m128i *)(((uintptr_t)buf.data() + 15) & ~(uintptr_t)15), *H0 = prof + (size_t)slen * 5, *H1 = H0 + slen, *E = H1 + slen, *Hmax = E + slen;
+  {
+    int16_t *t = (int16_t *)prof;
+    for (int a = 0; a < 5; ++a)
+      for (int j = 0; j < slen; ++j)
+        for (int l = 0; l < 8; ++l) {
+          const int k = j + l * slen;
+          *t++ = (int16_t)(k >= qlen ? 0 : mat[a * 5 + query[k]]);
+        }
+  }
+  const __m128i zero = _mm_setzero_si128(), goe = _mm_set1_epi16((short)(gapo + gape)), ge = _mm_set1_epi16((short)gape);
+  for (int j = 0; j < slen; ++j) H0[j] = E[j] = Hmax[j] = zero;
+  int gmax = 0;
+  for (int i = 0; i < tlen; ++i) {
+    const __m128i *S = prof + (size_t)target[i] * slen;
+    __m128i f = zero, rowmax = zero;
+    __m128i h = _mm_slli_si128(H0[slen - 1], 2);  // the last vector of the previous row, moved up one lane
+    for (int j = 0; j < slen; ++j) {
+      h = _mm_adds_epi16(h, S[j]);
+      __m128i e = E[j];
+      h = _mm_max_epi16(h, e);
+      h = _mm_max_epi16(h, f);
+      rowmax = _mm_max_epi16(rowmax, h);
+      H1[j] = h;
+      h = _mm_subs_epu16(h, goe);
+      e = _mm_max_epi16(_mm_subs_epu16(e, ge), h);
+      E[j] = e;
+      f = _mm_max_epi16(_mm_subs_epu16(f, ge), h);
+      h = H0[j];
+    }
+    for (int k = 0, done = 0; k < 8 && !done; ++k) {  // lazy F: propagate horizontal gaps across the stripes
+      f = _mm_slli_si128(f, 2);
+      for (int j = 0; j < slen; ++j) {
+        h = _mm_max_epi16(H1[j], f);
+        H1[j] = h;
+        h = _mm_subs_epu16(h, goe);
+        f = _mm_subs_epu16(f, ge);
+        if (!_mm_movemask_epi8(_mm_cmpgt_epi16(f, h))) {
+          done = 1;
+          break;
+        }
+      }
+    }
+    __m128i m = _mm_max_epi16(rowmax, _mm_srli_si128(rowmax, 8));
+    m = _mm_max_epi16(m, _mm_srli_si128(m, 4));
+    m = _mm_max_epi16(m, _mm_srli_si128(m, 2));
+    const int imax = _mm_extract_epi16(m, 0);
+    if (imax >= gmax) {
+      gmax = imax, *te = i;
+      memcpy(Hmax, H1, (size_t)slen * sizeof(__m128i));
+    }
+    std::swap(H0, H1);
+  }
+  const uint16_t *H8 = (const uint16_t *)Hmax;
+  for (int i = 0; i < slen * 8; ++i)
+    if ((int)H8[i] == gmax) *qe = i / 8 + i % 8 * slen;
+  return gmax;
+}
+#else
 // striped local alignment score with 16-bit lanes, restated lane by lane (ksw2_ll_sse.c:37-152): the result depends on
 // the striped layout (ties for the end positions, saturation), so the layout is kept: vector j, lane l <-> query j+l*slen
 int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,
@@ -1157,6 +1232,8 @@ int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
     if ((int)(uint16_t)Hmax[i / 8][i % 8] == gmax) *qe = i / 8 + i % 8 * slen;
   return gmax;
 }
+
+#endif
 
 namespace {
 void parallel_for(int n, int n_threads, const std::function<void(int)> &fn) {
