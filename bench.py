@@ -232,7 +232,9 @@ def ours(args):
 
     def round_resident(idx):
         idx.build()
-        return idx.map_self(raw=True)
+        out = idx.map_self(raw=True)
+        idx.close()  # device blocks go back to the pool for the next round
+        return out
 
     def finish(results):
         hits = 0
@@ -281,9 +283,6 @@ def ours(args):
     abi.get_stats(reset=True)
     t_res, hits_res = timed(step_resident, resident)
     st_res = abi.get_stats(reset=True)
-    for idxs in resident:
-        for idx in idxs:
-            idx.close()
     # ---- e2e: host buffers through the C-ABI ----
     t_e2e, hits_e2e = timed(step_e2e, [args.warmup + s for s in range(args.steps)])
     st_e2e = abi.get_stats(reset=True)

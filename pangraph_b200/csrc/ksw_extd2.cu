@@ -445,8 +445,9 @@ KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
 }
 
 struct KswEngine::Impl {
-  cudaStream_t cls_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, fork = nullptr;
+  static constexpr int kClasses = 20;  // 5 CTA widths x 4 state-size tiers
+  cudaStream_t cls_stream[kClasses] = {};
+  cudaEvent_t cls_done[kClasses] = {}, fork = nullptr;
   DevBuf<KswJob> d_jobs;
   DevBuf<int> d_ids;
   DevBuf<KswOut> d_outs;
@@ -466,7 +467,7 @@ KswEngine::KswEngine() : impl_(new Impl) {
   PGMM_CUDA(cudaEventCreate(&impl_->ev0));
   PGMM_CUDA(cudaEventCreate(&impl_->ev1));
   PGMM_CUDA(cudaEventCreateWithFlags(&impl_->fork, cudaEventDisableTiming));
-  for (int c = 0; c < 5; ++c) {
+  for (int c = 0; c < Impl::kClasses; ++c) {
     PGMM_CUDA(cudaStreamCreateWithFlags(&impl_->cls_stream[c], cudaStreamNonBlocking));
     PGMM_CUDA(cudaEventCreateWithFlags(&impl_->cls_done[c], cudaEventDisableTiming));
   }
@@ -475,7 +476,7 @@ KswEngine::~KswEngine() {
   cudaEventDestroy(impl_->ev0);
   cudaEventDestroy(impl_->ev1);
   cudaEventDestroy(impl_->fork);
-  for (int c = 0; c < 5; ++c) cudaStreamDestroy(impl_->cls_stream[c]), cudaEventDestroy(impl_->cls_done[c]);
+  for (int c = 0; c < Impl::kClasses; ++c) cudaStreamDestroy(impl_->cls_stream[c]), cudaEventDestroy(impl_->cls_done[c]);
   delete impl_;
 }
 
@@ -521,28 +522,32 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       ++end;
     }
     const size_t nw = end - pos;
-    // ---- size classes (threads per CTA follow the width of the wavefront) ----
-    std::vector<int> cls[5];
-    size_t cls_smem[5] = {0, 0, 0, 0, 0};
+    // ---- launch classes: threads per CTA follow the width of the wavefront (one word of 4 cells per thread and
+    // anti-diagonal for everything but the small fills), shared memory follows the length of the target ----
+    constexpr int kClasses = Impl::kClasses;
+    std::vector<int> cls[kClasses];
+    size_t cls_smem[kClasses] = {};
     KswJob *hj = m.h_jobs.ensure(nw);
     for (size_t k = 0; k < nw; ++k) {  // jobs of this wave are renumbered 0..nw-1 on the device
       const int i = order[pos + k];
       hj[k] = jobs[i];
       const size_t sb = geo[i].state_bytes;
-      int c;
-      if (sb > kSmemMax) c = 4;
-      else if (sb <= 6 * 1024) c = 0;
-      else if (sb <= 24 * 1024) c = 1;
-      else if (sb <= 64 * 1024) c = 2;
-      else c = 3;
+      const int ww = jobs[i].w < 0 ? INT32_MAX : jobs[i].w;
+      const int front = std::min(std::min(jobs[i].qlen, jobs[i].tlen), ww < INT32_MAX ? ww + 1 : INT32_MAX);
+      const int words = (front + 32 + 3) / 4;
+      int nt_tier, sm_tier;
+      if (sb <= 6 * 1024 && words <= 96) nt_tier = 0;  // small fills: one warp, a few words per lane
+      else nt_tier = words <= 64 ? 1 : words <= 128 ? 2 : words <= 256 ? 3 : 4;
+      sm_tier = sb > kSmemMax ? 3 : sb <= 12 * 1024 ? 0 : sb <= 48 * 1024 ? 1 : 2;
+      const int c = nt_tier * 4 + sm_tier;
       cls[c].push_back((int)k);
-      if (c < 4) cls_smem[c] = std::max(cls_smem[c], sb);
+      if (sm_tier < 3) cls_smem[c] = std::max(cls_smem[c], sb);
       res.cells += (uint64_t)std::min<int64_t>((int64_t)jobs[i].qlen * jobs[i].tlen,
                                                 (int64_t)geo[i].n_row * std::min(geo[i].n_col16, geo[i].T));
     }
     int *hid = m.h_ids.ensure(nw);
-    size_t cls_off[5], nid = 0;
-    for (int c = 0; c < 5; ++c) {
+    size_t cls_off[kClasses], nid = 0;
+    for (int c = 0; c < kClasses; ++c) {
       cls_off[c] = nid;
       for (int k : cls[c]) hid[nid++] = k;
     }
@@ -555,19 +560,19 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     // the size classes are independent launches: fork them onto their own streams so that the few long problems of the
     // large classes overlap with the many short ones instead of queueing behind each other
     PGMM_CUDA(cudaEventRecord(m.fork, stream));
-    for (int c = 0; c < 5; ++c) {
+    for (int c = kClasses - 1; c >= 0; --c) {  // widest / longest first
       if (cls[c].empty()) continue;
       cudaStream_t cs = m.cls_stream[c];
       PGMM_CUDA(cudaStreamWaitEvent(cs, m.fork, 0));
 #define PGMM_LAUNCH(NT, SMEM)                                                                                                     \
   launch_class<NT>(cls[c], SMEM, m.d_ids.p, cls_off[c], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, \
                    m.cig_packed.p, m.d_counter.p, cs)
-      switch (c) {
-        case 0: PGMM_LAUNCH(32, cls_smem[0]); break;
-        case 1: PGMM_LAUNCH(64, cls_smem[1]); break;
-        case 2: PGMM_LAUNCH(128, cls_smem[2]); break;
-        case 3: PGMM_LAUNCH(256, cls_smem[3]); break;
-        default: PGMM_LAUNCH(256, 0); break;
+      switch (c / 4) {
+        case 0: PGMM_LAUNCH(32, cls_smem[c]); break;
+        case 1: PGMM_LAUNCH(64, cls_smem[c]); break;
+        case 2: PGMM_LAUNCH(128, cls_smem[c]); break;
+        case 3: PGMM_LAUNCH(256, cls_smem[c]); break;
+        default: PGMM_LAUNCH(512, cls_smem[c]); break;
       }
 #undef PGMM_LAUNCH
       PGMM_CUDA(cudaEventRecord(m.cls_done[c], cs));
