@@ -194,30 +194,18 @@ def ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = abi.lib()
+    abi.set_device(local)
     from concurrent.futures import ThreadPoolExecutor
     P = args.rounds_per_step
     n_pool = max(P, args.pool)
     pairs = make_pairs(n_pool, rank * n_pool, args.genome_len)
     bp_pair = [sum(len(x) for x in seqs) for seqs, _ in pairs]
-    pool = ThreadPoolExecutor(P)
+    pool = ThreadPoolExecutor(min(P, args.workers))  # rounds in flight at any moment
 
     def pairs_of_step(s):
         return [(s * P + j) % n_pool for j in range(P)]
 
-    def gather_matches(n_regs, regs):
-        """NCCL: variable-length match lists of every rank -> rank 0 (sizes first, then padded payloads)."""
-        if dist is None:
-            return
-        payload = pack_regs(n_regs, regs)
-        size = torch.tensor([len(payload)], dtype=torch.int64, device="cuda")
-        sizes = [torch.zeros_like(size) for _ in range(world)]
-        dist.all_gather(sizes, size)
-        mx = int(max(int(s.item()) for s in sizes))
-        buf = torch.zeros(max(mx, 1), dtype=torch.uint8, device="cuda")
-        if payload:
-            buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
-        dst = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, dst, dst=0)
+    from pangraph_b200 import sharding
 
     def round_e2e(p):
         seqs, names = pairs[p]
@@ -237,9 +225,13 @@ def ours(args):
         return out
 
     def finish(results):
+        """Rank 0 receives the match lists of every rank's rounds, in round order, over NCCL."""
         hits = 0
-        for n_regs, regs in results:  # rank 0 receives the match lists in round order
-            gather_matches(n_regs, regs)
+        if dist is not None:
+            payloads = [(rank + world * j, pack_regs(n_regs, regs)) for j, (n_regs, regs) in enumerate(results)]
+            got = sharding.gather_rounds(payloads, torch.device("cuda", local))
+            assert rank != 0 or len(got) == world * len(results)
+        for n_regs, regs in results:
             hits += free_regs(abi, n_regs, regs)
         return hits
 
@@ -255,9 +247,12 @@ def ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    cpu_used = {}
+
     def timed(fn, items):
         sync()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = os.times()
         t0 = time.perf_counter()
         ev0.record()
         hits = 0
@@ -266,6 +261,8 @@ def ours(args):
         ev1.record()
         sync()
         wall = time.perf_counter() - t0
+        c1 = os.times()
+        cpu_used[fn.__name__] = ((c1.user - c0.user) + (c1.system - c0.system)) / max(wall, 1e-9)  # busy host cores
         ms = max(ev0.elapsed_time(ev1), 0.0)
         t = torch.tensor([max(wall, ms / 1e3)], dtype=torch.float64, device="cuda")
         if dist is not None:
@@ -320,7 +317,9 @@ def ours(args):
             "config": {"workload": f"{P} leaf-merge alignment rounds per rank per step, each 2 x {args.genome_len} bp synthetic genomes "
                                    f"at 1% divergence, 10 rearrangements (asm10, k=19 w=19)",
                        "l2": "working set > L2: distinct genome pairs in every round, > 1 GB of traceback written per round",
-                       "rounds_per_step": P, "hits_per_round": hits_res / max(1, args.steps * P), "host_threads": os.cpu_count()},
+                       "rounds_per_step": P, "rounds_in_flight": min(P, args.workers),
+                       "busy_host_cores": {"value": round(cpu_used.get("step_resident", 0), 1), "e2e": round(cpu_used.get("step_e2e", 0), 1)},
+                       "hits_per_round": hits_res / max(1, args.steps * P), "host_threads": os.cpu_count()},
             "e2e": {"value": bp_total / t_e2e / 1e9, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
             "gpu_launches": int(st_res["launches"]),
@@ -349,6 +348,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--rounds-per-step", type=int, default=8, help="independent leaf-merge rounds a rank keeps in flight per step")
+    ap.add_argument("--workers", type=int, default=16, help="host threads driving rounds concurrently (one CUDA stream each)")
     ap.add_argument("--pool", type=int, default=8, help="distinct genome pairs generated per rank (steps cycle through them)")
     ap.add_argument("--ref-sample-len", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -269,6 +269,9 @@ PGMM_API void pgmm_alignments_free(pgmm_alignment_t *alns, size_t n);
 /* ===================== Part 3: stage-level entry points (tests, bench) ===================== */
 
 PGMM_API int pgmm_device_count(void);
+/* Binds the process to one GPU (one process per GPU; call before anything else, e.g. with LOCAL_RANK).  Without it the
+ * device that is current at the first call is used.  0 ok, -1 no such device, -2 already bound to another device. */
+PGMM_API int pgmm_set_device(int device);
 
 /* K5 alone: n DP problems over windows of two host code buffers (bases coded 0..4).  flag = KSW_EZ_* of the
  * reference (ksw2.h:8-14) | 0x10000 to read both windows back to front.  out_ez: 11 int32 per problem

@@ -134,6 +134,12 @@ def ksw_extd2_batch(qlen, tlen, q_off, t_off, qcodes, tcodes, w, zdrop, end_bonu
     return ez, cigs, ms.value
 
 
+def set_device(device):
+    rc = lib().pgmm_set_device(int(device))
+    if rc != 0:
+        raise RuntimeError(f"pgmm_set_device({device}) -> {rc}")
+
+
 STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_cells", "dp_waves", "bases_mapped",
               "bases_indexed", "batches", "launches", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch", "t_final",
               "h2d_bytes", "d2h_bytes", "dp_seq_bytes")

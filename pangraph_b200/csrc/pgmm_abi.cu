@@ -262,6 +262,7 @@ mm_idx_t *pgmm_idx_upload(int n, const char **seq, const char **name) {
 }
 
 void pgmm_idx_build(mm_idx_t *mi, int w, int k, int bucket_bits) {
+  require_device();
   PgmmIndex *ix = (PgmmIndex *)mi->h;
   if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200");
   CtxLease cx;
@@ -291,6 +292,15 @@ mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n, const cha
   return mi;
 }
 
+int pgmm_set_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return -1;
+  if (bound_device() >= 0 && bound_device() != device) return -2;  // already computing on another device
+  bound_device() = device;
+  PGMM_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
 void pgmm_map_self(const mm_idx_t *mi, const mm_mapopt_t *opt, int *n_regs, mm_reg1_t **regs) {
   map_with_index(mi, 0, nullptr, nullptr, nullptr, opt, n_regs, regs);
 }
@@ -298,6 +308,7 @@ void pgmm_map_self(const mm_idx_t *mi, const mm_mapopt_t *opt, int *n_regs, mm_r
 void mm_mapopt_update(mm_mapopt_t *opt, const mm_idx_t *mi) {
   if ((opt->flag & MM_F_SPLICE_FOR) || (opt->flag & MM_F_SPLICE_REV)) opt->flag |= MM_F_SPLICE;
   if (opt->mid_occ <= 0) {
+    require_device();
     PgmmIndex *ix = (PgmmIndex *)mi->h;
     if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200");
     CtxLease cx;

@@ -144,6 +144,12 @@ struct PinBuf {
   }
 };
 
+// The one device this process computes on (one process per GPU).  Fixed by pgmm_set_device or by the first call;
+// every entry point re-selects it, because a host thread that never touched CUDA starts on device 0.
+inline int &bound_device() {
+  static int d = -1;
+  return d;
+}
 // Require a usable CUDA device; the library has no CPU path.
 inline void require_device() {
   int n = 0;
@@ -151,6 +157,9 @@ inline void require_device() {
   if (e != cudaSuccess || n <= 0)
     PGMM_FATAL("no CUDA device available (%s); libpgmm_b200 has no CPU fallback",
                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  int &d = bound_device();
+  if (d < 0) PGMM_CUDA(cudaGetDevice(&d));
+  else PGMM_CUDA(cudaSetDevice(d));
 }
 
 }  // namespace pgmm
