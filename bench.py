@@ -4,7 +4,7 @@
 One ROUND = one find_matches call of a guide-tree leaf merge: two related synthetic 5-Mbp genomes (1 % divergence,
 10 rearrangements each) are indexed and aligned all-vs-all, i.e. mm_idx_str + mm_mapopt_update + one
 mm_map per sequence in the reference, index kernels + pgmm_map_batch here.
-One STEP = `--rounds-per-step` (default 8) such rounds: sibling leaf merges of the guide tree are independent
+One STEP = `--rounds-per-step` (default 32) such rounds, `--workers` (default 16) of them in flight at any moment: sibling leaf merges of the guide tree are independent
 (merge_graphs only reads its two children), so a rank keeps several of them in flight, one host thread and one CUDA
 stream each.  bp per step = total length of the genomes of its rounds.
 
@@ -29,6 +29,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# many independent streams (one per round in flight + one per DP size class): give them their own hardware queues,
+# otherwise unrelated kernels serialise behind each other.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "Gbp aligned/sec for `pangraph build` alignment rounds (find_matches)"
 UNIT = "Gbp/s"
@@ -193,6 +196,8 @@ def ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ.setdefault("PGMM_CONTEXTS", str(max(8, args.workers)))
+    os.environ.setdefault("PGMM_ARENA_GB", "4")
     L = abi.lib()
     abi.set_device(local)
     from concurrent.futures import ThreadPoolExecutor
@@ -323,6 +328,7 @@ def ours(args):
             "e2e": {"value": bp_total / t_e2e / 1e9, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
             "gpu_launches": int(st_res["launches"]),
+            "device_mallocs_in_timed_region": {"value": int(st_res["device_mallocs"]), "e2e": int(st_e2e["device_mallocs"])},
             "roofline": {"bound": "hbm", "kernel": "ksw_extd2_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "gcups": st_res["dp_cells"] / ker_s / 1e9 if ker_s > 0 else 0.0,
@@ -343,13 +349,13 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--rounds-per-step", type=int, default=8, help="independent leaf-merge rounds a rank keeps in flight per step")
+    ap.add_argument("--rounds-per-step", type=int, default=32, help="independent leaf-merge rounds a rank keeps in flight per step")
     ap.add_argument("--workers", type=int, default=16, help="host threads driving rounds concurrently (one CUDA stream each)")
-    ap.add_argument("--pool", type=int, default=8, help="distinct genome pairs generated per rank (steps cycle through them)")
+    ap.add_argument("--pool", type=int, default=16, help="distinct genome pairs generated per rank (steps cycle through them)")
     ap.add_argument("--ref-sample-len", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -69,6 +69,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
+        # one stream per round in flight and per DP size class: more hardware queues than the default 8 (only
+        # effective if CUDA has not been initialised in this process yet)
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
                                "pangraph_b200 has no fallback implementation")
@@ -142,7 +145,7 @@ def set_device(device):
 
 STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_cells", "dp_waves", "bases_mapped",
               "bases_indexed", "batches", "launches", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch", "t_final",
-              "h2d_bytes", "d2h_bytes", "dp_seq_bytes")
+              "h2d_bytes", "d2h_bytes", "dp_seq_bytes", "device_mallocs")
 
 
 def get_stats(reset=False):

@@ -525,6 +525,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     // ---- launch classes: threads per CTA follow the width of the wavefront (one word of 4 cells per thread and
     // anti-diagonal for everything but the small fills), shared memory follows the length of the target ----
     constexpr int kClasses = Impl::kClasses;
+    static const int max_nt_tier = getenv("PGMM_MAX_NT_TIER") ? atoi(getenv("PGMM_MAX_NT_TIER")) : 4;
     std::vector<int> cls[kClasses];
     size_t cls_smem[kClasses] = {};
     KswJob *hj = m.h_jobs.ensure(nw);
@@ -538,6 +539,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       int nt_tier, sm_tier;
       if (sb <= 6 * 1024 && words <= 96) nt_tier = 0;  // small fills: one warp, a few words per lane
       else nt_tier = words <= 64 ? 1 : words <= 128 ? 2 : words <= 256 ? 3 : 4;
+      if (nt_tier > max_nt_tier) nt_tier = max_nt_tier;
       sm_tier = sb > kSmemMax ? 3 : sb <= 12 * 1024 ? 0 : sb <= 48 * 1024 ? 1 : 2;
       const int c = nt_tier * 4 + sm_tier;
       cls[c].push_back((int)k);
@@ -552,7 +554,10 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       for (int k : cls[c]) hid[nid++] = k;
     }
     m.d_jobs.ensure(nw), m.d_outs.ensure(nw), m.d_ids.ensure(nw), m.d_counter.ensure(1);
-    m.p_arena.ensure(p_used + 256), m.cig_arena.ensure(cig_used + 4), m.cig_packed.ensure(cig_used + 4), m.scratch.ensure(scr_used + 256);
+    // the traceback arena is taken once at its full budget: growing it later would mean a cudaMalloc, which stalls
+    // every stream of the device
+    m.p_arena.ensure(std::max(p_used + 256, arena_budget_bytes + 256));
+    m.cig_arena.ensure(2 * cig_used + 4), m.cig_packed.ensure(2 * cig_used + 4), m.scratch.ensure(scr_used + 256);
     PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, hj, nw * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
     PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, hid, nw * sizeof(int), cudaMemcpyHostToDevice, stream));
     PGMM_CUDA(cudaMemsetAsync(m.d_counter.p, 0, sizeof(unsigned long long), stream));

@@ -353,13 +353,14 @@ void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *cons
 //        [8] bases_indexed [9] batches [10] kernel launches of the DP engine
 void pgmm_get_stats(double *out, int n, int reset) {
   std::lock_guard<std::mutex> sl(g_stats_mu);
-  const double v[20] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+  const double v[21] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
                         (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
                         (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches,
                         g_stats.t_encode, g_stats.t_seed, g_stats.t_chain, g_stats.t_dp, g_stats.t_stitch, g_stats.t_final,
-                        (double)pgmm::h2d_bytes(), (double)pgmm::d2h_bytes(), (double)g_stats.dp_seq_bytes};
-  for (int i = 0; i < n && i < 20; ++i) out[i] = v[i];
-  if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0;
+                        (double)pgmm::h2d_bytes(), (double)pgmm::d2h_bytes(), (double)g_stats.dp_seq_bytes,
+                        (double)pgmm::DevicePool::misses()};
+  for (int i = 0; i < n && i < 21; ++i) out[i] = v[i];
+  if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0, pgmm::DevicePool::misses() = 0;
   if (reset) g_stats = Stats();
 }
 

@@ -72,6 +72,7 @@ class DevicePool {
       }
     }
     void *p = nullptr;
+    __atomic_fetch_add(&misses(), 1, __ATOMIC_RELAXED);
     cudaError_t e = cudaMalloc(&p, cls);
     if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
       trim();
@@ -83,6 +84,10 @@ class DevicePool {
   void release(void *p, size_t cls) {
     std::lock_guard<std::mutex> g(mu_);
     free_[cls].push_back(p);
+  }
+  static uint64_t &misses() {  // cudaMalloc calls so far (each one synchronises the device)
+    static uint64_t v = 0;
+    return v;
   }
   void trim() {
     std::lock_guard<std::mutex> g(mu_);
@@ -163,6 +168,27 @@ inline void require_device() {
 }
 
 }  // namespace pgmm
+
+namespace pgmm {
+// Waiting for a stream must not burn a host core (the cores are needed for chaining other rounds): block on an event
+// created with cudaEventBlockingSync instead of spinning in cudaStreamSynchronize.
+inline cudaError_t blocking_stream_sync(cudaStream_t st) {
+  thread_local cudaEvent_t ev = nullptr;
+  thread_local int ev_dev = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (ev == nullptr || ev_dev != dev) {
+    e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    ev_dev = dev;
+  }
+  e = cudaEventRecord(ev, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev);
+}
+}  // namespace pgmm
+#define cudaStreamSynchronize(st) pgmm::blocking_stream_sync((st))
 
 // every copy in the library goes through the counter
 #define cudaMemcpyAsync(dst, src, n, kind, st) pgmm::counted_memcpy_async((dst), (src), (n), (kind), (st))
