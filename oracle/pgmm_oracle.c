@@ -235,3 +235,145 @@ int orc_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 	free(u); free(H); free(p); free(off);
 	return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The same recurrence for problems whose band never binds (w >= max(qlen, tlen): every gap fill on pangraph's
+ * path, C/align.c:733-755), stated WITHOUT the 16-lane artefacts: only cells inside the matrix are evaluated, in
+ * plain int arithmetic.  This is what a kernel may compute when padded cells cannot reach any real cell: a real
+ * cell (r,t) reads (r-1,t-1) and (r-1,t), which are real cells or the first-row / first-column boundary values,
+ * and the traceback never leaves the matrix.  Real cells never overflow a signed byte -- the reference's own
+ * precondition (q+e)+(q2+e2) <= 127, C/options.c:205 -- so int arithmetic equals the wrap-around byte arithmetic.
+ * tests/test_oracle_ksw.py checks this function against ksw_extd2_sse on unbanded problems.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_ksw_extd2_unbanded(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                           int q, int e, int q2, int e2, int zdrop, int end_bonus, int flag,
+                           orc_ez_t *ez, uint32_t *cigar, int *overflow /* set to 1 if any value left [-128,127] */)
+{
+	const int m = 5;
+	int r, t, approx_max = !!(flag & ORC_EZ_APPROX_MAX);
+	ez->max_q = ez->max_t = ez->mqe_t = ez->mte_q = -1;
+	ez->max = 0, ez->score = ez->mqe = ez->mte = ORC_NEG_INF;
+	ez->n_cigar = 0, ez->zdropped = 0, ez->reach_end = 0;
+	*overflow = 0;
+	if (qlen <= 0 || tlen <= 0) return 0;
+	if (q2 + e2 < q + e) { t = q, q = q2, q2 = t, t = e, e = e2, e2 = t; }
+	int sc_mch = mat[0], sc_mis = mat[1], sc_N = mat[m * m - 1] == 0 ? -e2 : mat[m * m - 1];
+	{
+		int min_sc = mat[1];
+		for (t = 1; t < m * m; ++t) min_sc = min_sc < mat[t] ? min_sc : mat[t];
+		if (-min_sc > 2 * (q + e)) return 0;
+	}
+	int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+	int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+	int *u = malloc(sizeof(int) * tlen * 8), *v = u + tlen, *x = v + tlen, *y = x + tlen, *x2 = y + tlen, *y2 = x2 + tlen;
+	int *vn = y2 + tlen, *xn = vn + tlen; /* v and x of the anti-diagonal being written (x2 reuses a third copy below) */
+	int *x2n = malloc(sizeof(int) * tlen);
+	int32_t *H = malloc(sizeof(int32_t) * tlen);
+	for (t = 0; t < tlen; ++t) u[t] = v[t] = x[t] = y[t] = -q - e, x2[t] = y2[t] = -q2 - e2, H[t] = ORC_NEG_INF;
+	int n_row = qlen + tlen - 1;
+	uint8_t *p = malloc((size_t)n_row * tlen);
+	int H0 = 0, last_H0_t = 0, qe = q + e, qe2 = q2 + e2;
+#define ORC_CHK(val) do { int v_ = (val); if (v_ < -128 || v_ > 127) *overflow = 1; } while (0)
+	for (r = 0; r < n_row; ++r) {
+		int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
+		int ufirst = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+		if (en0 == r) y[r] = -q - e, y2[r] = -q2 - e2, u[r] = ufirst; /* first row */
+		for (t = st0; t <= en0; ++t) {
+			int xt1, vt1, x2t1;
+			if (t == 0) xt1 = -q - e, x2t1 = -q2 - e2, vt1 = ufirst; /* first column */
+			else xt1 = x[t - 1], vt1 = v[t - 1], x2t1 = x2[t - 1];
+			int a = target[t], b = query[r - t];
+			int z = (a == m - 1 || b == m - 1) ? sc_N : a == b ? sc_mch : sc_mis, d;
+			int ut = u[t], A = xt1 + vt1, B = y[t] + ut, A2 = x2t1 + vt1, B2 = y2[t] + ut;
+			ORC_CHK(A); ORC_CHK(B); ORC_CHK(A2); ORC_CHK(B2);
+			if (!(flag & ORC_EZ_RIGHT)) {
+				d = A > z ? 1 : 0;  z = z > A ? z : A;
+				d = B > z ? 2 : d;  z = z > B ? z : B;
+				d = A2 > z ? 3 : d; z = z > A2 ? z : A2;
+				d = B2 > z ? 4 : d; z = z > B2 ? z : B2;
+			} else {
+				d = z > A ? 0 : 1;  z = z > A ? z : A;
+				d = z > B ? d : 2;  z = z > B ? z : B;
+				d = z > A2 ? d : 3; z = z > A2 ? z : A2;
+				d = z > B2 ? d : 4; z = z > B2 ? z : B2;
+			}
+			z = z < sc_mch ? z : sc_mch;
+			int un = z - vt1, vnew = z - ut;
+			A -= z - q, B -= z - q, A2 -= z - q2, B2 -= z - q2;
+			ORC_CHK(un); ORC_CHK(vnew); ORC_CHK(A); ORC_CHK(B); ORC_CHK(A2); ORC_CHK(B2);
+			int pa, pb, pa2, pb2;
+			if (!(flag & ORC_EZ_RIGHT)) pa = A > 0, pb = B > 0, pa2 = A2 > 0, pb2 = B2 > 0;
+			else pa = A >= 0, pb = B >= 0, pa2 = A2 >= 0, pb2 = B2 >= 0;
+			u[t] = un, vn[t] = vnew;
+			xn[t] = (pa ? A : 0) - qe, y[t] = (pb ? B : 0) - qe, x2n[t] = (pa2 ? A2 : 0) - qe2, y2[t] = (pb2 ? B2 : 0) - qe2;
+			ORC_CHK(xn[t]); ORC_CHK(y[t]); ORC_CHK(x2n[t]); ORC_CHK(y2[t]);
+			p[(size_t)r * tlen + t] = (uint8_t)(d | pa << 3 | pb << 4 | pa2 << 5 | pb2 << 6);
+		}
+		for (t = st0; t <= en0; ++t) v[t] = vn[t], x[t] = xn[t], x2[t] = x2n[t];
+		if (!approx_max) {
+			int32_t max_H, max_t;
+			if (r > 0) {
+				int en1 = st0 + (en0 - st0) / 4 * 4, i;
+				int32_t HH[4], tt[4];
+				max_H = H[en0] = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
+				max_t = en0;
+				for (i = 0; i < 4; ++i) HH[i] = max_H, tt[i] = max_t;
+				for (t = st0; t < en1; t += 4)
+					for (i = 0; i < 4; ++i) {
+						H[t + i] += v[t + i];
+						if (H[t + i] > HH[i]) HH[i] = H[t + i], tt[i] = t;
+					}
+				for (i = 0; i < 4; ++i)
+					if (max_H < HH[i]) max_H = HH[i], max_t = tt[i] + i;
+				for (; t < en0; ++t) {
+					H[t] += v[t];
+					if (H[t] > max_H) max_H = H[t], max_t = t;
+				}
+			} else H[0] = v[0] - qe, max_H = H[0], max_t = 0;
+			if (en0 == tlen - 1 && H[en0] > ez->mte) ez->mte = H[en0], ez->mte_q = r - en0;
+			if (r - st0 == qlen - 1 && H[st0] > ez->mqe) ez->mqe = H[st0], ez->mqe_t = st0;
+			if (max_H > ez->max) ez->max = max_H, ez->max_t = max_t, ez->max_q = r - max_t;
+			else if (max_t >= ez->max_t && r - max_t >= ez->max_q) {
+				int tl = max_t - ez->max_t, ql = (r - max_t) - ez->max_q, l = tl > ql ? tl - ql : ql - tl;
+				if (zdrop >= 0 && ez->max - max_H > zdrop + l * e2) { ez->zdropped = 1; break; }
+			}
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H[tlen - 1];
+		} else {
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					int d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += v[last_H0_t];
+				else ++last_H0_t, H0 += u[last_H0_t];
+			} else H0 = v[0] - qe, last_H0_t = 0;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H0;
+		}
+	}
+	{
+		int i = -1, j = -1, n = 0, state = 0, go = 1;
+		if (!ez->zdropped && !(flag & ORC_EZ_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
+		else if (!ez->zdropped && (flag & ORC_EZ_EXTZ_ONLY) && ez->mqe + end_bonus > ez->max) ez->reach_end = 1, i = ez->mqe_t, j = qlen - 1;
+		else if (ez->max_t >= 0 && ez->max_q >= 0) i = ez->max_t, j = ez->max_q;
+		else go = 0;
+		if (go) {
+			while (i >= 0 && j >= 0) {
+				int tmp = p[(size_t)(i + j) * tlen + i];
+				if (state == 0) state = tmp & 7;
+				else if (!(tmp >> (state + 2) & 1)) state = 0;
+				if (state == 0) state = tmp & 7;
+				if (state == 0) orc_push(cigar, &n, 0, 1), --i, --j;
+				else if (state == 1 || state == 3) orc_push(cigar, &n, 2, 1), --i;
+				else orc_push(cigar, &n, 1, 1), --j;
+			}
+			if (i >= 0) orc_push(cigar, &n, 2, i + 1);
+			if (j >= 0) orc_push(cigar, &n, 1, j + 1);
+			if (!(flag & ORC_EZ_REV_CIGAR))
+				for (i = 0; i < n >> 1; ++i) { uint32_t c = cigar[i]; cigar[i] = cigar[n - 1 - i]; cigar[n - 1 - i] = c; }
+			ez->n_cigar = n;
+		}
+	}
+	free(u); free(x2n); free(H); free(p);
+	return 0;
+}

@@ -80,6 +80,288 @@ __device__ __forceinline__ void cta_bar() {
   else __syncthreads();
 }
 
+// Traceback (ksw2.h:127-159, ksw2_extd2_sse.c:388-399), CIGAR packing and -- for first-pass fills -- the mm_test_zdrop
+// scan, run by one thread once the wavefront of a problem is done.  TQ8 = target, QR8[i] = query[qlen-1-i].
+__device__ __noinline__ void finish_job(const KswJob &job, int jid, EzState ez, int n_diag, int w, bool abs_layout, int stride,
+                                        const uint8_t *__restrict__ P, const uint8_t *TQ8, const uint8_t *QR8, const KswScoring &sc,
+                                        uint32_t *__restrict__ cig_arena, uint32_t *__restrict__ cig_packed,
+                                        unsigned long long *__restrict__ cig_counter, KswOut *__restrict__ outs) {
+  const int qlen = job.qlen, tlen = job.tlen, flag = job.flag;
+  {
+    int i = -1, j = -1, n = 0, state = 0;
+    bool go = true;
+    if (!ez.zdropped && !(flag & KSW_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
+    else if (!ez.zdropped && (flag & KSW_EXTZ_ONLY) && ez.mqe + job.end_bonus > ez.max) ez.reach_end = 1, i = ez.mqe_t, j = qlen - 1;
+    else if (ez.max_t >= 0 && ez.max_q >= 0) i = ez.max_t, j = ez.max_q;
+    else go = false;
+    uint32_t *cig = cig_arena + job.cig_off;
+    if (go) {
+      uint32_t last = 0;  // run being built: len<<4|op, flushed when the op changes
+      while (i >= 0 && j >= 0) {
+        const int r = i + j;
+        int st0, en0;
+        band(r, qlen, tlen, w, st0, en0);
+        // rows hold the padded range [off, off_end] of their anti-diagonal (the reference's layout) or, for the
+        // kernels that only evaluate real cells, all target positions from 0
+        const int off = abs_layout ? 0 : st0 / 16 * 16, off_end = abs_layout ? tlen - 1 : (en0 + 16) / 16 * 16 - 1;
+        int force = -1;
+        if (i < off) force = 2;
+        if (i > off_end) force = 1;
+        const int tmp = force < 0 ? __ldcg(P + (size_t)r * stride + (i - off)) : 0;
+        if (state == 0) state = tmp & 7;
+        else if (!((tmp >> (state + 2)) & 1)) state = 0;
+        if (state == 0) state = tmp & 7;
+        if (force >= 0) state = force;
+        uint32_t op;
+        if (state == 0) op = 0, --i, --j;
+        else if (state == 1 || state == 3) op = 2, --i;
+        else op = 1, --j;
+        if (last != 0 && (last & 0xf) == op) last += 1u << 4;
+        else {
+          if (last != 0) cig[n++] = last;
+          last = 1u << 4 | op;
+        }
+      }
+      if (i >= 0) {  // leading deletion
+        if (last != 0 && (last & 0xf) == 2) last += (uint32_t)(i + 1) << 4;
+        else {
+          if (last != 0) cig[n++] = last;
+          last = (uint32_t)(i + 1) << 4 | 2;
+        }
+      }
+      if (j >= 0) {  // leading insertion
+        if (last != 0 && (last & 0xf) == 1) last += (uint32_t)(j + 1) << 4;
+        else {
+          if (last != 0) cig[n++] = last;
+          last = (uint32_t)(j + 1) << 4 | 1;
+        }
+      }
+      if (last != 0) cig[n++] = last;
+    }
+    // reserve a slot in the packed output and move the run there (the walk produced it back to front)
+    const unsigned long long pos = n > 0 ? atomicAdd(cig_counter, (unsigned long long)n) : 0ull;
+    uint32_t *dst = cig_packed + pos;
+    if (flag & KSW_REV_CIGAR)
+      for (int k = 0; k < n; ++k) dst[k] = cig[k];
+    else
+      for (int k = 0; k < n; ++k) dst[k] = cig[n - 1 - k];
+    KswOut o;
+    o.cig_pos = (uint32_t)pos;
+    o.zd_max = 0, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
+    if ((flag & KSW_APPROX_MAX) && n > 0) {
+      // first-pass fill: re-score the path like mm_test_zdrop (align.c:33-68) while the sequences are still in shared
+      // memory, so that the host only has to look at five numbers per fill
+      const int amb = sc.sc_ambi < 0 ? sc.sc_ambi : -sc.sc_ambi;
+      int32_t score = 0, mx = INT32_MIN, mx_i = -1, mx_j = -1, ti = 0, qj = 0, zd = 0;
+      int p00 = -1, p01 = -1, p10 = -1, p11 = -1;
+      for (int k = 0; k < n; ++k) {
+        const uint32_t c = dst[k], op = c & 0xf, len = c >> 4;
+        if (op == 0) {
+          for (uint32_t l = 0; l < len; ++l) {
+            const int ct = TQ8[ti + l], cq = QR8[qlen - 1 - (qj + (int)l)];
+            score += (ct > 3 || cq > 3) ? amb : ct == cq ? sc.sc_mch : sc.sc_mis;
+            if (score < mx) {
+              const int li = ti + (int)l - mx_i, lj = qj + (int)l - mx_j, diff = li > lj ? li - lj : lj - li;
+              const int z = mx - score - diff * sc.e;
+              if (z > zd) zd = z, p00 = mx_i, p01 = ti + (int)l, p10 = mx_j, p11 = qj + (int)l;
+            } else mx = score, mx_i = ti + (int)l, mx_j = qj + (int)l;
+          }
+          ti += len, qj += len;
+        } else {
+          score -= sc.q + sc.e * (int)len;
+          if (op == 1) qj += len;
+          else ti += len;
+          if (score < mx) {
+            const int li = ti - mx_i, lj = qj - mx_j, diff = li > lj ? li - lj : lj - li;
+            const int z = mx - score - diff * sc.e;
+            if (z > zd) zd = z, p00 = mx_i, p01 = ti, p10 = mx_j, p11 = qj;
+          } else mx = score, mx_i = ti, mx_j = qj;
+        }
+      }
+      o.zd_max = zd, o.zd_t0 = p00, o.zd_t1 = p01, o.zd_q0 = p10, o.zd_q1 = p11;
+    }
+    o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t, o.mqe = ez.mqe, o.mqe_t = ez.mqe_t;
+    o.mte = ez.mte, o.mte_q = ez.mte_q, o.score = ez.score, o.reach_end = ez.reach_end, o.n_cigar = n;
+    o.n_diag = n_diag;
+    outs[jid] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5a: first-pass gap fills (flag == KSW_APPROX_MAX, band never binding, target window <= 256 bases) -- about 85 % of
+// all DP cells of a round (~28 000 windows of ~205 x 205 per 5-Mbp pair).  Specialised because, when the band cannot
+// bind, padded cells can never reach a real cell (oracle/pgmm_oracle.c::orc_ksw_extd2_unbanded states and tests this):
+// only real cells are evaluated, and since real cells never leave the signed-byte range (the reference's
+// (q+e)+(q2+e2) <= 127 precondition) the recurrence runs in 16-bit lanes, two cells per 32-bit register, on the native
+// VIADD.16x2 / VIMNMX.S16x2 instructions (the byte-wide __v*4 intrinsics are emulated with 5-6 instructions each).
+//
+// One warp per problem, all state in registers: pair p = 32*slot + lane holds cells t = 2p, 2p+1 (4 slots = 256 cells).
+// Slots that do not intersect the active range of an anti-diagonal are skipped; the left neighbour of a pair comes
+// from the previous lane by shuffle.  Traceback bytes go to HBM (row = anti-diagonal, column = target position).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFillWarps = 4;     // problems per CTA
+constexpr int kFillMaxT = 256;    // target window limit (4 slots x 32 lanes x 2 cells)
+constexpr int kFillMaxQ = 1024;   // query window limit (two 16-bit copies of the reversed query in shared memory)
+
+__device__ __forceinline__ uint32_t pk2(int v) { return (uint32_t)(uint16_t)(int16_t)v * 0x00010001u; }
+__device__ __forceinline__ int lo16(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t w) { return (int)(int16_t)(w >> 16); }
+__device__ __forceinline__ uint32_t neg2(uint32_t w) { return __vadd2(~w, 0x00010001u); }
+
+__global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
+                                                                         int n_jobs, const uint8_t *__restrict__ qcodes,
+                                                                         const uint8_t *__restrict__ tcodes, KswScoring sc, int q_cap,
+                                                                         uint8_t *__restrict__ p_arena, uint32_t *__restrict__ cig_arena,
+                                                                         KswOut *__restrict__ outs, uint32_t *__restrict__ cig_packed,
+                                                                         unsigned long long *__restrict__ cig_counter) {
+  extern __shared__ uint32_t dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot_id = blockIdx.x * kFillWarps + warp;
+  if (slot_id >= n_jobs) return;  // whole warp leaves together
+  const int jid = job_ids[slot_id];
+  const KswJob job = jobs[jid];
+  const int qlen = job.qlen, tlen = job.tlen;
+  int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
+  if (q2 + e2 < q + e) {
+    int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t;
+  }
+  // per-warp shared memory: target bytes [kFillMaxT+16], reversed query bytes [4 + q_cap + 28], and the reversed query
+  // as 16-bit codes twice (second copy shifted by one element) so that the two query bases of a pair are always one
+  // aligned 32-bit load; both copies have 2*kFillMaxT zero elements in front and behind
+  const int qh_len = q_cap + 4 * kFillMaxT;  // halfwords per copy
+  const int per_warp_bytes = (kFillMaxT + 16) + (q_cap + 32) + 2 * qh_len * 2;
+  uint8_t *wbase = (uint8_t *)dyn_smem + (size_t)warp * ((per_warp_bytes + 15) / 16 * 16);
+  uint8_t *TQ8 = wbase;
+  uint8_t *QRraw = TQ8 + kFillMaxT + 16;  // QR8 = QRraw + 4
+  uint16_t *QH0 = (uint16_t *)(QRraw + q_cap + 32), *QH1 = QH0 + qh_len;
+  uint8_t *QR8 = QRraw + 4;
+  for (int i = lane; i < (kFillMaxT + 16) / 4; i += 32) ((uint32_t *)TQ8)[i] = 0;
+  for (int i = lane; i < (q_cap + 32) / 4; i += 32) ((uint32_t *)QRraw)[i] = 0;
+  for (int i = lane; i < qh_len; i += 32) ((uint32_t *)QH0)[i] = 0;  // both copies (2*qh_len halfwords)
+  __syncwarp();
+  {
+    const uint8_t *tb = tcodes + job.t_off, *qb = qcodes + job.q_off;
+    for (int i = lane; i < tlen; i += 32) TQ8[i] = tb[i];
+    for (int i = lane; i < qlen; i += 32) {
+      const uint8_t c = qb[qlen - 1 - i];  // reversed query: element i pairs with target t on anti-diagonal r when i = qlen-1-r+t
+      QR8[i] = c;
+      QH0[2 * kFillMaxT + i] = c;
+      QH1[2 * kFillMaxT + i - 1] = c;  // QH1[k] = QH0[k+1]
+    }
+  }
+  __syncwarp();
+
+  const int long_thres0 = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+  const int long_thres = (q2 + e2 + long_thres0 * e2 > q + e + long_thres0 * e) ? long_thres0 + 1 : long_thres0;
+  const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+  const int scN = sc.sc_ambi == 0 ? -e2 : -(sc.sc_ambi < 0 ? -sc.sc_ambi : sc.sc_ambi);
+  const uint32_t MCH = pk2(sc.sc_mch), MIS = pk2(sc.sc_mis), SCN = pk2(scN), ONE = 0x00010001u;
+  const uint32_t DMCH = (uint32_t)(sc.sc_mch - sc.sc_mis);  // multiplies a 0/1-per-lane word: no carry between lanes
+  const uint32_t QP = pk2(q), Q2P = pk2(q2), NQE = pk2(-q - e), NQE2 = pk2(-q2 - e2);
+  const int Tp = (tlen + 15) / 16 * 16, n_row = qlen + tlen - 1, qe = q + e;
+  uint8_t *P = p_arena + job.p_off;
+
+  uint32_t U[4], Y[4], Y2[4], V[4], X[4], X2[4], TQ[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    U[k] = Y[k] = V[k] = X[k] = NQE, Y2[k] = X2[k] = NQE2;
+    const int t = 2 * (32 * k + lane);
+    TQ[k] = (uint32_t)TQ8[t] | (uint32_t)TQ8[t + 1] << 16;
+  }
+  int32_t H0 = 0, last = 0;
+
+  for (int r = 0; r < n_row; ++r) {
+    const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
+    const int ufirst = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+    const int p_lo = st0 >> 1, p_hi = en0 >> 1;  // active pairs
+    const int qbase = 2 * kFillMaxT + (qlen - 1 - r);  // halfword index of the query base of target position 0
+    const uint16_t *QH = (qbase & 1) ? QH1 : QH0;
+    const int qword = (qbase & 1) ? (qbase - 1) >> 1 : qbase >> 1;  // 32-bit index of (t=0, t=1) in the chosen copy
+    uint8_t *prow = P + (size_t)r * Tp;
+    int d0 = 0, d1 = 0;  // v[last], u[last+1] of this anti-diagonal (for the tracked score)
+    const int l0p = last >> 1, l1p = (last + 1) >> 1;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+      if (32 * k > p_hi || 32 * k + 31 < p_lo) continue;  // warp-uniform
+      const int p = 32 * k + lane;
+      // previous anti-diagonal's x, v, x2 of the cell to the left: high half of the previous pair
+      uint32_t px = __shfl_up_sync(0xffffffffu, X[k], 1), pv = __shfl_up_sync(0xffffffffu, V[k], 1), px2 = __shfl_up_sync(0xffffffffu, X2[k], 1);
+      if (k > 0) {
+        const uint32_t wx = __shfl_sync(0xffffffffu, X[k - 1], 31), wv = __shfl_sync(0xffffffffu, V[k - 1], 31), wx2 = __shfl_sync(0xffffffffu, X2[k - 1], 31);
+        if (lane == 0) px = wx, pv = wv, px2 = wx2;
+      }
+      uint32_t XT1 = __funnelshift_l(px, X[k], 16), VT1 = __funnelshift_l(pv, V[k], 16), X2T1 = __funnelshift_l(px2, X2[k], 16);
+      if (p == 0) {  // first column (ksw2_extd2_sse.c:156-159)
+        XT1 = (XT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q - e);
+        X2T1 = (X2T1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q2 - e2);
+        VT1 = (VT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst;
+      }
+      uint32_t Uo = U[k], Yo = Y[k], Y2o = Y2[k];
+      if (en0 == r && (r >> 1) == p) {  // first row (:160-163)
+        if (r & 1) Uo = (Uo & 0x0000ffffu) | (uint32_t)(uint16_t)(int16_t)ufirst << 16, Yo = (Yo & 0x0000ffffu) | (NQE & 0xffff0000u), Y2o = (Y2o & 0x0000ffffu) | (NQE2 & 0xffff0000u);
+        else Uo = (Uo & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst, Yo = (Yo & 0xffff0000u) | (NQE & 0xffffu), Y2o = (Y2o & 0xffff0000u) | (NQE2 & 0xffffu);
+      }
+      // substitution scores of the two cells
+      const uint32_t qq = ((const uint32_t *)QH)[qword + p];
+      const uint32_t ne = __vminu2(TQ[k] ^ qq, ONE);
+      uint32_t Z = __vadd2(MIS, (ne ^ ONE) * DMCH);
+      const uint32_t isn = __vminu2((TQ[k] | qq) & 0x00040004u, ONE) * 0xffffu;
+      Z = (Z & ~isn) | (SCN & isn);
+      // the recurrence (left gap alignment, :228-275), two cells at a time
+      uint32_t A = __vadd2(XT1, VT1), B = __vadd2(Yo, Uo), A2 = __vadd2(X2T1, VT1), B2 = __vadd2(Y2o, Uo);
+      bool ph, pl;
+      uint32_t dl = 0, dh = 0;
+      Z = __vibmax_s16x2(Z, A, &ph, &pl);  dl = pl ? dl : 1u; dh = ph ? dh : 1u;
+      Z = __vibmax_s16x2(Z, B, &ph, &pl);  dl = pl ? dl : 2u; dh = ph ? dh : 2u;
+      Z = __vibmax_s16x2(Z, A2, &ph, &pl); dl = pl ? dl : 3u; dh = ph ? dh : 3u;
+      Z = __vibmax_s16x2(Z, B2, &ph, &pl); dl = pl ? dl : 4u; dh = ph ? dh : 4u;
+      Z = __vmins2(Z, MCH);
+      const uint32_t NZ = neg2(Z);
+      const uint32_t Un = __vadd2(Z, neg2(VT1)), Vn = __vadd2(Z, neg2(Uo));
+      const uint32_t T1 = __vadd2(NZ, QP), T2 = __vadd2(NZ, Q2P);
+      A = __vadd2(A, T1), B = __vadd2(B, T1), A2 = __vadd2(A2, T2), B2 = __vadd2(B2, T2);
+      // continuation flags: a > 0 <=> a >= 1.  (With a literal first operand nvcc 12.9 swaps the operands of
+      // __vibmax_s16x2 without flipping the predicates, so the variable goes first and the clamp is a separate max.)
+      (void)__vibmax_s16x2(A, ONE, &ph, &pl);  dl |= pl ? 0x08u : 0u; dh |= ph ? 0x08u : 0u;
+      (void)__vibmax_s16x2(B, ONE, &ph, &pl);  dl |= pl ? 0x10u : 0u; dh |= ph ? 0x10u : 0u;
+      (void)__vibmax_s16x2(A2, ONE, &ph, &pl); dl |= pl ? 0x20u : 0u; dh |= ph ? 0x20u : 0u;
+      (void)__vibmax_s16x2(B2, ONE, &ph, &pl); dl |= pl ? 0x40u : 0u; dh |= ph ? 0x40u : 0u;
+      A = __vmaxs2(A, 0u), B = __vmaxs2(B, 0u), A2 = __vmaxs2(A2, 0u), B2 = __vmaxs2(B2, 0u);
+      U[k] = Un, V[k] = Vn;
+      X[k] = __vadd2(A, NQE), Y[k] = __vadd2(B, NQE), X2[k] = __vadd2(A2, NQE2), Y2[k] = __vadd2(B2, NQE2);
+      if (p <= p_hi) *(uint16_t *)(prow + 2 * p) = (uint16_t)(dl | dh << 8);  // cells past the target end share the padded row
+      // values the tracked score needs (:367-379)
+      if ((l0p >> 5) == k) {
+        const uint32_t w = __shfl_sync(0xffffffffu, Vn, l0p & 31);
+        d0 = (last & 1) ? hi16(w) : lo16(w);
+      }
+      if ((l1p >> 5) == k) {
+        const uint32_t w = __shfl_sync(0xffffffffu, Un, l1p & 31);
+        d1 = ((last + 1) & 1) ? hi16(w) : lo16(w);
+      }
+    }
+    if (r > 0) {
+      const bool in0 = last >= st0 && last <= en0, in1 = last + 1 >= st0 && last + 1 <= en0;
+      if (in0 && in1) {
+        if (d0 > d1) H0 += d0;
+        else H0 += d1, ++last;
+      } else if (in0) H0 += d0;
+      else ++last, H0 += d1;
+    } else H0 = d0 - qe, last = 0;
+  }
+
+  __threadfence_block();  // every lane's traceback bytes must be visible to the lane that walks them
+  __syncwarp();
+  if (lane == 0) {
+    EzState ez;
+    ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+    ez.max = 0, ez.mqe = ez.mte = KSW_NEG_INF;
+    ez.zdropped = 0, ez.reach_end = 0;
+    ez.score = H0;  // the last anti-diagonal is the single cell (tlen-1, qlen-1)
+    finish_job(job, jid, ez, n_row, /*w=*/tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed, cig_counter, outs);
+  }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
                                                        const uint8_t *__restrict__ qcodes,
@@ -318,104 +600,9 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
     sw = X2c32, X2c32 = X2n32, X2n32 = sw;
   }
 
-  // ---- traceback on thread 0, ksw2.h:127-159 and ksw2_extd2_sse.c:388-399 ----
-  if (tid == 0) {
-    int i = -1, j = -1, n = 0, state = 0;
-    bool go = true;
-    if (!ez.zdropped && !(flag & KSW_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
-    else if (!ez.zdropped && (flag & KSW_EXTZ_ONLY) && ez.mqe + job.end_bonus > ez.max) ez.reach_end = 1, i = ez.mqe_t, j = qlen - 1;
-    else if (ez.max_t >= 0 && ez.max_q >= 0) i = ez.max_t, j = ez.max_q;
-    else go = false;
-    uint32_t *cig = cig_arena + job.cig_off;
-    if (go) {
-      uint32_t last = 0;  // run being built: len<<4|op, flushed when the op changes
-      while (i >= 0 && j >= 0) {
-        const int r = i + j;
-        int st0, en0;
-        band(r, qlen, tlen, w, st0, en0);
-        const int off = st0 / 16 * 16, off_end = (en0 + 16) / 16 * 16 - 1;
-        int force = -1;
-        if (i < off) force = 2;
-        if (i > off_end) force = 1;
-        const int tmp = force < 0 ? __ldcg(P + (size_t)r * stride + (i - off)) : 0;
-        if (state == 0) state = tmp & 7;
-        else if (!((tmp >> (state + 2)) & 1)) state = 0;
-        if (state == 0) state = tmp & 7;
-        if (force >= 0) state = force;
-        uint32_t op;
-        if (state == 0) op = 0, --i, --j;
-        else if (state == 1 || state == 3) op = 2, --i;
-        else op = 1, --j;
-        if (last != 0 && (last & 0xf) == op) last += 1u << 4;
-        else {
-          if (last != 0) cig[n++] = last;
-          last = 1u << 4 | op;
-        }
-      }
-      if (i >= 0) {  // leading deletion
-        if (last != 0 && (last & 0xf) == 2) last += (uint32_t)(i + 1) << 4;
-        else {
-          if (last != 0) cig[n++] = last;
-          last = (uint32_t)(i + 1) << 4 | 2;
-        }
-      }
-      if (j >= 0) {  // leading insertion
-        if (last != 0 && (last & 0xf) == 1) last += (uint32_t)(j + 1) << 4;
-        else {
-          if (last != 0) cig[n++] = last;
-          last = (uint32_t)(j + 1) << 4 | 1;
-        }
-      }
-      if (last != 0) cig[n++] = last;
-    }
-    // reserve a slot in the packed output and move the run there (the walk produced it back to front)
-    const unsigned long long pos = n > 0 ? atomicAdd(cig_counter, (unsigned long long)n) : 0ull;
-    uint32_t *dst = cig_packed + pos;
-    if (flag & KSW_REV_CIGAR)
-      for (int k = 0; k < n; ++k) dst[k] = cig[k];
-    else
-      for (int k = 0; k < n; ++k) dst[k] = cig[n - 1 - k];
-    KswOut o;
-    o.cig_pos = (uint32_t)pos;
-    o.zd_max = 0, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
-    if ((flag & KSW_APPROX_MAX) && n > 0) {
-      // first-pass fill: re-score the path like mm_test_zdrop (align.c:33-68) while the sequences are still in shared
-      // memory, so that the host only has to look at five numbers per fill
-      const uint8_t *TQ8 = (const uint8_t *)TQ32, *QR8 = (const uint8_t *)QR32 + 4;
-      const int amb = sc.sc_ambi < 0 ? sc.sc_ambi : -sc.sc_ambi;
-      int32_t score = 0, mx = INT32_MIN, mx_i = -1, mx_j = -1, ti = 0, qj = 0, zd = 0;
-      int p00 = -1, p01 = -1, p10 = -1, p11 = -1;
-      for (int k = 0; k < n; ++k) {
-        const uint32_t c = dst[k], op = c & 0xf, len = c >> 4;
-        if (op == 0) {
-          for (uint32_t l = 0; l < len; ++l) {
-            const int ct = TQ8[ti + l], cq = QR8[qlen - 1 - (qj + (int)l)];
-            score += (ct > 3 || cq > 3) ? amb : ct == cq ? sc.sc_mch : sc.sc_mis;
-            if (score < mx) {
-              const int li = ti + (int)l - mx_i, lj = qj + (int)l - mx_j, diff = li > lj ? li - lj : lj - li;
-              const int z = mx - score - diff * sc.e;
-              if (z > zd) zd = z, p00 = mx_i, p01 = ti + (int)l, p10 = mx_j, p11 = qj + (int)l;
-            } else mx = score, mx_i = ti + (int)l, mx_j = qj + (int)l;
-          }
-          ti += len, qj += len;
-        } else {
-          score -= sc.q + sc.e * (int)len;
-          if (op == 1) qj += len;
-          else ti += len;
-          if (score < mx) {
-            const int li = ti - mx_i, lj = qj - mx_j, diff = li > lj ? li - lj : lj - li;
-            const int z = mx - score - diff * sc.e;
-            if (z > zd) zd = z, p00 = mx_i, p01 = ti, p10 = mx_j, p11 = qj;
-          } else mx = score, mx_i = ti, mx_j = qj;
-        }
-      }
-      o.zd_max = zd, o.zd_t0 = p00, o.zd_t1 = p01, o.zd_q0 = p10, o.zd_q1 = p11;
-    }
-    o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t, o.mqe = ez.mqe, o.mqe_t = ez.mqe_t;
-    o.mte = ez.mte, o.mte_q = ez.mte_q, o.score = ez.score, o.reach_end = ez.reach_end, o.n_cigar = n;
-    o.n_diag = r_done + 1;
-    outs[jid] = o;
-  }
+  if (tid == 0)
+    finish_job(job, jid, ez, r_done + 1, w, /*abs_layout=*/false, stride, P, (const uint8_t *)TQ32, (const uint8_t *)QR32 + 4, sc,
+               cig_arena, cig_packed, cig_counter, outs);
 }
 
 constexpr size_t kSmemMax = 200 * 1024;
@@ -437,6 +624,14 @@ void launch_class(const std::vector<int> &ids, size_t smem, const int *d_ids_bas
 
 }  // namespace
 
+// first-pass gap fills whose band cannot bind and whose target window fits one warp's registers: K5a
+static inline bool is_small_fill(const KswJob &j) {
+  static const bool off = getenv("PGMM_NO_FILL_KERNEL") != nullptr;
+  if (off) return false;
+  const int mx = j.qlen > j.tlen ? j.qlen : j.tlen;
+  return j.flag == KSW_APPROX_MAX && (j.w < 0 || j.w >= mx) && j.tlen <= kFillMaxT && j.qlen <= kFillMaxQ && j.qlen > 0 && j.tlen > 0;
+}
+
 KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
   Geom g = make_geom(qlen, tlen, w, flag);
   KswGeom o;
@@ -445,7 +640,7 @@ KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
 }
 
 struct KswEngine::Impl {
-  static constexpr int kClasses = 20;  // 5 CTA widths x 4 state-size tiers
+  static constexpr int kClasses = 21;  // 5 CTA widths x 4 state-size tiers + the small first-pass fills
   cudaStream_t cls_stream[kClasses] = {};
   cudaEvent_t cls_done[kClasses] = {}, fork = nullptr;
   DevBuf<KswJob> d_jobs;
@@ -503,6 +698,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       continue;
     }
     geo[i] = make_geom(j.qlen, j.tlen, j.w, j.flag);
+    if (is_small_fill(j)) geo[i].p_bytes = (size_t)geo[i].n_row * (size_t)geo[i].T;  // rows indexed by target position
     order.push_back((int)i);
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return geo[a].p_bytes > geo[b].p_bytes; });
@@ -536,6 +732,12 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       const int ww = jobs[i].w < 0 ? INT32_MAX : jobs[i].w;
       const int front = std::min(std::min(jobs[i].qlen, jobs[i].tlen), ww < INT32_MAX ? ww + 1 : INT32_MAX);
       const int words = (front + 32 + 3) / 4;
+      if (is_small_fill(jobs[i])) {
+        cls[20].push_back((int)k);
+        cls_smem[20] = std::max<size_t>(cls_smem[20], (size_t)jobs[i].qlen);  // here: the longest query of the class
+        res.cells += (uint64_t)jobs[i].qlen * jobs[i].tlen;
+        continue;
+      }
       int nt_tier, sm_tier;
       if (sb <= 6 * 1024 && words <= 96) nt_tier = 0;  // small fills: one warp, a few words per lane
       else nt_tier = words <= 64 ? 1 : words <= 128 ? 2 : words <= 256 ? 3 : 4;
@@ -572,6 +774,19 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
 #define PGMM_LAUNCH(NT, SMEM)                                                                                                     \
   launch_class<NT>(cls[c], SMEM, m.d_ids.p, cls_off[c], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, \
                    m.cig_packed.p, m.d_counter.p, cs)
+      if (c == 20) {
+        const int q_cap = ((int)cls_smem[20] + 15) / 16 * 16;
+        const size_t per_warp = ((size_t)(kFillMaxT + 16) + (q_cap + 32) + 4 * (size_t)(q_cap + 4 * kFillMaxT) + 15) / 16 * 16;
+        static bool attr_set = false;
+        if (!attr_set) {
+          PGMM_CUDA(cudaFuncSetAttribute(ksw_fill_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+          attr_set = true;
+        }
+        const int nj = (int)cls[20].size();
+        ksw_fill_small_kernel<<<(nj + kFillWarps - 1) / kFillWarps, kFillWarps * 32, per_warp * kFillWarps, cs>>>(
+            m.d_jobs.p, m.d_ids.p + cls_off[20], nj, d_q, d_t, sc, q_cap, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p);
+        PGMM_CUDA(cudaGetLastError());
+      } else
       switch (c / 4) {
         case 0: PGMM_LAUNCH(32, cls_smem[c]); break;
         case 1: PGMM_LAUNCH(64, cls_smem[c]); break;

@@ -103,3 +103,14 @@ FLAG_LEFT_EXT = 0x40 | 0x02 | 0x80
 FLAG_FILL1 = 0x08
 FLAG_FILL2 = 0
 FLAG_RIGHT_EXT = 0x40
+
+
+def orc_extd2_unbanded(lib, q, t, mat, gq, ge, gq2, ge2, zdrop, end_bonus, flag):
+    ez = orc_ez_t()
+    cig = np.zeros(len(q) + len(t) + 2, dtype=np.uint32)
+    ovf = C.c_int(0)
+    lib.orc_ksw_extd2_unbanded(len(q), C.c_void_p(q.ctypes.data), len(t), C.c_void_p(t.ctypes.data), C.c_void_p(mat.ctypes.data),
+                               gq, ge, gq2, ge2, zdrop, end_bonus, flag, C.byref(ez), C.c_void_p(cig.ctypes.data), C.byref(ovf))
+    return dict(max=ez.max, zdropped=ez.zdropped, max_q=ez.max_q, max_t=ez.max_t, mqe=ez.mqe, mqe_t=ez.mqe_t,
+                mte=ez.mte, mte_q=ez.mte_q, score=ez.score, reach_end=ez.reach_end,
+                cigar=tuple(int(c) for c in cig[:ez.n_cigar])), ovf.value

@@ -110,3 +110,24 @@ def test_ksw_edge_cases(ref):
 
 def kswref_neg():
     return -0x40000000
+
+
+def test_small_fill_kernel_k5a(ref):
+    """K5a (16-bit lanes, real cells only) takes the first-pass gap fills with tlen <= 256, qlen <= 1024 and a band that
+    cannot bind: every small shape, the size limits, long queries, Ns, all presets."""
+    rng = np.random.default_rng(21)
+    probs = {p: [] for p in PRESETS}
+    for ql in range(1, 14):
+        for tl in range(1, 14):
+            q = rng.integers(0, 4, size=ql).astype(np.uint8)
+            t = rng.integers(0, 4, size=tl).astype(np.uint8)
+            probs[list(PRESETS)[(ql + tl) % 3]].append((q, t, 150001, kswref.FLAG_FILL1, 200, -1))
+    shapes = [(256, 256), (255, 256), (1024, 256), (1023, 3), (1, 256), (256, 1), (700, 64), (31, 33), (32, 32), (64, 63), (65, 64),
+              (200, 201), (205, 231), (300, 129), (128, 127)]
+    for i, (ql, tl) in enumerate(shapes * 3):
+        q, t = kswref.random_pair(rng, ql, tl, div=float(rng.choice([0.0, 0.02, 0.3])), indel=float(rng.choice([0.0, 0.03])),
+                                  n_frac=float(rng.choice([0.0, 0.03])), big_indel=int(rng.choice([0, 0, 40])))
+        w = max(ql, tl) + int(rng.choice([0, 5, 150001]))
+        probs[list(PRESETS)[i % 3]].append((q, t, w, kswref.FLAG_FILL1, 200, -1))
+    for preset, ps in probs.items():
+        check(ps, preset, ref)

@@ -49,3 +49,40 @@ def test_oracle_extd2_matches_reference(ref):
         assert got == want, (len(q), len(t), w, hex(flag), preset, zdrop, end_bonus)
         n += 1
     assert n == 600
+
+
+def test_unbanded_restatement_without_lane_artefacts(ref):
+    """When the band cannot bind (every gap fill), evaluating only real cells in plain int arithmetic gives the
+    reference's result, and no value ever leaves the signed-byte range (so byte wrap-around is never exercised)."""
+    orc = kswref.load_oracle()
+    rng = np.random.default_rng(77)
+    n = 0
+    for i in range(700):
+        kind = i % 5
+        if kind == 0:
+            ql, tl = int(rng.integers(1, 50)), int(rng.integers(1, 50))
+        elif kind == 1:
+            ql, tl = int(rng.integers(180, 260)), int(rng.integers(180, 260))
+        elif kind == 2:
+            ql, tl = int(rng.integers(1, 30)), int(rng.integers(200, 900))
+        elif kind == 3:
+            ql, tl = int(rng.integers(300, 1200)), int(rng.integers(300, 1200))
+        else:
+            ql = tl = int(rng.integers(1, 30)) * 16
+        div = float(rng.choice([0.0, 0.01, 0.1, 0.75]))
+        q, t = kswref.random_pair(rng, ql, tl, div=div, indel=float(rng.choice([0.0, 0.02, 0.2])),
+                                  n_frac=float(rng.choice([0.0, 0.0, 0.05, 0.5])), big_indel=int(rng.choice([0, 0, 60, 400])))
+        if i % 11 == 0:
+            q = rng.integers(0, 5, size=ql).astype(np.uint8)  # unrelated, with Ns
+        flag = [kswref.FLAG_FILL1, kswref.FLAG_FILL2, kswref.FLAG_RIGHT_EXT, kswref.FLAG_LEFT_EXT][int(rng.integers(0, 4))]
+        preset = list(PRESETS)[int(rng.integers(0, 3))]
+        a, b, gq, ge, gq2, ge2 = PRESETS[preset]
+        mat = kswref.simple_mat(a, b, 1)
+        zdrop, end_bonus = int(rng.choice([200, 200, 30])), int(rng.choice([-1, 7]))
+        w = max(ql, tl) + int(rng.choice([0, 1, 150001]))
+        want = kswref.ref_extd2(ref, q, t, mat, gq, ge, gq2, ge2, w, zdrop, end_bonus, flag)
+        got, overflow = kswref.orc_extd2_unbanded(orc, q, t, mat, gq, ge, gq2, ge2, zdrop, end_bonus, flag)
+        assert overflow == 0, (i, ql, tl, preset)
+        assert got == want, (i, ql, tl, hex(flag), preset)
+        n += 1
+    assert n == 700
