@@ -8,8 +8,10 @@
 // host threads, one query per thread, overlapped across the queries of a batch.
 #include "chain.h"
 
+#include <algorithm>
 #include <cassert>
 #include <cstring>
+#include <set>
 
 namespace pgmm {
 
@@ -373,8 +375,16 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
   std::vector<int64_t> p(n);
   std::vector<int32_t> f(n), t(n, 0), v(n);
   Pool pool;
-  MinTree outer(pool), inner(pool);
+  MinTree outer(pool);
   int64_t i0 = 0, st = 0, st_inner = 0;
+  // The second ("inner") tree of the reference is only ever searched for a floor element and walked backwards in key
+  // order (lchain.c:323-348): what it returns depends on the SET of anchors it holds, not on its shape.  That set is
+  // the index window [st_inner, i0): a small window is kept as a sorted array of (y, index) (insertions and evictions
+  // are short memmoves), a large one (repeats) is mirrored in an ordered set.
+  constexpr int64_t kMirrorOn = 1024, kMirrorOff = 256;
+  std::set<std::pair<int32_t, int64_t>> mirror;
+  bool mirrored = false;
+  std::vector<std::pair<int32_t, int64_t>> near;  // ascending, the members of the window while !mirrored
 
   for (int64_t i = 0; i < n; ++i) {
     int64_t max_j = -1;
@@ -389,10 +399,9 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
         nq.pri = -(f[j] + 0.5 * cp.pen_gap * ((int32_t)a[j].x + (int32_t)a[j].y));
         outer.insert(q);
         if (max_dist_inner > 0) {
-          const int32_t r = pool.alloc();
-          Node &nr = pool.nd[r];
-          nr.y = pool.nd[q].y, nr.i = j, nr.pri = pool.nd[q].pri;
-          inner.insert(r);
+          const std::pair<int32_t, int64_t> key((int32_t)a[j].y, j);
+          if (mirrored) mirror.insert(key);
+          else near.insert(std::upper_bound(near.begin(), near.end(), key), key);
         }
       }
       i0 = i;
@@ -405,10 +414,24 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
     }
     if (max_dist_inner > 0) {
       while (st_inner < i && (a[i].x >> 32 != a[st_inner].x >> 32 || a[i].x > a[st_inner].x + max_dist_inner ||
-                              (int64_t)inner.size() > cp.cap_rmq_size)) {
-        const int32_t q = inner.erase((int32_t)a[st_inner].y, st_inner);
-        if (q != NIL) pool.release(q);
+                              std::max<int64_t>(0, i0 - st_inner) > cp.cap_rmq_size)) {
+        if (st_inner < i0) {
+          const std::pair<int32_t, int64_t> key((int32_t)a[st_inner].y, st_inner);
+          if (mirrored) mirror.erase(key);
+          else near.erase(std::lower_bound(near.begin(), near.end(), key));
+        }
         ++st_inner;
+      }
+      const int64_t in_size = std::max<int64_t>(0, i0 - st_inner);
+      if (!mirrored && in_size > kMirrorOn) {
+        mirror.clear();
+        mirror.insert(near.begin(), near.end());
+        near.clear();
+        mirrored = true;
+      } else if (mirrored && in_size < kMirrorOff) {
+        near.assign(mirror.begin(), mirror.end());
+        mirror.clear();
+        mirrored = false;
       }
     }
     // best predecessor by priority inside the query window, then a bounded scan of the near neighbourhood (:313-351)
@@ -419,26 +442,36 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
       int64_t j = pool.nd[qn].i;
       int32_t sc = f[j] + link_score(a[i], a[j], cp.pen_gap, cp.pen_skip, &exact, &width);
       if (width <= bw && sc > max_f) max_f = sc, max_j = j;
-      if (!exact && inner.root != NIL && (int32_t)a[i].y > 0) {
-        const int32_t lo = inner.floor_node((int32_t)a[i].y - 1, n);
-        if (lo != NIL) {
-          MinTree::Cursor cur;
-          inner.seek(lo, cur);
-          while (cur.top >= 0) {
-            const Node &nq = pool.nd[cur.stack[cur.top]];
-            if (nq.y < (int32_t)a[i].y - max_dist_inner) break;
-            j = nq.i;
-            sc = f[j] + link_score(a[i], a[j], cp.pen_gap, cp.pen_skip, nullptr, &width);
-            if (width <= bw) {
-              if (sc > max_f) {
-                max_f = sc, max_j = j;
-                if (n_skip > 0) --n_skip;
-              } else if (t[j] == (int32_t)i) {
-                if (++n_skip > cp.max_chn_skip) break;
-              }
-              if (p[j] >= 0) t[p[j]] = (int32_t)i;
+      if (!exact && max_dist_inner > 0 && i0 > st_inner && (int32_t)a[i].y > 0) {
+        const int32_t y_hi = (int32_t)a[i].y - 1, y_lo = (int32_t)a[i].y - max_dist_inner;
+        // visits window members in descending (y, index) order from the floor of (y_hi, n), like the reference's cursor
+        const auto visit = [&](int64_t jj) -> bool {
+          j = jj;
+          sc = f[j] + link_score(a[i], a[j], cp.pen_gap, cp.pen_skip, nullptr, &width);
+          if (width <= bw) {
+            if (sc > max_f) {
+              max_f = sc, max_j = j;
+              if (n_skip > 0) --n_skip;
+            } else if (t[j] == (int32_t)i) {
+              if (++n_skip > cp.max_chn_skip) return false;
             }
-            if (!inner.prev(cur)) break;
+            if (p[j] >= 0) t[p[j]] = (int32_t)i;
+          }
+          return true;
+        };
+        if (mirrored) {
+          auto it = mirror.upper_bound(std::make_pair(y_hi, n));
+          while (it != mirror.begin()) {
+            --it;
+            if (it->first < y_lo) break;
+            if (!visit(it->second)) break;
+          }
+        } else {
+          auto it = std::upper_bound(near.begin(), near.end(), std::make_pair(y_hi, n));
+          while (it != near.begin()) {
+            --it;
+            if (it->first < y_lo) break;
+            if (!visit(it->second)) break;
           }
         }
       }
