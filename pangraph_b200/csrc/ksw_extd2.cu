@@ -362,6 +362,235 @@ __global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const K
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K5b: wide problems whose band cannot bind -- the long gap fills a chain makes across an inversion or a big indel
+// (up to ~10k x 10k), first pass (approximate max) and second pass (exact max with z-drop).  Same recurrence and lane
+// format as K5a, one CTA per problem: pair p = slot*NT + thread, KP slots per thread in registers.  A pair's left
+// neighbour comes by shuffle; across warp boundaries it comes from a small shared-memory mailbox that the last lane
+// of every warp fills at the end of an anti-diagonal (double-buffered by parity), so ONE block barrier per
+// anti-diagonal is enough.  All threads keep the scalar bookkeeping (tracked score, running maximum, z-drop state)
+// redundantly from values published through that mailbox, so no thread ever waits for a "leader".
+// ---------------------------------------------------------------------------------------------------------------
+struct WideMail {      // per parity
+  uint32_t x[32][8], v[32][8], x2[32][8];  // [warp][slot]: new x, v, x2 of the warp's last pair
+  int32_t hhi[32][8];                      // and the exact-mode H of its high cell
+  long long wbest[32];                     // per-warp best (H, rank) key
+  int32_t d0, d1;                          // v[last], u[last+1] for the tracked score
+  int32_t hen, hst0;                       // H[en0], H[st0] of this anti-diagonal
+};
+
+template <int NW, int KP, bool EXACT>
+__global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
+                                                                const uint8_t *__restrict__ qcodes, const uint8_t *__restrict__ tcodes,
+                                                                KswScoring sc, uint8_t *__restrict__ p_arena,
+                                                                uint32_t *__restrict__ cig_arena, KswOut *__restrict__ outs,
+                                                                uint32_t *__restrict__ cig_packed, unsigned long long *__restrict__ cig_counter) {
+  constexpr int NT = NW * 32;
+  extern __shared__ uint32_t dyn_smem[];
+  __shared__ WideMail mail[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jid = job_ids[blockIdx.x];
+  const KswJob job = jobs[jid];
+  const int qlen = job.qlen, tlen = job.tlen;
+  int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
+  if (q2 + e2 < q + e) {
+    int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t;
+  }
+  const int Tp = (tlen + 15) / 16 * 16, n_row = qlen + tlen - 1, qe = q + e;
+  // shared memory: target bytes [Tp + 16], reversed query bytes [4 + qlen + pad], reversed query as 16-bit codes with
+  // Tp + 16 zero elements in front and behind
+  uint8_t *TQ8 = (uint8_t *)dyn_smem;
+  const int qr_bytes = (qlen + 4 + 28 + 15) / 16 * 16;
+  uint8_t *QRraw = TQ8 + Tp + 16, *QR8 = QRraw + 4;
+  uint16_t *QH = (uint16_t *)(QRraw + qr_bytes);
+  const int qh_pad = Tp + 16, qh_len = qlen + 2 * qh_pad;
+  for (int i = tid; i < (Tp + 16) / 4; i += NT) ((uint32_t *)TQ8)[i] = 0;
+  for (int i = tid; i < qr_bytes / 4; i += NT) ((uint32_t *)QRraw)[i] = 0;
+  for (int i = tid; i < (qh_len + 1) / 2; i += NT) ((uint32_t *)QH)[i] = 0;
+  __syncthreads();
+  {
+    const uint8_t *tb = tcodes + job.t_off, *qb = qcodes + job.q_off;
+    for (int i = tid; i < tlen; i += NT) TQ8[i] = tb[i];
+    for (int i = tid; i < qlen; i += NT) {
+      const uint8_t c = qb[qlen - 1 - i];
+      QR8[i] = c;
+      QH[qh_pad + i] = c;
+    }
+  }
+  __syncthreads();
+
+  const int long_thres0 = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+  const int long_thres = (q2 + e2 + long_thres0 * e2 > q + e + long_thres0 * e) ? long_thres0 + 1 : long_thres0;
+  const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+  const int scN = sc.sc_ambi == 0 ? -e2 : -(sc.sc_ambi < 0 ? -sc.sc_ambi : sc.sc_ambi);
+  const uint32_t MCH = pk2(sc.sc_mch), MIS = pk2(sc.sc_mis), SCN = pk2(scN), ONE = 0x00010001u;
+  const uint32_t DMCH = (uint32_t)(sc.sc_mch - sc.sc_mis);
+  const uint32_t QP = pk2(q), Q2P = pk2(q2), NQE = pk2(-q - e), NQE2 = pk2(-q2 - e2);
+  uint8_t *P = p_arena + job.p_off;
+
+  uint32_t U[KP], Y[KP], Y2[KP], V[KP], X[KP], X2[KP], TQ[KP];
+  int32_t HL[KP], HH[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    U[k] = Y[k] = V[k] = X[k] = NQE, Y2[k] = X2[k] = NQE2;
+    HL[k] = HH[k] = KSW_NEG_INF;
+    const int t = 2 * (NT * k + tid);
+    TQ[k] = t + 1 < Tp + 16 ? ((uint32_t)TQ8[t] | (uint32_t)TQ8[t + 1] << 16) : 0u;
+  }
+  EzState ez;
+  ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+  ez.max = 0, ez.score = ez.mqe = ez.mte = KSW_NEG_INF;
+  ez.zdropped = 0, ez.reach_end = 0;
+  int32_t H0 = 0, last = 0;
+  int r_done = 0;
+
+  for (int r = 0; r < n_row; ++r) {
+    r_done = r;
+    const int par = r & 1;
+    WideMail &in = mail[par ^ 1], &out = mail[par];
+    const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
+    const int ufirst = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+    const int p_lo = st0 >> 1, p_hi = en0 >> 1;
+    const int qbase = qh_pad + (qlen - 1 - r);  // halfword index of the query base that meets target position 0
+    uint8_t *prow = P + (size_t)r * Tp;
+    const int en1 = st0 + (en0 - st0) / 4 * 4, NB = (en1 - st0) >> 2;
+    long long best = LLONG_MIN;
+#pragma unroll
+    for (int k = KP - 1; k >= 0; --k) {
+      if (NT * k > p_hi || NT * k + NT - 1 < p_lo) continue;  // block-uniform
+      const int p = NT * k + tid;
+      uint32_t px = __shfl_up_sync(0xffffffffu, X[k], 1), pv = __shfl_up_sync(0xffffffffu, V[k], 1), px2 = __shfl_up_sync(0xffffffffu, X2[k], 1);
+      int32_t ph_old = EXACT ? __shfl_up_sync(0xffffffffu, HH[k], 1) : 0;
+      if (lane == 0) {  // previous warp's last pair, or the last pair of the previous slot, as of the previous anti-diagonal
+        if (warp > 0) px = in.x[warp - 1][k], pv = in.v[warp - 1][k], px2 = in.x2[warp - 1][k], ph_old = EXACT ? in.hhi[warp - 1][k] : 0;
+        else if (k > 0) px = in.x[NW - 1][k - 1], pv = in.v[NW - 1][k - 1], px2 = in.x2[NW - 1][k - 1], ph_old = EXACT ? in.hhi[NW - 1][k - 1] : 0;
+      }
+      uint32_t XT1 = __funnelshift_l(px, X[k], 16), VT1 = __funnelshift_l(pv, V[k], 16), X2T1 = __funnelshift_l(px2, X2[k], 16);
+      if (p == 0) {
+        XT1 = (XT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q - e);
+        X2T1 = (X2T1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q2 - e2);
+        VT1 = (VT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst;
+      }
+      uint32_t Uo = U[k], Yo = Y[k], Y2o = Y2[k];
+      if (en0 == r && (r >> 1) == p) {
+        if (r & 1) Uo = (Uo & 0x0000ffffu) | (uint32_t)(uint16_t)(int16_t)ufirst << 16, Yo = (Yo & 0x0000ffffu) | (NQE & 0xffff0000u), Y2o = (Y2o & 0x0000ffffu) | (NQE2 & 0xffff0000u);
+        else Uo = (Uo & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst, Yo = (Yo & 0xffff0000u) | (NQE & 0xffffu), Y2o = (Y2o & 0xffff0000u) | (NQE2 & 0xffffu);
+      }
+      const int qi = qbase + 2 * p;
+      const uint32_t qq = qi + 1 < qh_len ? ((uint32_t)QH[qi] | (uint32_t)QH[qi + 1] << 16) : 0u;
+      const uint32_t ne = __vminu2(TQ[k] ^ qq, ONE);
+      uint32_t Z = __vadd2(MIS, (ne ^ ONE) * DMCH);
+      const uint32_t isn = __vminu2((TQ[k] | qq) & 0x00040004u, ONE) * 0xffffu;
+      Z = (Z & ~isn) | (SCN & isn);
+      uint32_t A = __vadd2(XT1, VT1), B = __vadd2(Yo, Uo), A2 = __vadd2(X2T1, VT1), B2 = __vadd2(Y2o, Uo);
+      bool ph, pl;
+      uint32_t dl = 0, dh = 0;
+      Z = __vibmax_s16x2(Z, A, &ph, &pl);  dl = pl ? dl : 1u; dh = ph ? dh : 1u;
+      Z = __vibmax_s16x2(Z, B, &ph, &pl);  dl = pl ? dl : 2u; dh = ph ? dh : 2u;
+      Z = __vibmax_s16x2(Z, A2, &ph, &pl); dl = pl ? dl : 3u; dh = ph ? dh : 3u;
+      Z = __vibmax_s16x2(Z, B2, &ph, &pl); dl = pl ? dl : 4u; dh = ph ? dh : 4u;
+      Z = __vmins2(Z, MCH);
+      const uint32_t NZ = neg2(Z);
+      const uint32_t Un = __vadd2(Z, neg2(VT1)), Vn = __vadd2(Z, neg2(Uo));
+      const uint32_t T1 = __vadd2(NZ, QP), T2 = __vadd2(NZ, Q2P);
+      A = __vadd2(A, T1), B = __vadd2(B, T1), A2 = __vadd2(A2, T2), B2 = __vadd2(B2, T2);
+      (void)__vibmax_s16x2(A, ONE, &ph, &pl);  dl |= pl ? 0x08u : 0u; dh |= ph ? 0x08u : 0u;
+      (void)__vibmax_s16x2(B, ONE, &ph, &pl);  dl |= pl ? 0x10u : 0u; dh |= ph ? 0x10u : 0u;
+      (void)__vibmax_s16x2(A2, ONE, &ph, &pl); dl |= pl ? 0x20u : 0u; dh |= ph ? 0x20u : 0u;
+      (void)__vibmax_s16x2(B2, ONE, &ph, &pl); dl |= pl ? 0x40u : 0u; dh |= ph ? 0x40u : 0u;
+      A = __vmaxs2(A, 0u), B = __vmaxs2(B, 0u), A2 = __vmaxs2(A2, 0u), B2 = __vmaxs2(B2, 0u);
+      U[k] = Un, V[k] = Vn;
+      X[k] = __vadd2(A, NQE), Y[k] = __vadd2(B, NQE), X2[k] = __vadd2(A2, NQE2), Y2[k] = __vadd2(B2, NQE2);
+      if (p <= p_hi) *(uint16_t *)(prow + 2 * p) = (uint16_t)(dl | dh << 8);
+      const int t_lo = 2 * p, t_hi = 2 * p + 1;
+      if (EXACT) {  // H[t] += v[t] for st0 <= t < en0; H[en0] = H[en0-1] (previous anti-diagonal) + u[en0]   (:333-357)
+        const int32_t hl_old = HL[k];
+        if (r == 0) {
+          if (p == 0) HL[k] = lo16(Vn) - qe;
+        } else {
+          if (t_lo >= st0 && t_lo < en0) HL[k] += lo16(Vn);
+          else if (t_lo == en0) HL[k] = en0 > 0 ? ph_old + lo16(Un) : HL[k] + lo16(Vn);
+          if (t_hi >= st0 && t_hi < en0) HH[k] += hi16(Vn);
+          else if (t_hi == en0) HH[k] = hl_old + hi16(Un);
+        }
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const int t = hsel ? t_hi : t_lo;
+          if (t >= st0 && t <= en0) {
+            const int32_t h = hsel ? HH[k] : HL[k];
+            const int d = t - st0;
+            const int rank = t == en0 ? 0 : t < en1 ? 1 + (d & 3) * NB + (d >> 2) : 1 + 4 * NB + (t - en1);
+            const long long key = (long long)h * 4294967296LL + (long long)(0x7fffffff - rank);
+            best = best > key ? best : key;
+            if (t == en0) out.hen = h;
+            if (t == st0) out.hst0 = h;
+          }
+        }
+      } else {
+        if (t_lo == last) out.d0 = lo16(Vn);
+        if (t_hi == last) out.d0 = hi16(Vn);
+        if (t_lo == last + 1) out.d1 = lo16(Un);
+        if (t_hi == last + 1) out.d1 = hi16(Un);
+      }
+      if (lane == 31) {
+        out.x[warp][k] = X[k], out.v[warp][k] = V[k], out.x2[warp][k] = X2[k];
+        if (EXACT) out.hhi[warp][k] = HH[k];
+      }
+    }
+    if (EXACT) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = best > other ? best : other;
+      }
+      if (lane == 0) out.wbest[warp] = best;
+    }
+    __syncthreads();
+    // ---- scalar bookkeeping, done by every thread from the mailbox ----
+    if (EXACT) {
+      long long b = lane < NW ? out.wbest[lane] : LLONG_MIN;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, b, o);
+        b = b > other ? b : other;
+      }
+      const int rank = 0x7fffffff - (int)(uint32_t)(b & 0xffffffffLL);
+      const int32_t max_H = (int32_t)(b >> 32);
+      int32_t max_t;
+      if (rank == 0) max_t = en0;
+      else if (rank - 1 < 4 * NB) max_t = st0 + 4 * ((rank - 1) % NB) + (rank - 1) / NB;
+      else max_t = en1 + (rank - 1 - 4 * NB);
+      const int32_t hen = out.hen, hst0 = out.hst0;
+      if (en0 == tlen - 1 && hen > ez.mte) ez.mte = hen, ez.mte_q = r - en0;
+      if (r - st0 == qlen - 1 && hst0 > ez.mqe) ez.mqe = hst0, ez.mqe_t = st0;
+      bool brk = false;
+      if (max_H > ez.max) ez.max = max_H, ez.max_t = max_t, ez.max_q = r - max_t;
+      else if (max_t >= ez.max_t && r - max_t >= ez.max_q) {
+        const int tl = max_t - ez.max_t, ql = (r - max_t) - ez.max_q, l = tl > ql ? tl - ql : ql - tl;
+        if (job.zdrop >= 0 && ez.max - max_H > job.zdrop + l * e2) ez.zdropped = 1, brk = true;
+      }
+      if (!brk && r == n_row - 1 && en0 == tlen - 1) ez.score = hen;
+      if (brk) break;
+    } else {
+      const int d0 = out.d0, d1 = out.d1;
+      if (r > 0) {
+        const bool in0 = last >= st0 && last <= en0, in1 = last + 1 >= st0 && last + 1 <= en0;
+        if (in0 && in1) {
+          if (d0 > d1) H0 += d0;
+          else H0 += d1, ++last;
+        } else if (in0) H0 += d0;
+        else ++last, H0 += d1;
+      } else H0 = d0 - qe, last = 0;
+      if (r == n_row - 1) ez.score = H0;
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (tid == 0)
+    finish_job(job, jid, ez, r_done + 1, tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed,
+               cig_counter, outs);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
                                                        const uint8_t *__restrict__ qcodes,
@@ -632,6 +861,23 @@ static inline bool is_small_fill(const KswJob &j) {
   return j.flag == KSW_APPROX_MAX && (j.w < 0 || j.w >= mx) && j.tlen <= kFillMaxT && j.qlen <= kFillMaxQ && j.qlen > 0 && j.tlen > 0;
 }
 
+// wide problems whose band cannot bind: K5b.  Returns the width configuration (0..3) or -1.
+static inline int wide_fill_cfg(const KswJob &j) {
+  static const bool off = getenv("PGMM_NO_FILL_KERNEL") != nullptr;
+  if (off || j.qlen <= 0 || j.tlen <= 0) return -1;
+  if (j.flag != KSW_APPROX_MAX && j.flag != 0) return -1;
+  const int mx = j.qlen > j.tlen ? j.qlen : j.tlen;
+  if (!(j.w < 0 || j.w >= mx)) return -1;
+  const size_t Tp = (size_t)(j.tlen + 15) / 16 * 16;
+  const size_t smem = (Tp + 16) + (size_t)(j.qlen + 4 + 28 + 15) / 16 * 16 + 2 * ((size_t)j.qlen + 2 * (Tp + 16)) + 64;
+  if (smem > 180 * 1024) return -1;
+  return j.tlen <= 256 ? 0 : j.tlen <= 1024 ? 1 : j.tlen <= 4096 ? 2 : j.tlen <= 8192 ? 3 : -1;
+}
+static inline size_t wide_fill_smem(const KswJob &j) {
+  const size_t Tp = (size_t)(j.tlen + 15) / 16 * 16;
+  return (Tp + 16) + (size_t)(j.qlen + 4 + 28 + 15) / 16 * 16 + 2 * ((size_t)j.qlen + 2 * (Tp + 16)) + 64;
+}
+
 KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
   Geom g = make_geom(qlen, tlen, w, flag);
   KswGeom o;
@@ -640,7 +886,7 @@ KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
 }
 
 struct KswEngine::Impl {
-  static constexpr int kClasses = 21;  // 5 CTA widths x 4 state-size tiers + the small first-pass fills
+  static constexpr int kClasses = 29;  // 5 CTA widths x 4 state-size tiers, K5a (20), K5b: 4 widths x {approximate, exact} (21..28)
   cudaStream_t cls_stream[kClasses] = {};
   cudaEvent_t cls_done[kClasses] = {}, fork = nullptr;
   DevBuf<KswJob> d_jobs;
@@ -698,7 +944,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       continue;
     }
     geo[i] = make_geom(j.qlen, j.tlen, j.w, j.flag);
-    if (is_small_fill(j)) geo[i].p_bytes = (size_t)geo[i].n_row * (size_t)geo[i].T;  // rows indexed by target position
+    if (is_small_fill(j) || wide_fill_cfg(j) >= 0) geo[i].p_bytes = (size_t)geo[i].n_row * (size_t)geo[i].T;  // rows indexed by target position
     order.push_back((int)i);
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return geo[a].p_bytes > geo[b].p_bytes; });
@@ -735,6 +981,13 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       if (is_small_fill(jobs[i])) {
         cls[20].push_back((int)k);
         cls_smem[20] = std::max<size_t>(cls_smem[20], (size_t)jobs[i].qlen);  // here: the longest query of the class
+        res.cells += (uint64_t)jobs[i].qlen * jobs[i].tlen;
+        continue;
+      }
+      if (const int wc = wide_fill_cfg(jobs[i]); wc >= 0) {
+        const int c = 21 + 2 * wc + (jobs[i].flag == 0 ? 1 : 0);
+        cls[c].push_back((int)k);
+        cls_smem[c] = std::max(cls_smem[c], wide_fill_smem(jobs[i]));
         res.cells += (uint64_t)jobs[i].qlen * jobs[i].tlen;
         continue;
       }
@@ -786,6 +1039,29 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
         ksw_fill_small_kernel<<<(nj + kFillWarps - 1) / kFillWarps, kFillWarps * 32, per_warp * kFillWarps, cs>>>(
             m.d_jobs.p, m.d_ids.p + cls_off[20], nj, d_q, d_t, sc, q_cap, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p);
         PGMM_CUDA(cudaGetLastError());
+      } else if (c > 20) {
+#define PGMM_WIDE(NW, KP, EX)                                                                                                   \
+  do {                                                                                                                          \
+    static bool attr_set = false;                                                                                               \
+    if (!attr_set) {                                                                                                            \
+      PGMM_CUDA(cudaFuncSetAttribute(ksw_fill_wide_kernel<NW, KP, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); \
+      attr_set = true;                                                                                                          \
+    }                                                                                                                           \
+    ksw_fill_wide_kernel<NW, KP, EX><<<(unsigned)cls[c].size(), NW * 32, cls_smem[c], cs>>>(                                    \
+        m.d_jobs.p, m.d_ids.p + cls_off[c], d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p); \
+    PGMM_CUDA(cudaGetLastError());                                                                                              \
+  } while (0)
+        switch (c - 21) {
+          case 0: PGMM_WIDE(4, 1, false); break;
+          case 1: PGMM_WIDE(4, 1, true); break;
+          case 2: PGMM_WIDE(8, 2, false); break;
+          case 3: PGMM_WIDE(8, 2, true); break;
+          case 4: PGMM_WIDE(16, 4, false); break;
+          case 5: PGMM_WIDE(16, 4, true); break;
+          case 6: PGMM_WIDE(16, 8, false); break;
+          default: PGMM_WIDE(16, 8, true); break;
+        }
+#undef PGMM_WIDE
       } else
       switch (c / 4) {
         case 0: PGMM_LAUNCH(32, cls_smem[c]); break;

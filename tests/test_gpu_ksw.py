@@ -131,3 +131,24 @@ def test_small_fill_kernel_k5a(ref):
         probs[list(PRESETS)[i % 3]].append((q, t, w, kswref.FLAG_FILL1, 200, -1))
     for preset, ps in probs.items():
         check(ps, preset, ref)
+
+
+def test_wide_fill_kernel_k5b(ref):
+    """K5b takes every problem whose band cannot bind that K5a does not: first and second (exact, z-drop) passes of the
+    long fills across inversions / big indels.  Shapes around the four width configurations, early z-drops, Ns."""
+    rng = np.random.default_rng(31)
+    probs = []
+    shapes = [(3, 2), (40, 255), (256, 256), (257, 257), (300, 1024), (1025, 1025), (1100, 700), (2000, 2100), (4096, 4096), (4097, 3000),
+              (5000, 6000), (900, 8192), (8000, 8192), (1200, 31), (64, 2049)]
+    for i, (ql, tl) in enumerate(shapes * 2):
+        div = float(rng.choice([0.01, 0.05, 0.3]))
+        q, t = kswref.random_pair(rng, ql, tl, div=div, indel=0.01, n_frac=float(rng.choice([0.0, 0.01])),
+                                  big_indel=int(rng.choice([0, 0, 300])))
+        if i % 5 == 0 and ql > 600:  # an unrelated stretch in the middle: the exact pass z-drops inside it
+            a = ql // 3
+            q[a:a + ql // 3] = rng.integers(0, 4, size=ql // 3)
+        flag = kswref.FLAG_FILL2 if i % 2 else kswref.FLAG_FILL1
+        probs.append((q, t, max(ql, tl) + int(rng.choice([0, 150001])), flag, int(rng.choice([200, 200, 60])), -1))
+    check(probs, "asm10", ref)
+    check([p for p in probs if len(p[0]) <= 2100], "asm5", ref)
+    check([p for p in probs if len(p[0]) <= 2100], "asm20", ref)
