@@ -4,7 +4,7 @@
 One ROUND = one find_matches call of a guide-tree leaf merge: two related synthetic 5-Mbp genomes (1 % divergence,
 10 rearrangements each) are indexed and aligned all-vs-all, i.e. mm_idx_str + mm_mapopt_update + one
 mm_map per sequence in the reference, index kernels + pgmm_map_batch here.
-One STEP = `--rounds-per-step` (default 32) such rounds, `--workers` (default 16) of them in flight at any moment: sibling leaf merges of the guide tree are independent
+One STEP = `--rounds-per-step` (default 48) such rounds, `--workers` (default 24) of them in flight at any moment: sibling leaf merges of the guide tree are independent
 (merge_graphs only reads its two children), so a rank keeps several of them in flight, one host thread and one CUDA
 stream each.  bp per step = total length of the genomes of its rounds.
 
@@ -197,7 +197,7 @@ def ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.environ.setdefault("PGMM_CONTEXTS", str(max(8, args.workers)))
-    os.environ.setdefault("PGMM_ARENA_GB", "4")
+    os.environ.setdefault("PGMM_ARENA_GB", "3")
     L = abi.lib()
     abi.set_device(local)
     from concurrent.futures import ThreadPoolExecutor
@@ -353,8 +353,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--rounds-per-step", type=int, default=32, help="independent leaf-merge rounds a rank keeps in flight per step")
-    ap.add_argument("--workers", type=int, default=16, help="host threads driving rounds concurrently (one CUDA stream each)")
+    ap.add_argument("--rounds-per-step", type=int, default=48, help="independent leaf-merge rounds a rank keeps in flight per step")
+    ap.add_argument("--workers", type=int, default=24, help="host threads driving rounds concurrently (one CUDA stream each)")
     ap.add_argument("--pool", type=int, default=16, help="distinct genome pairs generated per rank (steps cycle through them)")
     ap.add_argument("--ref-sample-len", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
