@@ -901,12 +901,14 @@ struct KswEngine::Impl {
   PinBuf<KswOut> h_outs;
   PinBuf<uint32_t> h_cigar;
   PinBuf<unsigned long long> h_counter;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a0 = nullptr, ev_a1 = nullptr;
 };
 
 KswEngine::KswEngine() : impl_(new Impl) {
   PGMM_CUDA(cudaEventCreate(&impl_->ev0));
   PGMM_CUDA(cudaEventCreate(&impl_->ev1));
+  PGMM_CUDA(cudaEventCreate(&impl_->ev_a0));
+  PGMM_CUDA(cudaEventCreate(&impl_->ev_a1));
   PGMM_CUDA(cudaEventCreateWithFlags(&impl_->fork, cudaEventDisableTiming));
   for (int c = 0; c < Impl::kClasses; ++c) {
     PGMM_CUDA(cudaStreamCreateWithFlags(&impl_->cls_stream[c], cudaStreamNonBlocking));
@@ -916,6 +918,8 @@ KswEngine::KswEngine() : impl_(new Impl) {
 KswEngine::~KswEngine() {
   cudaEventDestroy(impl_->ev0);
   cudaEventDestroy(impl_->ev1);
+  cudaEventDestroy(impl_->ev_a0);
+  cudaEventDestroy(impl_->ev_a1);
   cudaEventDestroy(impl_->fork);
   for (int c = 0; c < Impl::kClasses; ++c) cudaStreamDestroy(impl_->cls_stream[c]), cudaEventDestroy(impl_->cls_done[c]);
   delete impl_;
@@ -928,6 +932,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
   res.cig_start.assign(n + 1, 0);
   res.cigar.clear();
   res.cells = 0, res.launches = 0, res.kernel_ms = 0.f;
+  res.k5a_ms = 0.f, res.k5a_cells = 0, res.k5a_bases = 0, res.k5a_launches = 0;
   if (n == 0) return;
   Impl &m = *impl_;
 
@@ -982,6 +987,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
         cls[20].push_back((int)k);
         cls_smem[20] = std::max<size_t>(cls_smem[20], (size_t)jobs[i].qlen);  // here: the longest query of the class
         res.cells += (uint64_t)jobs[i].qlen * jobs[i].tlen;
+        res.k5a_cells += (uint64_t)jobs[i].qlen * jobs[i].tlen, res.k5a_bases += (uint64_t)jobs[i].qlen + jobs[i].tlen;
         continue;
       }
       if (const int wc = wide_fill_cfg(jobs[i]); wc >= 0) {
@@ -1036,9 +1042,12 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
           attr_set = true;
         }
         const int nj = (int)cls[20].size();
+        PGMM_CUDA(cudaEventRecord(m.ev_a0, cs));
         ksw_fill_small_kernel<<<(nj + kFillWarps - 1) / kFillWarps, kFillWarps * 32, per_warp * kFillWarps, cs>>>(
             m.d_jobs.p, m.d_ids.p + cls_off[20], nj, d_q, d_t, sc, q_cap, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p);
         PGMM_CUDA(cudaGetLastError());
+        PGMM_CUDA(cudaEventRecord(m.ev_a1, cs));
+        ++res.k5a_launches;
       } else if (c > 20) {
 #define PGMM_WIDE(NW, KP, EX)                                                                                                   \
   do {                                                                                                                          \
@@ -1086,6 +1095,10 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     float ms = 0.f;
     PGMM_CUDA(cudaEventElapsedTime(&ms, m.ev0, m.ev1));
     res.kernel_ms += ms;
+    if (!cls[20].empty()) {
+      PGMM_CUDA(cudaEventElapsedTime(&ms, m.ev_a0, m.ev_a1));
+      res.k5a_ms += ms;
+    }
     const size_t tot = (size_t)*hc, base = res.cigar.size();
     if (tot > 0) {
       uint32_t *hcig = m.h_cigar.ensure(tot);

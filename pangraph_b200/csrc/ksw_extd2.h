@@ -60,7 +60,11 @@ struct KswBatchResult {
   std::vector<uint64_t> cig_start;
   uint64_t cells = 0;               // in-band cells actually asked for (for the GCUPS / roofline figures)
   int launches = 0;
-  float kernel_ms = 0.f;            // CUDA-event time of the DP kernels alone
+  float kernel_ms = 0.f;            // CUDA-event time of the DP kernels alone (all launch classes of a wave, concurrent)
+  // the dominant kernel on its own (K5a, first-pass gap fills): CUDA events on the stream it is launched on
+  float k5a_ms = 0.f;
+  uint64_t k5a_cells = 0, k5a_bases = 0;
+  int k5a_launches = 0;
 };
 
 class KswEngine {
