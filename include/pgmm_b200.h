@@ -301,7 +301,8 @@ PGMM_API int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, cons
  * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] kernel launches [11..16] wall ms of the phases of
  * pgmm_map_batch (encode, seeding, sort+chain+plan, DP waves, stitching between waves, final filters)
  * [17] host->device bytes [18] device->host bytes [19] bases read by the DP kernels [20] cudaMalloc calls
- * [21..24] the dominant kernel (K5a, first-pass gap fills) alone: ms on its own stream, cells, bases read, launches */
+ * [21..32] per DP kernel family (K5 generic, K5a small fills, K5b wide fills): ms on the launch streams, cells, bases read,
+ * launches */
 PGMM_API void pgmm_get_stats(double *out, int n, int reset);
 
 #ifdef __cplusplus

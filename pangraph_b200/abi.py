@@ -145,7 +145,9 @@ def set_device(device):
 
 STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_cells", "dp_waves", "bases_mapped",
               "bases_indexed", "batches", "launches", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch", "t_final",
-              "h2d_bytes", "d2h_bytes", "dp_seq_bytes", "device_mallocs", "k5a_ms", "k5a_cells", "k5a_bases", "k5a_launches")
+              "h2d_bytes", "d2h_bytes", "dp_seq_bytes", "device_mallocs",
+              "k5_ms", "k5_cells", "k5_bases", "k5_launches", "k5a_ms", "k5a_cells", "k5a_bases", "k5a_launches",
+              "k5b_ms", "k5b_cells", "k5b_bases", "k5b_launches")
 
 
 def get_stats(reset=False):

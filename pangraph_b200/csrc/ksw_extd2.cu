@@ -901,27 +901,27 @@ struct KswEngine::Impl {
   PinBuf<KswOut> h_outs;
   PinBuf<uint32_t> h_cigar;
   PinBuf<unsigned long long> h_counter;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_a0 = nullptr, ev_a1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t cls_t0[kClasses] = {}, cls_t1[kClasses] = {};  // timing of each class launch on its own stream
 };
 
 KswEngine::KswEngine() : impl_(new Impl) {
   PGMM_CUDA(cudaEventCreate(&impl_->ev0));
   PGMM_CUDA(cudaEventCreate(&impl_->ev1));
-  PGMM_CUDA(cudaEventCreate(&impl_->ev_a0));
-  PGMM_CUDA(cudaEventCreate(&impl_->ev_a1));
   PGMM_CUDA(cudaEventCreateWithFlags(&impl_->fork, cudaEventDisableTiming));
   for (int c = 0; c < Impl::kClasses; ++c) {
     PGMM_CUDA(cudaStreamCreateWithFlags(&impl_->cls_stream[c], cudaStreamNonBlocking));
     PGMM_CUDA(cudaEventCreateWithFlags(&impl_->cls_done[c], cudaEventDisableTiming));
+    PGMM_CUDA(cudaEventCreate(&impl_->cls_t0[c]));
+    PGMM_CUDA(cudaEventCreate(&impl_->cls_t1[c]));
   }
 }
 KswEngine::~KswEngine() {
   cudaEventDestroy(impl_->ev0);
   cudaEventDestroy(impl_->ev1);
-  cudaEventDestroy(impl_->ev_a0);
-  cudaEventDestroy(impl_->ev_a1);
   cudaEventDestroy(impl_->fork);
-  for (int c = 0; c < Impl::kClasses; ++c) cudaStreamDestroy(impl_->cls_stream[c]), cudaEventDestroy(impl_->cls_done[c]);
+  for (int c = 0; c < Impl::kClasses; ++c)
+    cudaStreamDestroy(impl_->cls_stream[c]), cudaEventDestroy(impl_->cls_done[c]), cudaEventDestroy(impl_->cls_t0[c]), cudaEventDestroy(impl_->cls_t1[c]);
   delete impl_;
 }
 
@@ -932,7 +932,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
   res.cig_start.assign(n + 1, 0);
   res.cigar.clear();
   res.cells = 0, res.launches = 0, res.kernel_ms = 0.f;
-  res.k5a_ms = 0.f, res.k5a_cells = 0, res.k5a_bases = 0, res.k5a_launches = 0;
+  for (int f = 0; f < 3; ++f) res.fam_ms[f] = 0.f, res.fam_cells[f] = 0, res.fam_bases[f] = 0, res.fam_launches[f] = 0;
   if (n == 0) return;
   Impl &m = *impl_;
 
@@ -987,7 +987,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
         cls[20].push_back((int)k);
         cls_smem[20] = std::max<size_t>(cls_smem[20], (size_t)jobs[i].qlen);  // here: the longest query of the class
         res.cells += (uint64_t)jobs[i].qlen * jobs[i].tlen;
-        res.k5a_cells += (uint64_t)jobs[i].qlen * jobs[i].tlen, res.k5a_bases += (uint64_t)jobs[i].qlen + jobs[i].tlen;
+        res.fam_cells[1] += (uint64_t)jobs[i].qlen * jobs[i].tlen, res.fam_bases[1] += (uint64_t)jobs[i].qlen + jobs[i].tlen;
         continue;
       }
       if (const int wc = wide_fill_cfg(jobs[i]); wc >= 0) {
@@ -995,6 +995,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
         cls[c].push_back((int)k);
         cls_smem[c] = std::max(cls_smem[c], wide_fill_smem(jobs[i]));
         res.cells += (uint64_t)jobs[i].qlen * jobs[i].tlen;
+        res.fam_cells[2] += (uint64_t)jobs[i].qlen * jobs[i].tlen, res.fam_bases[2] += (uint64_t)jobs[i].qlen + jobs[i].tlen;
         continue;
       }
       int nt_tier, sm_tier;
@@ -1005,8 +1006,10 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       const int c = nt_tier * 4 + sm_tier;
       cls[c].push_back((int)k);
       if (sm_tier < 3) cls_smem[c] = std::max(cls_smem[c], sb);
-      res.cells += (uint64_t)std::min<int64_t>((int64_t)jobs[i].qlen * jobs[i].tlen,
-                                                (int64_t)geo[i].n_row * std::min(geo[i].n_col16, geo[i].T));
+      const uint64_t band_cells = (uint64_t)std::min<int64_t>((int64_t)jobs[i].qlen * jobs[i].tlen,
+                                                              (int64_t)geo[i].n_row * std::min(geo[i].n_col16, geo[i].T));
+      res.cells += band_cells;
+      res.fam_cells[0] += band_cells, res.fam_bases[0] += (uint64_t)jobs[i].qlen + jobs[i].tlen;
     }
     int *hid = m.h_ids.ensure(nw);
     size_t cls_off[kClasses], nid = 0;
@@ -1030,6 +1033,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       if (cls[c].empty()) continue;
       cudaStream_t cs = m.cls_stream[c];
       PGMM_CUDA(cudaStreamWaitEvent(cs, m.fork, 0));
+      PGMM_CUDA(cudaEventRecord(m.cls_t0[c], cs));
 #define PGMM_LAUNCH(NT, SMEM)                                                                                                     \
   launch_class<NT>(cls[c], SMEM, m.d_ids.p, cls_off[c], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, \
                    m.cig_packed.p, m.d_counter.p, cs)
@@ -1042,12 +1046,9 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
           attr_set = true;
         }
         const int nj = (int)cls[20].size();
-        PGMM_CUDA(cudaEventRecord(m.ev_a0, cs));
         ksw_fill_small_kernel<<<(nj + kFillWarps - 1) / kFillWarps, kFillWarps * 32, per_warp * kFillWarps, cs>>>(
             m.d_jobs.p, m.d_ids.p + cls_off[20], nj, d_q, d_t, sc, q_cap, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p);
         PGMM_CUDA(cudaGetLastError());
-        PGMM_CUDA(cudaEventRecord(m.ev_a1, cs));
-        ++res.k5a_launches;
       } else if (c > 20) {
 #define PGMM_WIDE(NW, KP, EX)                                                                                                   \
   do {                                                                                                                          \
@@ -1080,6 +1081,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
         default: PGMM_LAUNCH(512, cls_smem[c]); break;
       }
 #undef PGMM_LAUNCH
+      PGMM_CUDA(cudaEventRecord(m.cls_t1[c], cs));
       PGMM_CUDA(cudaEventRecord(m.cls_done[c], cs));
       PGMM_CUDA(cudaStreamWaitEvent(stream, m.cls_done[c], 0));
       ++res.launches;
@@ -1095,9 +1097,11 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     float ms = 0.f;
     PGMM_CUDA(cudaEventElapsedTime(&ms, m.ev0, m.ev1));
     res.kernel_ms += ms;
-    if (!cls[20].empty()) {
-      PGMM_CUDA(cudaEventElapsedTime(&ms, m.ev_a0, m.ev_a1));
-      res.k5a_ms += ms;
+    for (int c = 0; c < kClasses; ++c) {
+      if (cls[c].empty()) continue;
+      const int fam = c < 20 ? 0 : c == 20 ? 1 : 2;
+      PGMM_CUDA(cudaEventElapsedTime(&ms, m.cls_t0[c], m.cls_t1[c]));
+      res.fam_ms[fam] += ms, res.fam_launches[fam] += 1;
     }
     const size_t tot = (size_t)*hc, base = res.cigar.size();
     if (tot > 0) {

@@ -61,10 +61,11 @@ struct KswBatchResult {
   uint64_t cells = 0;               // in-band cells actually asked for (for the GCUPS / roofline figures)
   int launches = 0;
   float kernel_ms = 0.f;            // CUDA-event time of the DP kernels alone (all launch classes of a wave, concurrent)
-  // the dominant kernel on its own (K5a, first-pass gap fills): CUDA events on the stream it is launched on
-  float k5a_ms = 0.f;
-  uint64_t k5a_cells = 0, k5a_bases = 0;
-  int k5a_launches = 0;
+  // per kernel family (0 = K5 generic band-limited, 1 = K5a small first-pass fills, 2 = K5b wide unbanded fills):
+  // CUDA-event time of every launch on the stream it is launched on, cells, bases read, launches
+  float fam_ms[3] = {0.f, 0.f, 0.f};
+  uint64_t fam_cells[3] = {0, 0, 0}, fam_bases[3] = {0, 0, 0};
+  int fam_launches[3] = {0, 0, 0};
 };
 
 class KswEngine {

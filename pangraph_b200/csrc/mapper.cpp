@@ -1360,7 +1360,9 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
       be.stats.jobs += jobs.size(), be.stats.cells += res.cells, be.stats.waves += 1;
       for (const KswJob &j : jobs) be.stats.seq_bytes += (uint64_t)j.qlen + j.tlen;
       be.stats.launches += res.launches, be.stats.kernel_ms += res.kernel_ms;
-      be.stats.k5a_ms += res.k5a_ms, be.stats.k5a_cells += res.k5a_cells, be.stats.k5a_bases += res.k5a_bases, be.stats.k5a_launches += res.k5a_launches;
+      for (int f = 0; f < 3; ++f)
+        be.stats.fam_ms[f] += res.fam_ms[f], be.stats.fam_cells[f] += res.fam_cells[f], be.stats.fam_bases[f] += res.fam_bases[f],
+            be.stats.fam_launches[f] += res.fam_launches[f];
     } else {
       res.out.clear(), res.cigar.clear(), res.cig_start.clear();
     }

@@ -45,8 +45,8 @@ struct QuerySeeds {
 
 struct DpStats {
   uint64_t jobs = 0, cells = 0, waves = 0, seq_bytes = 0;
-  uint64_t k5a_cells = 0, k5a_bases = 0, k5a_launches = 0;
-  double k5a_ms = 0;
+  uint64_t fam_cells[3] = {0, 0, 0}, fam_bases[3] = {0, 0, 0}, fam_launches[3] = {0, 0, 0};  // per DP kernel family
+  double fam_ms[3] = {0, 0, 0};
   int launches = 0;
   double kernel_ms = 0;
   // wall-clock phases of map_batch (ms): encode, seeding (GPU), anchor sort + chain + plan (host), DP waves (GPU incl.

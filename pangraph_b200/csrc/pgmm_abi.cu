@@ -24,8 +24,8 @@ struct Stats {
   double seed_ms = 0, dp_kernel_ms = 0, total_ms = 0, index_ms = 0;
   uint64_t dp_seq_bytes = 0, dp_jobs = 0, dp_cells = 0, dp_waves = 0, bases_mapped = 0, bases_indexed = 0, batches = 0, launches = 0;
   double t_encode = 0, t_seed = 0, t_chain = 0, t_dp = 0, t_stitch = 0, t_final = 0;
-  double k5a_ms = 0;
-  uint64_t k5a_cells = 0, k5a_bases = 0, k5a_launches = 0;
+  double fam_ms[3] = {0, 0, 0};
+  uint64_t fam_cells[3] = {0, 0, 0}, fam_bases[3] = {0, 0, 0}, fam_launches[3] = {0, 0, 0};
 };
 Stats g_stats;
 std::mutex g_stats_mu;
@@ -209,8 +209,9 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   g_stats.launches += be.stats.launches, g_stats.batches += 1, g_stats.dp_seq_bytes += be.stats.seq_bytes;
   g_stats.t_encode += be.stats.t_encode, g_stats.t_seed += be.stats.t_seed, g_stats.t_chain += be.stats.t_chain;
   g_stats.t_dp += be.stats.t_dp, g_stats.t_stitch += be.stats.t_stitch, g_stats.t_final += be.stats.t_final;
-  g_stats.k5a_ms += be.stats.k5a_ms, g_stats.k5a_cells += be.stats.k5a_cells, g_stats.k5a_bases += be.stats.k5a_bases;
-  g_stats.k5a_launches += be.stats.k5a_launches;
+  for (int f = 0; f < 3; ++f)
+    g_stats.fam_ms[f] += be.stats.fam_ms[f], g_stats.fam_cells[f] += be.stats.fam_cells[f], g_stats.fam_bases[f] += be.stats.fam_bases[f],
+        g_stats.fam_launches[f] += be.stats.fam_launches[f];
   for (int i = 0; i < n; ++i) g_stats.bases_mapped += lens[i];
 }
 
@@ -357,14 +358,16 @@ void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *cons
 //        [8] bases_indexed [9] batches [10] kernel launches of the DP engine
 void pgmm_get_stats(double *out, int n, int reset) {
   std::lock_guard<std::mutex> sl(g_stats_mu);
-  const double v[25] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+  const double v[33] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
                         (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
                         (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches,
                         g_stats.t_encode, g_stats.t_seed, g_stats.t_chain, g_stats.t_dp, g_stats.t_stitch, g_stats.t_final,
                         (double)pgmm::h2d_bytes(), (double)pgmm::d2h_bytes(), (double)g_stats.dp_seq_bytes,
-                        (double)pgmm::DevicePool::misses(), g_stats.k5a_ms, (double)g_stats.k5a_cells, (double)g_stats.k5a_bases,
-                        (double)g_stats.k5a_launches};
-  for (int i = 0; i < n && i < 25; ++i) out[i] = v[i];
+                        (double)pgmm::DevicePool::misses(),
+                        g_stats.fam_ms[0], (double)g_stats.fam_cells[0], (double)g_stats.fam_bases[0], (double)g_stats.fam_launches[0],
+                        g_stats.fam_ms[1], (double)g_stats.fam_cells[1], (double)g_stats.fam_bases[1], (double)g_stats.fam_launches[1],
+                        g_stats.fam_ms[2], (double)g_stats.fam_cells[2], (double)g_stats.fam_bases[2], (double)g_stats.fam_launches[2]};
+  for (int i = 0; i < n && i < 33; ++i) out[i] = v[i];
   if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0, pgmm::DevicePool::misses() = 0;
   if (reset) g_stats = Stats();
 }
