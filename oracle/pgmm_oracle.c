@@ -377,3 +377,73 @@ int orc_ksw_extd2_unbanded(int qlen, const uint8_t *query, int tlen, const uint8
 	free(u); free(x2n); free(H); free(p);
 	return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * mm_sketch: symmetric (w,k)-minimizers.  C/sketch.c:77-143 (hash: :28-38, base codes: :9-26), non-HPC.
+ * Restated with an explicit ring of the last w "events" (an event is any position except a skipped palindromic
+ * k-mer) so that the emission rules can be read one by one; the CUDA kernel decides the same rules per event in
+ * parallel.  Output: x = hash<<8 | span, y = rid<<32 | lastPos<<1 | strand, in emission order.
+ * ---------------------------------------------------------------------------------------------------------- */
+static uint64_t orc_hash64(uint64_t key, uint64_t mask)
+{
+	key = (~key + (key << 21)) & mask;
+	key = key ^ key >> 24;
+	key = ((key + (key << 3)) + (key << 8)) & mask;
+	key = key ^ key >> 14;
+	key = ((key + (key << 2)) + (key << 4)) & mask;
+	key = key ^ key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+static int orc_code(unsigned char c)
+{
+	switch (c) {
+	case 'A': case 'a': return 0;
+	case 'C': case 'c': return 1;
+	case 'G': case 'g': return 2;
+	case 'T': case 't': case 'U': case 'u': return 3;
+	default: return c < 4 ? c : 4; /* the table also maps bytes 0..3 to themselves */
+	}
+}
+/* returns the number of minimizers; out_x/out_y need room for len entries */
+long orc_sketch(const char *str, int len, int w, int k, uint32_t rid, uint64_t *out_x, uint64_t *out_y)
+{
+	const uint64_t MAXV = ~0ULL, shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
+	uint64_t kmer[2] = {0, 0}, ring_x[256], ring_y[256], min_x = MAXV, min_y = MAXV;
+	int i, j, l = 0, pos = 0, min_pos = 0;
+	long n = 0;
+	for (j = 0; j < w; ++j) ring_x[j] = ring_y[j] = MAXV;
+#define ORC_EMIT(X, Y) (out_x[n] = (X), out_y[n] = (Y), ++n)
+	for (i = 0; i < len; ++i) {
+		int c = orc_code((unsigned char)str[i]);
+		uint64_t ix = MAXV, iy = MAXV;
+		if (c < 4) {
+			int z, span = l + 1 < k ? l + 1 : k;
+			kmer[0] = (kmer[0] << 2 | c) & mask;
+			kmer[1] = (kmer[1] >> 2) | (3ULL ^ c) << shift1;
+			if (kmer[0] == kmer[1]) continue; /* strand unknown: no event at all (:108) */
+			z = kmer[0] < kmer[1] ? 0 : 1;
+			if (++l >= k) ix = orc_hash64(kmer[z], mask) << 8 | span, iy = (uint64_t)rid << 32 | (uint32_t)i << 1 | z;
+		} else l = 0; /* the k-mer registers are NOT cleared */
+		ring_x[pos] = ix, ring_y[pos] = iy;
+		if (l == w + k - 1 && min_x != MAXV) { /* first full window: duplicates of the minimum (:116-121) */
+			for (j = pos + 1; j < w; ++j) if (min_x == ring_x[j] && ring_y[j] != min_y) ORC_EMIT(ring_x[j], ring_y[j]);
+			for (j = 0; j < pos; ++j) if (min_x == ring_x[j] && ring_y[j] != min_y) ORC_EMIT(ring_x[j], ring_y[j]);
+		}
+		if (ix <= min_x) { /* new minimum displaces the old one (:122-124) */
+			if (l >= w + k && min_x != MAXV) ORC_EMIT(min_x, min_y);
+			min_x = ix, min_y = iy, min_pos = pos;
+		} else if (pos == min_pos) { /* the minimum leaves the window (:125-138) */
+			if (l >= w + k - 1 && min_x != MAXV) ORC_EMIT(min_x, min_y);
+			for (j = pos + 1, min_x = MAXV; j < w; ++j) if (min_x >= ring_x[j]) min_x = ring_x[j], min_y = ring_y[j], min_pos = j;
+			for (j = 0; j <= pos; ++j) if (min_x >= ring_x[j]) min_x = ring_x[j], min_y = ring_y[j], min_pos = j;
+			if (l >= w + k - 1 && min_x != MAXV) {
+				for (j = pos + 1; j < w; ++j) if (min_x == ring_x[j] && min_y != ring_y[j]) ORC_EMIT(ring_x[j], ring_y[j]);
+				for (j = 0; j <= pos; ++j) if (min_x == ring_x[j] && min_y != ring_y[j]) ORC_EMIT(ring_x[j], ring_y[j]);
+			}
+		}
+		if (++pos == w) pos = 0;
+	}
+	if (min_x != MAXV) ORC_EMIT(min_x, min_y);
+	return n;
+}

@@ -25,6 +25,7 @@ struct Node {
   double pri;
   int32_t ch[2];
   int32_t smin;  // node holding the minimum priority of this subtree (history-dependent among ties)
+  double smin_pri;  // its priority, cached so that comparisons need no second hop
   int8_t bal;
   uint32_t size;
 };
@@ -64,19 +65,23 @@ struct MinTree {
   // subtree minimum of p given the children it is about to have: left child's minimum beats p on ties, right child's
   // minimum beats both on ties
   void pull_min(int32_t p, int32_t l, int32_t r) {
-    int32_t s = (l == NIL || lt(p, N(l).smin)) ? p : N(l).smin;
-    s = (r == NIL || lt(s, N(r).smin)) ? s : N(r).smin;
-    N(p).smin = s;
+    Node &np = N(p);
+    int32_t s = p;
+    double sp = np.pri;
+    if (l != NIL && !(sp < N(l).smin_pri)) s = N(l).smin, sp = N(l).smin_pri;
+    if (r != NIL && !(sp < N(r).smin_pri)) s = N(r).smin, sp = N(r).smin_pri;
+    np.smin = s, np.smin_pri = sp;
   }
 
   int32_t rotate_single(int32_t p, int dir) {
     const int opp = 1 - dir;
     const int32_t q = N(p).ch[opp], s = N(p).smin;
+    const double s_pri = N(p).smin_pri;
     const uint32_t size_p = N(p).size;
     N(p).size -= N(q).size - child_size(q, dir);
     N(q).size = size_p;
     pull_min(p, N(p).ch[dir], N(q).ch[dir]);
-    N(q).smin = s;
+    N(q).smin = s, N(q).smin_pri = s_pri;
     N(p).ch[opp] = N(q).ch[dir];
     N(q).ch[dir] = p;
     return q;
@@ -85,13 +90,14 @@ struct MinTree {
   int32_t rotate_double(int32_t p, int dir) {
     const int opp = 1 - dir;
     const int32_t q = N(p).ch[opp], r = N(q).ch[dir], s = N(p).smin;
+    const double s_pri = N(p).smin_pri;
     const uint32_t size_r_dir = child_size(r, dir);
     N(r).size = N(p).size;
     N(p).size -= N(q).size - size_r_dir;
     N(q).size -= size_r_dir + 1;
     pull_min(p, N(p).ch[dir], N(r).ch[dir]);
     pull_min(q, N(q).ch[opp], N(r).ch[opp]);
-    N(r).smin = s;
+    N(r).smin = s, N(r).smin_pri = s_pri;
     N(p).ch[opp] = N(r).ch[dir];
     N(r).ch[dir] = p;
     N(q).ch[dir] = N(r).ch[opp];
@@ -121,7 +127,7 @@ struct MinTree {
       q = p, p = N(p).ch[which];
     }
     Node &nx = N(x);
-    nx.bal = 0, nx.size = 1, nx.ch[0] = nx.ch[1] = NIL, nx.smin = x;
+    nx.bal = 0, nx.size = 1, nx.ch[0] = nx.ch[1] = NIL, nx.smin = x, nx.smin_pri = nx.pri;
     if (q == NIL) root = x;
     else N(q).ch[which] = x;
     if (anchor == NIL) return;
@@ -258,17 +264,18 @@ struct MinTree {
     if (k == plen[0] || k == plen[1]) return NIL;
     const int lca = k;
     int32_t best = path[0][lca];
+    double best_pri = N(best).pri;
     for (k = lca + 1; k < plen[0]; ++k)
       if (pc[0][k] <= 0) {
-        const int32_t n = path[0][k], rc = N(n).ch[1];
-        if (lt(n, best)) best = n;
-        if (rc != NIL && lt(N(rc).smin, best)) best = N(rc).smin;
+        const Node &nn = N(path[0][k]);
+        if (nn.pri < best_pri) best = path[0][k], best_pri = nn.pri;
+        if (nn.ch[1] != NIL && N(nn.ch[1]).smin_pri < best_pri) best = N(nn.ch[1]).smin, best_pri = N(nn.ch[1]).smin_pri;
       }
     for (k = lca + 1; k < plen[1]; ++k)
       if (pc[1][k] >= 0) {
-        const int32_t n = path[1][k], lc = N(n).ch[0];
-        if (lt(n, best)) best = n;
-        if (lc != NIL && lt(N(lc).smin, best)) best = N(lc).smin;
+        const Node &nn = N(path[1][k]);
+        if (nn.pri < best_pri) best = path[1][k], best_pri = nn.pri;
+        if (nn.ch[0] != NIL && N(nn.ch[0]).smin_pri < best_pri) best = N(nn.ch[0]).smin, best_pri = N(nn.ch[0]).smin_pri;
       }
     return best;
   }

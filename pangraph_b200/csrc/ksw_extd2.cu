@@ -909,8 +909,13 @@ KswEngine::KswEngine() : impl_(new Impl) {
   PGMM_CUDA(cudaEventCreate(&impl_->ev0));
   PGMM_CUDA(cudaEventCreate(&impl_->ev1));
   PGMM_CUDA(cudaEventCreateWithFlags(&impl_->fork, cudaEventDisableTiming));
+  int prio_lo = 0, prio_hi = 0;
+  PGMM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = more urgent
   for (int c = 0; c < Impl::kClasses; ++c) {
-    PGMM_CUDA(cudaStreamCreateWithFlags(&impl_->cls_stream[c], cudaStreamNonBlocking));
+    // the few long, latency-bound problems (wide CTAs, long fills) decide when a wave ends: their CTAs go first;
+    // the thousands of small fills soak up whatever is left
+    const bool small = c == 20 || c < 4;
+    PGMM_CUDA(cudaStreamCreateWithPriority(&impl_->cls_stream[c], cudaStreamNonBlocking, small ? prio_lo : prio_hi));
     PGMM_CUDA(cudaEventCreateWithFlags(&impl_->cls_done[c], cudaEventDisableTiming));
     PGMM_CUDA(cudaEventCreate(&impl_->cls_t0[c]));
     PGMM_CUDA(cudaEventCreate(&impl_->cls_t1[c]));
