@@ -357,7 +357,12 @@ def ours(args):
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "phases_ms_per_round": {k: st_res[k] / (args.steps * P) for k in ("index_ms", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch",
-                                                                       "t_final", "dp_kernel_ms", "total_ms")},
+                                                                       "t_final", "dp_kernel_ms", "total_ms", "t_chain_sort", "t_chain_fill",
+                                                                       "t_chain_rest", "chain_kernel_ms")},
+            "chain": {"anchors_per_round": st_res["chain_anchors"] / (args.steps * P), "segments_per_round": st_res["chain_segments"] / (args.steps * P),
+                      "segments_to_host_arbiter": st_res["chain_redo_segments"] / (args.steps * P),
+                      "anchors_to_host_arbiter": st_res["chain_redo_anchors"] / (args.steps * P),
+                      "fill_kernel_ms_per_round": st_res["chain_kernel_ms"] / (args.steps * P)},
             "dp": {"jobs_per_round": st_res["dp_jobs"] / (args.steps * P), "cells_per_round": st_res["dp_cells"] / (args.steps * P),
                    "waves_per_round": st_res["dp_waves"] / (args.steps * P)},
         }

@@ -297,12 +297,23 @@ PGMM_API int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, cons
                                 const mm_mapopt_t *opt, uint64_t *out_anchor, uint64_t anchor_cap, uint64_t *out_mini,
                                 uint64_t mini_cap, int64_t *out_n);
 
+/* K4 alone: chains n anchors (2 uint64 each, sorted like radix_sort_128x leaves them) the way mg_lchain_rmq does
+ * (lchain.c:250-368): the device fills scores / predecessors / peak scores segment by segment, the host backtracks and
+ * compacts.  Segments the device hands back (equal priorities inside an RMQ window, oversized windows) are filled by the
+ * host arbiter when host_redo != 0; with host_redo == 0 the call returns -2 if there was any.  Returns the number of
+ * chains; u[i] = score<<32 | n_anchors, xy = the kept anchors chain after chain, *n_a_out their number; out_fpv
+ * (optional, 3n int32) = f, p, v as filled; seg_stats (optional) = {segments, handed back, their anchors}. */
+PGMM_API int64_t pgmm_chain_rmq(uint64_t *xy, int64_t n, int max_dist, int max_dist_inner, int bw, int max_skip, int cap,
+                                int min_cnt, int min_sc, float pen_gap, float pen_skip, uint64_t *u, int64_t *n_a_out,
+                                int32_t *out_fpv, int64_t *seg_stats, int host_redo);
+
 /* counters since the last reset: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells
  * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] kernel launches [11..16] wall ms of the phases of
  * pgmm_map_batch (encode, seeding, sort+chain+plan, DP waves, stitching between waves, final filters)
  * [17] host->device bytes [18] device->host bytes [19] bases read by the DP kernels [20] cudaMalloc calls
  * [21..32] per DP kernel family (K5 generic, K5a small fills, K5b wide fills): ms on the launch streams, cells, bases read,
- * launches */
+ * launches [33..41] chaining: host sort ms, device fill ms (with copies), host rest ms (redo + backtrack + hit skeletons +
+ * plan), fill kernel ms, anchors, segments, segments handed back to the host, their anchors, launches */
 PGMM_API void pgmm_get_stats(double *out, int n, int reset);
 
 #ifdef __cplusplus

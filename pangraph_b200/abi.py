@@ -137,6 +137,25 @@ def ksw_extd2_batch(qlen, tlen, q_off, t_off, qcodes, tcodes, w, zdrop, end_bonu
     return ez, cigs, ms.value
 
 
+def chain_rmq(a, max_dist, max_dist_inner, bw, max_skip, cap, min_cnt, min_sc, pen_gap, pen_skip, host_redo=True):
+    """Stage K4 (+ host backtrack) on sorted anchors a[n,2] uint64.  Returns (u, kept anchors, fpv[3,n] int32,
+    (segments, handed back, their anchors)); raises if the device handed segments back and host_redo is False."""
+    L = lib()
+    L.pgmm_chain_rmq.restype = C.c_int64
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    n = len(a)
+    u = np.zeros(n + 1, dtype=np.uint64)
+    fpv = np.zeros((3, max(n, 1)), dtype=np.int32)
+    seg = np.zeros(3, dtype=np.int64)
+    n_a = C.c_int64(0)
+    n_u = L.pgmm_chain_rmq(_p(a), C.c_int64(n), C.c_int(max_dist), C.c_int(max_dist_inner), C.c_int(bw), C.c_int(max_skip),
+                           C.c_int(cap), C.c_int(min_cnt), C.c_int(min_sc), C.c_float(pen_gap), C.c_float(pen_skip), _p(u),
+                           C.byref(n_a), _p(fpv), _p(seg), C.c_int(1 if host_redo else 0))
+    if n_u < 0:
+        raise RuntimeError(f"pgmm_chain_rmq -> {n_u} ({int(seg[1])} of {int(seg[0])} segments handed back)")
+    return u[:n_u].copy(), a[:n_a.value].copy(), fpv[:, :n], tuple(int(v) for v in seg)
+
+
 def set_device(device):
     rc = lib().pgmm_set_device(int(device))
     if rc != 0:
@@ -147,7 +166,9 @@ STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_
               "bases_indexed", "batches", "launches", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch", "t_final",
               "h2d_bytes", "d2h_bytes", "dp_seq_bytes", "device_mallocs",
               "k5_ms", "k5_cells", "k5_bases", "k5_launches", "k5a_ms", "k5a_cells", "k5a_bases", "k5a_launches",
-              "k5b_ms", "k5b_cells", "k5b_bases", "k5b_launches")
+              "k5b_ms", "k5b_cells", "k5b_bases", "k5b_launches",
+              "t_chain_sort", "t_chain_fill", "t_chain_rest", "chain_kernel_ms", "chain_anchors", "chain_segments",
+              "chain_redo_segments", "chain_redo_anchors", "chain_launches")
 
 
 def get_stats(reset=False):

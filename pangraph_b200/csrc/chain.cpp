@@ -354,7 +354,7 @@ inline int32_t link_score(const U128 &ai, const U128 &aj, float pen_gap, float p
 }
 
 // where a chain ending at z[k] stops when walked backwards (lchain.c:9-25)
-int64_t chain_stop(int32_t max_drop, const U128 *z, const int32_t *f, const int64_t *p, int32_t *t, int64_t k) {
+int64_t chain_stop(int32_t max_drop, const U128 *z, const int32_t *f, const int32_t *p, int32_t *t, int64_t k) {
   int64_t i = (int64_t)z[k].y, end_i = -1, max_i = i;
   int32_t max_s = 0;
   if (i < 0 || t[i] != 0) return i;
@@ -371,19 +371,25 @@ int64_t chain_stop(int32_t max_drop, const U128 *z, const int32_t *f, const int6
 
 }  // namespace
 
-void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t> &u) {
-  u.clear();
-  const int64_t n = (int64_t)a.size();
+void chain_find_segments(const ChainParams &cp, const U128 *a, int64_t n, std::vector<ChainSeg> &segs) {
+  segs.clear();
   if (n == 0) return;
+  const int64_t max_dist = cp.max_dist < cp.bw ? cp.bw : cp.max_dist;
+  int64_t s = 0;
+  for (int64_t i = 1; i < n; ++i)
+    if (a[i].x >> 32 != a[i - 1].x >> 32 || a[i].x > a[i - 1].x + (uint64_t)max_dist) segs.push_back(ChainSeg{s, i}), s = i;
+  segs.push_back(ChainSeg{s, n});
+}
+
+void chain_fill_host(const ChainParams &cp, const U128 *a, int64_t n, int64_t seg_start, int64_t seg_end, int32_t *f, int32_t *p,
+                     int32_t *v, int32_t *t) {
   int max_dist = cp.max_dist, max_dist_inner = cp.max_dist_inner;
   const int bw = cp.bw;
   if (max_dist < bw) max_dist = bw;
   if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
-  std::vector<int64_t> p(n);
-  std::vector<int32_t> f(n), t(n, 0), v(n);
   Pool pool;
   MinTree outer(pool);
-  int64_t i0 = 0, st = 0, st_inner = 0;
+  int64_t i0 = seg_start, st = seg_start, st_inner = seg_start;
   // The second ("inner") tree of the reference is only ever searched for a floor element and walked backwards in key
   // order (lchain.c:323-348): what it returns depends on the SET of anchors it holds, not on its shape.  That set is
   // the index window [st_inner, i0): a small window is kept as a sorted array of (y, index) (insertions and evictions
@@ -393,7 +399,7 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
   bool mirrored = false;
   std::vector<std::pair<int32_t, int64_t>> near;  // ascending, the members of the window while !mirrored
 
-  for (int64_t i = 0; i < n; ++i) {
+  for (int64_t i = seg_start; i < seg_end; ++i) {
     int64_t max_j = -1;
     const int32_t q_span = (int32_t)(a[i].y >> 32 & 0xff);
     int32_t max_f = q_span;
@@ -483,10 +489,17 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
         }
       }
     }
-    f[i] = max_f, p[i] = max_j;
+    f[i] = max_f, p[i] = (int32_t)max_j;
     v[i] = max_j >= 0 && v[max_j] > max_f ? v[max_j] : max_f;
   }
+}
 
+void chain_backtrack(const ChainParams &cp, std::vector<U128> &a, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t,
+                     std::vector<uint64_t> &u) {
+  u.clear();
+  const int64_t n = (int64_t)a.size();
+  if (n == 0) return;
+  const int bw = cp.bw;
   // ---- backtrack (lchain.c:27-76): best end points first, each anchor used once ----
   const int32_t min_sc = cp.min_sc, min_cnt = cp.min_cnt, max_drop = bw;
   std::vector<U128> z;
@@ -497,12 +510,12 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
     return;
   }
   flag_sort_128x(z.data(), z.data() + z.size());
-  std::fill(t.begin(), t.end(), 0);
+  std::fill(t, t + n, 0);
   int64_t n_v = 0;
   for (int64_t k = (int64_t)z.size() - 1; k >= 0; --k) {
     if (t[z[k].y] != 0) continue;
     const int64_t n_v0 = n_v;
-    const int64_t end_i = chain_stop(max_drop, z.data(), f.data(), p.data(), t.data(), k);
+    const int64_t end_i = chain_stop(max_drop, z.data(), f, p, t, k);
     int64_t i;
     for (i = (int64_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = (int32_t)i, t[i] = 1;
     const int32_t sc = i < 0 ? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
@@ -534,6 +547,17 @@ void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t
     k += cnt;
   }
   u.swap(u2);
+}
+
+void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t> &u) {
+  u.clear();
+  const int64_t n = (int64_t)a.size();
+  if (n == 0) return;
+  std::vector<int32_t> f(n), p(n), t(n, 0), v(n);
+  std::vector<ChainSeg> segs;
+  chain_find_segments(cp, a.data(), n, segs);
+  for (const ChainSeg &sg : segs) chain_fill_host(cp, a.data(), n, sg.start, sg.end, f.data(), p.data(), v.data(), t.data());
+  chain_backtrack(cp, a, f.data(), p.data(), v.data(), t.data(), u);
 }
 
 }  // namespace pgmm

@@ -1,0 +1,437 @@
+// K4: the score fill of RMQ chaining on the GPU.
+//
+// Reference: the main loop of mg_lchain_rmq (minimap2/lchain.c:276-358) with comput_sc_simple (:232-248) and
+// mg_log2 (mmpriv.h:118-126).  The reference walks the anchors in target order and keeps two balanced trees keyed by
+// query position: one answers "smallest priority among the anchors at most max_dist behind on both axes", the other is
+// walked backwards over the near neighbourhood (rmq_inner_dist) with the max_chain_skip early exit.
+//
+// What the trees hold is always a contiguous index window of the sorted anchor array, [st, i0) and [st_inner, i0),
+// so no tree exists here: one warp owns one independent segment of the array (chain.h) and, per anchor,
+//   * advances the two window starts with one ballot each (the eviction conditions are monotone in the index),
+//   * scans the outer window for the smallest priority inside the query range (coalesced loads of y and of an
+//     order-preserving 64-bit image of the double priority, two redux.sync to reduce),
+//   * when the best predecessor is not an exact diagonal neighbour, gathers the near window, puts it in descending
+//     (query position, index) order (usually it already is; otherwise a bitonic sort in shared memory) and evaluates
+//     32 candidates at a time; the reference's sequential "skip" counter is replayed over two ballot masks.
+// The anchor loop itself is sequential by nature (every score depends on earlier ones); parallelism comes from the
+// 32 lanes inside a step and from the independent segments, queries and rounds in flight.
+//
+// The one thing a tree-free scan cannot reproduce is the reference's choice among EQUAL priorities inside an RMQ window,
+// which follows the rotation history of its AVL tree.  Such a segment is flagged and handed back to the host
+// (chain_fill_host); so are windows beyond kRing / kInnerCap.  Everything else is bit-identical.
+#include "chain_fill.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace pgmm {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kScanUnroll = 8;
+
+struct ChainDevParams {
+  int max_dist, max_dist_inner, bw, max_skip, cap;
+  float pen_gap, pen_skip;
+};
+
+// mmpriv.h:118-126, every operation rounded separately like the host build (-ffp-contract=off)
+__device__ __forceinline__ float fast_log2_dev(float x) {
+  uint32_t zi = __float_as_uint(x);
+  float log_2 = (float)(int)(((zi >> 23) & 255) - 128);
+  zi &= ~(255u << 23);
+  zi += 127u << 23;
+  const float zf = __uint_as_float(zi);
+  float t = __fadd_rn(__fmul_rn(-0.34484843f, zf), 2.02466578f);
+  t = __fadd_rn(__fmul_rn(t, zf), -0.67487759f);
+  return __fadd_rn(log_2, t);
+}
+
+// lchain.c:232-248
+__device__ __forceinline__ int link_score_dev(int xi, int yi, int xj, int yj, int q_span, float pen_gap, float pen_skip, bool &exact,
+                                              int &width) {
+  const int dq = yi - yj, dr = xi - xj;
+  const int dd = dr > dq ? dr - dq : dq - dr, dg = dr < dq ? dr : dq;
+  int sc = q_span < dg ? q_span : dg;
+  width = dd;
+  exact = dd == 0 && dg <= q_span;
+  if (dd || dq > q_span) {
+    const float lin_pen = __fadd_rn(__fmul_rn(pen_gap, (float)dd), __fmul_rn(pen_skip, (float)dg));
+    const float log_pen = dd >= 1 ? fast_log2_dev((float)(dd + 1)) : 0.0f;
+    sc -= (int)__fadd_rn(lin_pen, __fmul_rn(.5f, log_pen));
+  }
+  return sc;
+}
+
+// -(f + 0.5 * pen_gap * (x + y)) in double (lchain.c:285), mapped to an unsigned key with the same order
+__device__ __forceinline__ unsigned long long pri_key(int f, int x, int y, float pen_gap) {
+  const double half_pen = __dmul_rn(0.5, (double)pen_gap);
+  const double pri = -__dadd_rn((double)f, __dmul_rn(half_pen, (double)(x + y)));
+  const long long b = __double_as_longlong(pri);
+  return b < 0 ? ~(unsigned long long)b : (unsigned long long)b | 0x8000000000000000ull;
+}
+
+__global__ void chain_prep_kernel(const U128 *__restrict__ a, int n, int *__restrict__ X, int *__restrict__ Y, uint8_t *__restrict__ QS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const U128 v = a[i];
+  X[i] = (int)(uint32_t)v.x, Y[i] = (int)(uint32_t)v.y, QS[i] = (uint8_t)(v.y >> 32 & 0xff);
+}
+
+// segs[b] = (first anchor, end, first anchor of the query, unused); one warp per segment.
+//
+// Everything the loop WRITES and later reads back -- priority keys, scores, peak scores, predecessors, the walk's
+// visit stamps -- lives in a shared-memory ring of kRing slots indexed by anchor number (the windows never reach further
+// back than that, or the segment is handed to the host), so the dependent chain of one step never waits for L2.  The
+// read-only coordinates stay in global memory (L1-resident after the first touch); the warp fetches its next 32
+// anchors one batch ahead and broadcasts them by shuffle; results leave in coalesced batches of 32.
+__global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ X, const int *__restrict__ Y, const uint8_t *__restrict__ QS,
+                                                        const int4 *__restrict__ segs, ChainDevParams P, int *__restrict__ F,
+                                                        int *__restrict__ PP, int *__restrict__ V, int *__restrict__ seg_flag) {
+  constexpr int R = ChainEngine::kRing, M = R - 1;
+  extern __shared__ unsigned long long smem_u64[];
+  unsigned long long *spri = smem_u64;                 // [R]
+  unsigned long long *keys = spri + R;                 // [kInnerCap]
+  int *sf = (int *)(keys + ChainEngine::kInnerCap);    // [R] score
+  int *sv = sf + R;                                    // [R] peak score
+  int *sp = sv + R;                                    // [R] predecessor (batch-absolute index, -1 = none)
+  int *stamp = sp + R;                                 // [R] last step whose walk marked this anchor
+  const int lane = threadIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int4 sg = segs[blockIdx.x];
+  const int s = sg.x, e = sg.y, qbase = sg.z;
+  int st = s, sti = s, i0 = s, xi0 = 0, flag = ChainEngine::DONE;
+  // smallest key of the visible window [st, i0) regardless of query position, its holder, whether it is shared
+  unsigned long long cb_key = ~0ull, last_key = ~0ull;
+  int cb_j = -1;
+  bool cb_tie = false, cb_valid = true;
+  for (int k = lane; k < R; k += 32) stamp[k] = -1;
+  __syncwarp();
+
+  int nx = 0, ny = 0, nq = 0;
+  if (s + lane < e) nx = X[s + lane], ny = Y[s + lane], nq = QS[s + lane];
+  for (int ib = s; ib < e && flag == ChainEngine::DONE; ib += 32) {
+    const int bx = nx, by = ny, bq = nq;
+    if (ib + 32 + lane < e) nx = X[ib + 32 + lane], ny = Y[ib + 32 + lane], nq = QS[ib + 32 + lane];
+    const int nb = min(32, e - ib);
+    for (int t = 0; t < nb; ++t) {
+      const int i = ib + t;
+      const int xi = __shfl_sync(FULL, bx, t), yi = __shfl_sync(FULL, by, t), qsi = __shfl_sync(FULL, bq, t);
+      int max_f = qsi, max_j = -1;
+      if (i == s) xi0 = xi;
+      if (i0 < i && xi0 != xi) {  // the previous target position's anchors become visible together (:280-293)
+        for (int jj = i0; jj < i; ++jj) {
+          const unsigned long long k = jj == i - 1 ? last_key : spri[jj & M];
+          if (k < cb_key) cb_key = k, cb_j = jj, cb_tie = false;
+          else if (k == cb_key) cb_tie = true;
+        }
+        i0 = i, xi0 = xi;
+      }
+      // evictions (:295-312): too far behind on the target, or the window is over the size cap.  Both conditions are
+      // monotone in the index, so one ballot finds how far each window start moves (both loads are issued first)
+      {
+        const int c = st + lane, ci = sti + lane;
+        const int xc = X[min(c, i)], xci = X[min(ci, i)];
+        bool ev = c < i && ((long long)xi > (long long)xc + P.max_dist || i0 - c > P.cap);
+        bool evi = P.max_dist_inner > 0 && ci < i && ((long long)xi > (long long)xci + P.max_dist_inner || i0 - ci > P.cap);
+        unsigned m = __ballot_sync(FULL, ev), mi = __ballot_sync(FULL, evi);
+        st += __popc(m), sti += __popc(mi);
+        while (m == FULL) {
+          const int c2 = st + lane;
+          ev = c2 < i && ((long long)xi > (long long)X[min(c2, i)] + P.max_dist || i0 - c2 > P.cap);
+          m = __ballot_sync(FULL, ev);
+          st += __popc(m);
+        }
+        while (mi == FULL) {
+          const int c2 = sti + lane;
+          evi = c2 < i && ((long long)xi > (long long)X[min(c2, i)] + P.max_dist_inner || i0 - c2 > P.cap);
+          mi = __ballot_sync(FULL, evi);
+          sti += __popc(mi);
+        }
+      }
+      if (i - st >= R) {  // the ring no longer covers the window
+        flag = ChainEngine::WINDOW;
+        break;
+      }
+      // range minimum over [st, i0) with query position in (yi - max_dist, yi]; at yi itself only the query's first
+      // anchor qualifies (the closed upper key is (yi, 0), :314).
+      //
+      // Fast path: the smallest key of the whole window, ignoring the query range, is carried from step to step (a newly
+      // visible anchor is folded in; it is recomputed when its holder is evicted).  Along a chain that holder is the
+      // newest anchor, and when it is unique and inside the query range it is the answer.  Otherwise the window is scanned.
+      const int ylo = yi - P.max_dist;
+      if (cb_j >= 0 && cb_j < st) cb_valid = false;
+      if (st >= i0) cb_valid = true, cb_tie = false, cb_j = -1, cb_key = ~0ull;
+      int j = -1;
+      bool fast = cb_valid && !cb_tie;
+      if (fast && cb_j >= 0) {
+        const int y = Y[cb_j];
+        if (y > ylo && (y < yi || (y == yi && cb_j == qbase))) j = cb_j;
+        else fast = false;
+      }
+      if (!fast) {  // branch-free scan, eight independent loads in flight; both the filtered and the unfiltered minimum
+        unsigned long long bk = ~0ull, uk = ~0ull;
+        int bj = -1, uj = -1;
+        bool tie = false, utie = false;
+        for (int jb = st + lane; jb < i0 + lane; jb += 32 * kScanUnroll) {
+          int yv[kScanUnroll];
+          unsigned long long kv[kScanUnroll];
+#pragma unroll
+          for (int u = 0; u < kScanUnroll; ++u) {
+            const int jc = min(jb + 32 * u, i0 - 1);
+            yv[u] = Y[jc], kv[u] = spri[jc & M];
+          }
+#pragma unroll
+          for (int u = 0; u < kScanUnroll; ++u) {
+            const int jj = jb + 32 * u, y = yv[u];
+            const bool in = jj < i0, ok = in && y > ylo && (y < yi || (y == yi && jj == qbase));
+            const unsigned long long k0 = in ? kv[u] : ~0ull, k = ok ? k0 : ~0ull;
+            tie = k < bk ? false : (ok && k == bk ? true : tie);
+            bj = k < bk ? jj : bj;
+            bk = k < bk ? k : bk;
+            utie = k0 < uk ? false : (in && k0 == uk ? true : utie);
+            uj = k0 < uk ? jj : uj;
+            uk = k0 < uk ? k0 : uk;
+          }
+        }
+        {  // refresh the carried minimum
+          const unsigned hi = (unsigned)(uk >> 32);
+          const unsigned mh = __reduce_min_sync(FULL, hi);
+          const unsigned ml = __reduce_min_sync(FULL, hi == mh ? (unsigned)uk : 0xffffffffu);
+          cb_key = (unsigned long long)mh << 32 | ml;
+          const unsigned hm = __ballot_sync(FULL, uj >= 0 && uk == cb_key);
+          cb_tie = __popc(hm) > 1 || __any_sync(FULL, utie && uk == cb_key);
+          cb_j = hm ? __shfl_sync(FULL, uj, __ffs(hm) - 1) : -1;
+          cb_valid = true;
+        }
+        const unsigned hi = (unsigned)(bk >> 32);
+        const unsigned mh = __reduce_min_sync(FULL, hi);
+        const unsigned ml = __reduce_min_sync(FULL, hi == mh ? (unsigned)bk : 0xffffffffu);
+        const unsigned long long gk = (unsigned long long)mh << 32 | ml;
+        if (gk != ~0ull) {
+          const unsigned hm = __ballot_sync(FULL, bj >= 0 && bk == gk);
+          if (__popc(hm) > 1 || __any_sync(FULL, tie && bk == gk)) {
+            flag = ChainEngine::TIE;
+            break;
+          }
+          j = __shfl_sync(FULL, bj, __ffs(hm) - 1);
+        }
+      }
+      if (j >= 0) {
+        bool exact;
+        int width;
+        const int sc = sf[j & M] + link_score_dev(xi, yi, X[j], Y[j], QS[j], P.pen_gap, P.pen_skip, exact, width);
+        if (width <= P.bw && sc > max_f) max_f = sc, max_j = j;
+        if (!exact && P.max_dist_inner > 0 && i0 > sti && yi > 0) {
+          // near neighbourhood (:319-348): members of [sti, i0) with query position in [yi - max_dist_inner, yi - 1],
+          // visited in descending (query position, index) order
+          const int y_hi = yi - 1, y_lo = yi - P.max_dist_inner;
+          int cnt = 0;
+          for (int base = i0 - 1; base >= sti; base -= 32) {
+            const int j2 = base - lane;
+            bool c = false;
+            int y = 0;
+            if (j2 >= sti) y = Y[j2], c = y >= y_lo && y <= y_hi;
+            const unsigned m = __ballot_sync(FULL, c);
+            const int pos = cnt + __popc(m & lt_mask);
+            if (c && pos < ChainEngine::kInnerCap) keys[pos] = (unsigned long long)(unsigned)y << 32 | (unsigned)(j2 - s);
+            cnt += __popc(m);
+          }
+          if (cnt > ChainEngine::kInnerCap) {
+            flag = ChainEngine::INNER;
+            break;
+          }
+          __syncwarp();
+          bool unsorted = false;
+          for (int k = lane; k + 1 < cnt; k += 32) unsorted |= keys[k] < keys[k + 1];
+          if (__any_sync(FULL, unsorted)) {
+            int n2 = 32;
+            while (n2 < cnt) n2 <<= 1;
+            for (int k = cnt + lane; k < n2; k += 32) keys[k] = 0;  // smallest: pads end up behind every member
+            __syncwarp();
+            for (int k = 2; k <= n2; k <<= 1)
+              for (int d = k >> 1; d > 0; d >>= 1) {
+                for (int w = lane; w < n2; w += 32) {
+                  const int u = w ^ d;
+                  if (u > w) {
+                    const unsigned long long ka = keys[w], kb = keys[u];
+                    const bool desc = (w & k) == 0;
+                    if (desc ? ka < kb : ka > kb) keys[w] = kb, keys[u] = ka;
+                  }
+                }
+                __syncwarp();
+              }
+          }
+          int n_skip = 0;
+          for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const int k = c0 + lane;
+            int j2 = -1, sc2 = INT32_MIN;
+            bool ok = false;
+            if (k < cnt) {
+              j2 = s + (int)(unsigned)keys[k];
+              bool ex2;
+              int w2;
+              sc2 = sf[j2 & M] + link_score_dev(xi, yi, X[j2], Y[j2], QS[j2], P.pen_gap, P.pen_skip, ex2, w2);
+              ok = w2 <= P.bw;
+              const int pj = sp[j2 & M];
+              // "a predecessor of something already seen in this walk" (:344); one outside the near window is never visited
+              if (ok && pj >= sti) stamp[pj & M] = i;
+            }
+            __syncwarp();
+            // every writer of an anchor's stamp sits earlier in the visiting order (a predecessor has a smaller query position)
+            const bool marked = ok && stamp[j2 & M] == i;
+            // running maximum before each lane's turn
+            const int val = ok ? sc2 : INT32_MIN;
+            int incl = val;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int o = __shfl_up_sync(FULL, incl, d);
+              if (lane >= d) incl = max(incl, o);
+            }
+            int excl = __shfl_up_sync(FULL, incl, 1);
+            if (lane == 0) excl = INT32_MIN;
+            excl = max(excl, max_f);
+            const bool upd = ok && sc2 > excl;
+            const unsigned um = __ballot_sync(FULL, upd), im = __ballot_sync(FULL, ok && !upd && marked);
+            // the skip counter, event by event (:338-343)
+            int brk = -1;
+            if (um == 0) {
+              const int room = P.max_skip - n_skip;  // increments that still fit
+              if (__popc(im) > room) {
+                unsigned m2 = im;
+                for (int r = 0; r < room; ++r) m2 &= m2 - 1;
+                brk = __ffs(m2) - 1, n_skip = P.max_skip + 1;  // increment number room+1 trips the limit
+              } else n_skip += __popc(im);
+            } else {
+              unsigned evs = um | im;
+              while (evs) {
+                const int b = __ffs(evs) - 1;
+                evs &= evs - 1;
+                if (um >> b & 1) {
+                  if (n_skip > 0) --n_skip;
+                } else if (++n_skip > P.max_skip) {
+                  brk = b;
+                  break;
+                }
+              }
+            }
+            const int last = brk >= 0 ? brk : 31;
+            const int best = max(max_f, __shfl_sync(FULL, incl, last));
+            if (best > max_f) {
+              const unsigned wm = __ballot_sync(FULL, ok && sc2 == best);  // the first lane reaching it made the last update
+              max_j = __shfl_sync(FULL, j2, __ffs(wm) - 1);
+              max_f = best;
+            }
+            if (brk >= 0) break;
+          }
+        }
+      }
+      last_key = pri_key(max_f, xi, yi, P.pen_gap);
+      if (lane == 0) {
+        int vv = max_f;
+        if (max_j >= 0) {
+          const int vm = sv[max_j & M];
+          if (vm > max_f) vv = vm;
+        }
+        sf[i & M] = max_f, sp[i & M] = max_j, sv[i & M] = vv;
+        spri[i & M] = last_key;
+      }
+      __syncwarp();
+    }
+    if (flag != ChainEngine::DONE) break;
+    if (lane < nb) {  // this batch's results, coalesced
+      const int i = ib + lane, pj = sp[i & M];
+      F[i] = sf[i & M], V[i] = sv[i & M], PP[i] = pj >= 0 ? pj - qbase : -1;
+    }
+  }
+  if (lane == 0) seg_flag[blockIdx.x] = flag;
+}
+
+}  // namespace
+
+constexpr size_t kFillSmem = (size_t)ChainEngine::kRing * (8 + 4 * 4) + (size_t)ChainEngine::kInnerCap * 8;
+
+ChainEngine::ChainEngine() {
+  static const bool once = [] {
+    PGMM_CUDA(cudaFuncSetAttribute(chain_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFillSmem));
+    return true;
+  }();
+  (void)once;
+  PGMM_CUDA(cudaEventCreate(&ev0_));
+  PGMM_CUDA(cudaEventCreate(&ev1_));
+}
+ChainEngine::~ChainEngine() {
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+}
+
+void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cudaStream_t st, ChainFillStats *stats) {
+  size_t n_total = 0, n_segs = 0;
+  for (const ChainFillJob &j : jobs) n_total += (size_t)j.n, n_segs += j.segs.size();
+  if (n_total == 0) return;
+  if (n_total >= (size_t)INT32_MAX) PGMM_FATAL("chain fill: %zu anchors in one batch exceed the 31-bit index space", n_total);
+  ChainDevParams P;
+  P.max_dist = cp.max_dist < cp.bw ? cp.bw : cp.max_dist;
+  P.max_dist_inner = (cp.max_dist_inner <= 0 || cp.max_dist_inner >= P.max_dist) ? 0 : cp.max_dist_inner;
+  P.bw = cp.bw, P.max_skip = cp.max_chn_skip, P.cap = cp.cap_rmq_size, P.pen_gap = cp.pen_gap, P.pen_skip = cp.pen_skip;
+
+  // staging: anchors query after query; segments longest first so that the long ones start first
+  U128 *ha = h_a_.ensure(n_total);
+  int4 *hs = h_segs_.ensure(n_segs);
+  struct Ref {
+    int job, seg;
+    int64_t len;
+  };
+  std::vector<Ref> order;
+  order.reserve(n_segs);
+  std::vector<size_t> base(jobs.size());
+  size_t off = 0;
+  for (size_t q = 0; q < jobs.size(); ++q) {
+    ChainFillJob &j = jobs[q];
+    base[q] = off;
+    if (j.n) memcpy(ha + off, j.a, (size_t)j.n * sizeof(U128));
+    off += (size_t)j.n;
+    j.redo.assign(j.segs.size(), 0);
+    for (size_t k = 0; k < j.segs.size(); ++k) order.push_back(Ref{(int)q, (int)k, j.segs[k].end - j.segs[k].start});
+  }
+  std::stable_sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.len > b.len; });
+  for (size_t k = 0; k < n_segs; ++k) {
+    const Ref &r = order[k];
+    const ChainSeg &sg = jobs[r.job].segs[r.seg];
+    hs[k] = make_int4((int)(base[r.job] + sg.start), (int)(base[r.job] + sg.end), (int)base[r.job], 0);
+  }
+  d_a_.ensure(n_total), d_x_.ensure(n_total), d_y_.ensure(n_total), d_qs_.ensure(n_total), d_f_.ensure(3 * n_total);
+  d_segs_.ensure(n_segs), d_flag_.ensure(n_segs);
+  int32_t *dF = d_f_.p, *dP = d_f_.p + n_total, *dV = d_f_.p + 2 * n_total;
+  PGMM_CUDA(cudaMemcpyAsync(d_a_.p, ha, n_total * sizeof(U128), cudaMemcpyHostToDevice, st));
+  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, n_segs * sizeof(int4), cudaMemcpyHostToDevice, st));
+  PGMM_CUDA(cudaEventRecord(ev0_, st));
+  chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, d_x_.p, d_y_.p, d_qs_.p);
+  chain_fill_kernel<<<(unsigned)n_segs, 32, kFillSmem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_segs_.p, P, dF, dP, dV, d_flag_.p);
+  PGMM_CUDA(cudaGetLastError());
+  PGMM_CUDA(cudaEventRecord(ev1_, st));
+  int32_t *hfpv = h_fpv_.ensure(3 * n_total);
+  int32_t *hflag = h_flag_.ensure(n_segs);
+  PGMM_CUDA(cudaMemcpyAsync(hfpv, d_f_.p, 3 * n_total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  PGMM_CUDA(cudaMemcpyAsync(hflag, d_flag_.p, n_segs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  PGMM_CUDA(cudaStreamSynchronize(st));
+  for (size_t q = 0; q < jobs.size(); ++q) {
+    ChainFillJob &j = jobs[q];
+    j.f = hfpv + base[q], j.p = hfpv + n_total + base[q], j.v = hfpv + 2 * n_total + base[q];
+  }
+  uint64_t redo_segs = 0, redo_anchors = 0;
+  for (size_t k = 0; k < n_segs; ++k)
+    if (hflag[k] != DONE) {
+      jobs[order[k].job].redo[order[k].seg] = (uint8_t)hflag[k];
+      ++redo_segs, redo_anchors += (uint64_t)order[k].len;
+    }
+  if (stats) {
+    float ms = 0;
+    PGMM_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats->anchors += n_total, stats->segments += n_segs, stats->redo_segments += redo_segs, stats->redo_anchors += redo_anchors;
+    stats->launches += 2, stats->kernel_ms += ms;
+  }
+}
+
+}  // namespace pgmm

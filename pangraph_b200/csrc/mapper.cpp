@@ -1292,7 +1292,9 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
   ChainParams cp{opt.max_gap, opt.rmq_inner_dist, opt.bw, opt.max_chain_skip, opt.rmq_size_cap, opt.min_cnt, opt.min_chain_score,
                  pen_gap, pen_skip};
 
-  // ---- per query: anchor order, chains, hit skeletons, first DP plan ----
+  // ---- per query: anchor order (host), chain scores (device), backtrack + hit skeletons + first DP plan (host) ----
+  const bool trace = getenv("PGMM_TRACE") != nullptr;
+  std::vector<ChainFillJob> cjobs(qb.n);
   parallel_for(qb.n, n_threads, [&](int i) {
     QCtx &q = Q[i];
     q.qi = i, q.qlen = qb.lens[i], q.qname = qb.names[i], q.qbase = qb.base[i];
@@ -1305,17 +1307,35 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     q.a.swap(seeds[i].a);
     q.mini_pos.swap(seeds[i].mini_pos);
     q.rep_len = seeds[i].rep_len;
-    const bool trace = getenv("PGMM_TRACE") != nullptr;
-    double c0 = now(), c1;
-    const size_t n_anchor = q.a.size();
     flag_sort_128x(q.a.data(), q.a.data() + q.a.size());  // map.c:202
+    ChainFillJob &cj = cjobs[i];
+    cj.a = q.a.data(), cj.n = (int64_t)q.a.size();
+    chain_find_segments(cp, cj.a, cj.n, cj.segs);
+  });
+  const double tc0 = now();
+  be.stats.t_chain_sort += tc0 - t0;
+  be.chain_fill(cp, cjobs);
+  const double tc1 = now();
+  be.stats.t_chain_fill += tc1 - tc0;
+  parallel_for(qb.n, n_threads, [&](int i) {
+    QCtx &q = Q[i];
+    ChainFillJob &cj = cjobs[i];
+    if (cj.n == 0) return;
+    double c0 = now(), c1;
+    std::vector<int32_t> t((size_t)cj.n, 0);
+    int64_t n_redo = 0;
+    for (size_t k = 0; k < cj.segs.size(); ++k)
+      if (cj.redo[k]) {
+        chain_fill_host(cp, cj.a, cj.n, cj.segs[k].start, cj.segs[k].end, cj.f, cj.p, cj.v, t.data());
+        n_redo += cj.segs[k].end - cj.segs[k].start;
+      }
     c1 = now();
-    const double t_sort = c1 - c0;
+    const double t_redo = c1 - c0;
     c0 = c1;
     std::vector<uint64_t> u;
-    chain_rmq(cp, q.a, u);
+    chain_backtrack(cp, q.a, cj.f, cj.p, cj.v, t.data(), u);
     c1 = now();
-    const double t_ch = c1 - c0;
+    const double t_bt = c1 - c0;
     c0 = c1;
     M.gen_regs(q, u);
     M.est_err(q);
@@ -1325,10 +1345,14 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     c0 = c1;
     for (auto &R : q.regs) M.plan_region(q, *R);
     c1 = now();
+    int64_t seg_max = 0;
+    for (const ChainSeg &sg : cj.segs) seg_max = std::max(seg_max, sg.end - sg.start);
     if (trace)
-      fprintf(stderr, "[pgmm trace] query %d: %zu anchors, sort %.1f ms, chain %.1f ms, regs %.1f ms, plan %.1f ms (%zu hits, %zu jobs)\n", i,
-              n_anchor, t_sort, t_ch, t_regs, c1 - c0, q.regs.size(), q.jobs.size());
+      fprintf(stderr, "[pgmm trace] query %d: %lld anchors in %zu segments (largest %lld), host refill %.1f ms (%lld anchors), backtrack %.1f ms, regs %.1f ms, "
+              "plan %.1f ms (%zu hits, %zu jobs)\n", i, (long long)cj.n, cj.segs.size(), (long long)seg_max, t_redo, (long long)n_redo, t_bt, t_regs, c1 - c0,
+              q.regs.size(), q.jobs.size());
   });
+  be.stats.t_chain_rest += now() - tc1;
 
   t1 = now(), be.stats.t_chain += t1 - t0, t0 = t1;
   // ---- DP waves ----

@@ -52,6 +52,10 @@ struct DpStats {
   // wall-clock phases of map_batch (ms): encode, seeding (GPU), anchor sort + chain + plan (host), DP waves (GPU incl.
   // copies), host work between waves, final filters + output
   double t_encode = 0, t_seed = 0, t_chain = 0, t_dp = 0, t_stitch = 0, t_final = 0;
+  // t_chain split: anchor sort + segments (host), score fill (device, incl. copies), segments redone on the host +
+  // backtrack + hit skeletons + first DP plan (host)
+  double t_chain_sort = 0, t_chain_fill = 0, t_chain_rest = 0;
+  ChainFillStats chain;
 };
 
 // The device stages.  The product has exactly one implementation (CUDA, cuda_backend.cu); a second one exists only in
@@ -61,6 +65,9 @@ struct Backend {
   virtual ~Backend() {}
   virtual void begin_batch(const TargetSet &ts, const QueryBatch &qb) = 0;
   virtual void seed_batch(const TargetSet &ts, const QueryBatch &qb, const mm_mapopt_t &opt, std::vector<QuerySeeds> &out) = 0;
+  // score fill of the chaining stage for every query of the batch (chain.h); segments the device hands back are
+  // marked in jobs[i].redo and filled by the caller with chain_fill_host
+  virtual void chain_fill(const ChainParams &cp, std::vector<ChainFillJob> &jobs) = 0;
   // q_off indexes qb.codes, t_off indexes ts.codes
   virtual void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) = 0;
   virtual void end_batch() {}

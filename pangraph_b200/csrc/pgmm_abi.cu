@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 
+#include "chain_fill.h"
 #include "ksw_extd2.h"
 #include "mapper.h"
 #include "pgmm_cuda.h"
@@ -26,6 +27,8 @@ struct Stats {
   double t_encode = 0, t_seed = 0, t_chain = 0, t_dp = 0, t_stitch = 0, t_final = 0;
   double fam_ms[3] = {0, 0, 0};
   uint64_t fam_cells[3] = {0, 0, 0}, fam_bases[3] = {0, 0, 0}, fam_launches[3] = {0, 0, 0};
+  double t_chain_sort = 0, t_chain_fill = 0, t_chain_rest = 0, chain_kernel_ms = 0;
+  uint64_t chain_anchors = 0, chain_segments = 0, chain_redo_segments = 0, chain_redo_anchors = 0, chain_launches = 0;
 };
 Stats g_stats;
 std::mutex g_stats_mu;
@@ -49,6 +52,7 @@ struct PgmmIndex {
 // concurrent callers (the reference maps queries from a rayon pool, one mm_tbuf_t each) run on different streams.
 struct DeviceCtx {
   SeedEngine seeder;
+  ChainEngine chainer;
   KswEngine ksw;
   DevBuf<uint8_t> d_qcodes;
   DeviceSeqSet qset;
@@ -172,6 +176,7 @@ struct CudaBackend : Backend {
     cx.seeder.collect(ix.didx, cx.qset, q_rank, opt, out, cx.stream);
     t_seed += now_ms() - t0;
   }
+  void chain_fill(const ChainParams &cp, std::vector<ChainFillJob> &jobs) override { cx.chainer.run(cp, jobs, cx.stream, &stats.chain); }
   void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) override {
     cx.ksw.run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res, cx.stream);
   }
@@ -212,6 +217,10 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   for (int f = 0; f < 3; ++f)
     g_stats.fam_ms[f] += be.stats.fam_ms[f], g_stats.fam_cells[f] += be.stats.fam_cells[f], g_stats.fam_bases[f] += be.stats.fam_bases[f],
         g_stats.fam_launches[f] += be.stats.fam_launches[f];
+  g_stats.t_chain_sort += be.stats.t_chain_sort, g_stats.t_chain_fill += be.stats.t_chain_fill, g_stats.t_chain_rest += be.stats.t_chain_rest;
+  g_stats.chain_kernel_ms += be.stats.chain.kernel_ms, g_stats.chain_anchors += be.stats.chain.anchors;
+  g_stats.chain_segments += be.stats.chain.segments, g_stats.chain_redo_segments += be.stats.chain.redo_segments;
+  g_stats.chain_redo_anchors += be.stats.chain.redo_anchors, g_stats.chain_launches += (uint64_t)be.stats.chain.launches;
   for (int i = 0; i < n; ++i) g_stats.bases_mapped += lens[i];
 }
 
@@ -355,19 +364,23 @@ void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *cons
 }
 
 // stats: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells [6] dp_waves [7] bases_mapped
-//        [8] bases_indexed [9] batches [10] kernel launches of the DP engine
+//        [8] bases_indexed [9] batches [10] kernel launches (all engines) ... [33..41] chaining: sort ms, fill ms, rest ms,
+//        fill kernel ms, anchors, segments, segments redone on the host, their anchors, launches
 void pgmm_get_stats(double *out, int n, int reset) {
   std::lock_guard<std::mutex> sl(g_stats_mu);
-  const double v[33] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+  const double v[42] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
                         (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
-                        (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches,
+                        (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches + (double)g_stats.chain_launches,
                         g_stats.t_encode, g_stats.t_seed, g_stats.t_chain, g_stats.t_dp, g_stats.t_stitch, g_stats.t_final,
                         (double)pgmm::h2d_bytes(), (double)pgmm::d2h_bytes(), (double)g_stats.dp_seq_bytes,
                         (double)pgmm::DevicePool::misses(),
                         g_stats.fam_ms[0], (double)g_stats.fam_cells[0], (double)g_stats.fam_bases[0], (double)g_stats.fam_launches[0],
                         g_stats.fam_ms[1], (double)g_stats.fam_cells[1], (double)g_stats.fam_bases[1], (double)g_stats.fam_launches[1],
-                        g_stats.fam_ms[2], (double)g_stats.fam_cells[2], (double)g_stats.fam_bases[2], (double)g_stats.fam_launches[2]};
-  for (int i = 0; i < n && i < 33; ++i) out[i] = v[i];
+                        g_stats.fam_ms[2], (double)g_stats.fam_cells[2], (double)g_stats.fam_bases[2], (double)g_stats.fam_launches[2],
+                        g_stats.t_chain_sort, g_stats.t_chain_fill, g_stats.t_chain_rest, g_stats.chain_kernel_ms,
+                        (double)g_stats.chain_anchors, (double)g_stats.chain_segments, (double)g_stats.chain_redo_segments,
+                        (double)g_stats.chain_redo_anchors, (double)g_stats.chain_launches};
+  for (int i = 0; i < n && i < 42; ++i) out[i] = v[i];
   if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0, pgmm::DevicePool::misses() = 0;
   if (reset) g_stats = Stats();
 }

@@ -1,6 +1,7 @@
 // Stage-level C-ABI entry points: each runs ONE device stage on host buffers so that tests can compare it with the
 // oracle in isolation.  Declared in include/pgmm_b200.h.
 #include "../../include/pgmm_b200.h"
+#include "chain_fill.h"
 #include "ksw_extd2.h"
 #include "pgmm_cuda.h"
 
@@ -51,4 +52,43 @@ extern "C" int pgmm_ksw_extd2_batch(int n, const int32_t *qlen, const int32_t *t
   if (!res.cigar.empty()) memcpy(out_cigar, res.cigar.data(), res.cigar.size() * sizeof(uint32_t));
   if (out_kernel_ms) *out_kernel_ms = res.kernel_ms;
   return 0;
+}
+
+// K4 alone: chains n sorted anchors (2 uint64 each) like mg_lchain_rmq.  The device fills the scores; segments it hands
+// back are filled by the host arbiter unless host_redo == 0, in which case -2 is returned when any segment was handed
+// back.  Returns n_u; u[] gets score<<32|count per chain, xy the compacted anchors, n_a_out their number;
+// out_fpv (3n int32, optional) gets f, p, v as filled; seg_stats (optional) = {segments, redone segments, redone anchors}.
+extern "C" int64_t pgmm_chain_rmq(uint64_t *xy, int64_t n, int max_dist, int max_dist_inner, int bw, int max_skip, int cap,
+                                  int min_cnt, int min_sc, float pen_gap, float pen_skip, uint64_t *u, int64_t *n_a_out,
+                                  int32_t *out_fpv, int64_t *seg_stats, int host_redo) {
+  require_device();
+  std::vector<U128> a((U128 *)xy, (U128 *)xy + n);
+  ChainParams cp{max_dist, max_dist_inner, bw, max_skip, cap, min_cnt, min_sc, pen_gap, pen_skip};
+  std::vector<ChainFillJob> jobs(1);
+  jobs[0].a = a.data(), jobs[0].n = n;
+  chain_find_segments(cp, a.data(), n, jobs[0].segs);
+  cudaStream_t st;
+  PGMM_CUDA(cudaStreamCreate(&st));
+  ChainEngine eng;
+  ChainFillStats cs;
+  eng.run(cp, jobs, st, &cs);
+  PGMM_CUDA(cudaStreamDestroy(st));
+  if (seg_stats) seg_stats[0] = (int64_t)cs.segments, seg_stats[1] = (int64_t)cs.redo_segments, seg_stats[2] = (int64_t)cs.redo_anchors;
+  *n_a_out = 0;
+  if (n == 0) return 0;
+  if (cs.redo_segments && !host_redo) return -2;
+  std::vector<int32_t> t((size_t)n, 0);
+  for (size_t k = 0; k < jobs[0].segs.size(); ++k)
+    if (jobs[0].redo[k]) chain_fill_host(cp, a.data(), n, jobs[0].segs[k].start, jobs[0].segs[k].end, jobs[0].f, jobs[0].p, jobs[0].v, t.data());
+  if (out_fpv) {
+    memcpy(out_fpv, jobs[0].f, (size_t)n * 4);
+    memcpy(out_fpv + n, jobs[0].p, (size_t)n * 4);
+    memcpy(out_fpv + 2 * n, jobs[0].v, (size_t)n * 4);
+  }
+  std::vector<uint64_t> uu;
+  chain_backtrack(cp, a, jobs[0].f, jobs[0].p, jobs[0].v, t.data(), uu);
+  memcpy(xy, a.data(), a.size() * 16);
+  memcpy(u, uu.data(), uu.size() * 8);
+  *n_a_out = (int64_t)a.size();
+  return (int64_t)uu.size();
 }

@@ -106,6 +106,17 @@ struct RefBackend : Backend {
       free(m), free(mini_pos), free(mv.a);
     }
   }
+  // no device here: every segment is handed back to the product's host arbiter (chain_fill_host)
+  std::vector<std::vector<int32_t>> fpv;
+  void chain_fill(const ChainParams &, std::vector<ChainFillJob> &jobs) override {
+    fpv.assign(jobs.size(), {});
+    for (size_t q = 0; q < jobs.size(); ++q) {
+      ChainFillJob &j = jobs[q];
+      fpv[q].assign((size_t)j.n * 3 + 1, 0);
+      j.f = fpv[q].data(), j.p = j.f + j.n, j.v = j.p + j.n;
+      j.redo.assign(j.segs.size(), 1);
+    }
+  }
   void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) override {
     const size_t n = jobs.size();
     res.out.assign(n, KswOut{});

@@ -1,0 +1,60 @@
+"""K4 (CUDA chain score fill) + the host backtrack through the C-ABI against the reference's mg_lchain_rmq: same
+chains, same scores, same anchors in the same order."""
+import numpy as np
+import pytest
+
+import chainref
+
+pytestmark = pytest.mark.gpu
+
+PEN_GAP = np.float32(0.8 * 0.01 * 19)
+
+
+def check(ref, a, max_dist=5000, inner=1000, bw=1000, skip=25, cap=100000, min_cnt=3, min_sc=40, pen_skip=0.0, host_redo=True):
+    from pangraph_b200 import abi
+    chainref.ref_sort(ref, a)
+    want_u, want_a = chainref.ref_chain(ref, a, max_dist, inner, bw, skip, cap, min_cnt, min_sc, PEN_GAP, pen_skip)
+    u, kept, fpv, seg = abi.chain_rmq(a, max_dist, inner, bw, skip, cap, min_cnt, min_sc, PEN_GAP, pen_skip, host_redo=host_redo)
+    assert np.array_equal(u, want_u)
+    assert np.array_equal(kept, want_a)
+    return len(want_u), seg
+
+
+@pytest.mark.parametrize("n,cap", [(0, 100000), (1, 100000), (8, 100000), (40, 100000), (2000, 100000), (30000, 100000), (30000, 300)])
+def test_noisy_anchor_sets(ref, n, cap):
+    """Collinear runs with jumps, 20 % noise anchors and repeated target positions; both strands, two targets."""
+    rng = np.random.default_rng(8 + n)
+    if n >= 8:
+        a = chainref.synth_anchors(rng, n)
+    else:
+        a = np.array([[1000, (19 << 32) | 700]] * n, dtype=np.uint64).reshape(n, 2)
+    n_u, seg = check(ref, a, max_dist=10000, cap=cap)
+    if n >= 2000:
+        assert n_u > 0
+
+
+@pytest.mark.parametrize("params", [dict(), dict(inner=0), dict(bw=100, max_dist=50), dict(skip=0), dict(skip=3, pen_skip=0.05),
+                                    dict(max_dist=300, inner=100)])
+def test_parameter_corners(ref, params):
+    rng = np.random.default_rng(31)
+    a = np.concatenate([chainref.synth_anchors(rng, 6000, noise=0.4), chainref.colinear_anchors(rng, 5000, rid=3)])
+    check(ref, a, **params)
+
+
+def test_genome_like_anchors_stay_on_the_device(ref):
+    """A long collinear stretch with substitutions, small indels and rearrangement jumps -- the benchmark's shape.
+    No segment may need the host arbiter (no equal priorities on such data)."""
+    rng = np.random.default_rng(5)
+    a = np.concatenate([chainref.colinear_anchors(rng, 200000), chainref.colinear_anchors(rng, 30000, strand=1, y0=40000)])
+    n_u, seg = check(ref, a, host_redo=False)
+    assert n_u > 5 and seg[1] == 0
+
+
+def test_dense_repeat_windows_go_to_the_host_arbiter(ref):
+    """An RMQ window beyond the device limit (every query position hits every target position of a repeat array)."""
+    from pangraph_b200 import abi
+    xs = np.repeat(np.arange(1000, 1000 + 3 * 150, 3, dtype=np.uint64), 60)
+    ys = np.tile(np.arange(500, 500 + 7 * 60, 7, dtype=np.uint64), 150)
+    a = np.stack([xs, (np.uint64(19) << np.uint64(32)) | ys], axis=1).copy()
+    n_u, seg = check(ref, a)
+    assert seg[1] >= 1
