@@ -64,20 +64,27 @@ __device__ __forceinline__ int link_score_dev(int xi, int yi, int xj, int yj, in
   return sc;
 }
 
-// -(f + 0.5 * pen_gap * (x + y)) in double (lchain.c:285), mapped to an unsigned key with the same order
-__device__ __forceinline__ unsigned long long pri_key(int f, int x, int y, float pen_gap) {
-  const double half_pen = __dmul_rn(0.5, (double)pen_gap);
-  const double pri = -__dadd_rn((double)f, __dmul_rn(half_pen, (double)(x + y)));
-  const long long b = __double_as_longlong(pri);
-  return b < 0 ? ~(unsigned long long)b : (unsigned long long)b | 0x8000000000000000ull;
-}
-
 __global__ void chain_prep_kernel(const U128 *__restrict__ a, int n, int *__restrict__ X, int *__restrict__ Y, uint8_t *__restrict__ QS) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const U128 v = a[i];
   X[i] = (int)(uint32_t)v.x, Y[i] = (int)(uint32_t)v.y, QS[i] = (uint8_t)(v.y >> 32 & 0xff);
 }
+
+// Shared memory is addressed through 32-bit shared-space addresses computed once (plain pointers into dynamic shared
+// memory made the compiler rebuild the shared window base from SR_CgaCtaId in front of every access).
+__device__ __forceinline__ int lds32(unsigned a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds64(unsigned a) {
+  unsigned long long v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(unsigned a, unsigned long long v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 
 // segs[b] = (first anchor, end, first anchor of the query, unused); one warp per segment.
 //
@@ -87,26 +94,32 @@ __global__ void chain_prep_kernel(const U128 *__restrict__ a, int n, int *__rest
 // read-only coordinates stay in global memory (L1-resident after the first touch); the warp fetches its next 32
 // anchors one batch ahead and broadcasts them by shuffle; results leave in coalesced batches of 32.
 __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ X, const int *__restrict__ Y, const uint8_t *__restrict__ QS,
-                                                        const int4 *__restrict__ segs, ChainDevParams P, int *__restrict__ F,
+                                                        const int4 *__restrict__ segs, const ChainDevParams P, int *__restrict__ F,
                                                         int *__restrict__ PP, int *__restrict__ V, int *__restrict__ seg_flag) {
   constexpr int R = ChainEngine::kRing, M = R - 1;
   extern __shared__ unsigned long long smem_u64[];
-  unsigned long long *spri = smem_u64;                 // [R]
-  unsigned long long *keys = spri + R;                 // [kInnerCap]
-  int *sf = (int *)(keys + ChainEngine::kInnerCap);    // [R] score
-  int *sv = sf + R;                                    // [R] peak score
-  int *sp = sv + R;                                    // [R] predecessor (batch-absolute index, -1 = none)
-  int *stamp = sp + R;                                 // [R] last step whose walk marked this anchor
+  const unsigned sm = (unsigned)__cvta_generic_to_shared(smem_u64);
+  const unsigned a_pri = sm;                                   // [R] u64 priority keys
+  const unsigned a_keys = a_pri + 8 * R;                       // [kInnerCap] u64 walk order
+  const unsigned a_f = a_keys + 8 * ChainEngine::kInnerCap;    // [R] score
+  const unsigned a_v = a_f + 4 * R;                            // [R] peak score
+  const unsigned a_p = a_v + 4 * R;                            // [R] predecessor (batch-absolute index, -1 = none)
+  const unsigned a_stamp = a_p + 4 * R;                        // [R] last step whose walk marked this anchor
   const int lane = threadIdx.x;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int4 sg = segs[blockIdx.x];
   const int s = sg.x, e = sg.y, qbase = sg.z;
+  const int max_dist = P.max_dist, max_dist_inner = P.max_dist_inner, bw = P.bw, max_skip = P.max_skip, cap = P.cap;
+  const float pen_gap = P.pen_gap, pen_skip = P.pen_skip;
+  const double half_pen = __dmul_rn(0.5, (double)pen_gap);
   int st = s, sti = s, i0 = s, xi0 = 0, flag = ChainEngine::DONE;
-  // smallest key of the visible window [st, i0) regardless of query position, its holder, whether it is shared
+  // smallest key of the visible window [st, i0) regardless of query position: its holder, the holder's query position,
+  // whether the key is shared
   unsigned long long cb_key = ~0ull, last_key = ~0ull;
-  int cb_j = -1;
+  int cb_j = -1, cb_y = 0;
   bool cb_tie = false, cb_valid = true;
-  for (int k = lane; k < R; k += 32) stamp[k] = -1;
+  int last_x = 0, last_y = 0, last_qs = 0, last_f = 0;  // the previous anchor, still in registers
+  for (int k = lane; k < R; k += 32) sts32(a_stamp + 4 * k, -1);
   __syncwarp();
 
   int nx = 0, ny = 0, nq = 0;
@@ -121,31 +134,38 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
       int max_f = qsi, max_j = -1;
       if (i == s) xi0 = xi;
       if (i0 < i && xi0 != xi) {  // the previous target position's anchors become visible together (:280-293)
-        for (int jj = i0; jj < i; ++jj) {
-          const unsigned long long k = jj == i - 1 ? last_key : spri[jj & M];
-          if (k < cb_key) cb_key = k, cb_j = jj, cb_tie = false;
-          else if (k == cb_key) cb_tie = true;
+        if (i0 == i - 1) {
+          if (last_key < cb_key) cb_key = last_key, cb_j = i - 1, cb_y = last_y, cb_tie = false;
+          else if (last_key == cb_key) cb_tie = true;
+        } else {
+#pragma unroll 1
+          for (int jj = i0; jj < i; ++jj) {
+            const unsigned long long k = lds64(a_pri + 8 * (jj & M));
+            if (k < cb_key) cb_key = k, cb_j = jj, cb_y = Y[jj], cb_tie = false;
+            else if (k == cb_key) cb_tie = true;
+          }
         }
         i0 = i, xi0 = xi;
       }
       // evictions (:295-312): too far behind on the target, or the window is over the size cap.  Both conditions are
-      // monotone in the index, so one ballot finds how far each window start moves (both loads are issued first)
+      // monotone in the index, so one ballot finds how far each window start moves (both loads are issued first);
+      // inside a segment the target coordinates differ by less than 2^31
       {
         const int c = st + lane, ci = sti + lane;
         const int xc = X[min(c, i)], xci = X[min(ci, i)];
-        bool ev = c < i && ((long long)xi > (long long)xc + P.max_dist || i0 - c > P.cap);
-        bool evi = P.max_dist_inner > 0 && ci < i && ((long long)xi > (long long)xci + P.max_dist_inner || i0 - ci > P.cap);
+        bool ev = c < i && (xi - xc > max_dist || i0 - c > cap);
+        bool evi = max_dist_inner > 0 && ci < i && (xi - xci > max_dist_inner || i0 - ci > cap);
         unsigned m = __ballot_sync(FULL, ev), mi = __ballot_sync(FULL, evi);
         st += __popc(m), sti += __popc(mi);
         while (m == FULL) {
           const int c2 = st + lane;
-          ev = c2 < i && ((long long)xi > (long long)X[min(c2, i)] + P.max_dist || i0 - c2 > P.cap);
+          ev = c2 < i && (xi - X[min(c2, i)] > max_dist || i0 - c2 > cap);
           m = __ballot_sync(FULL, ev);
           st += __popc(m);
         }
         while (mi == FULL) {
           const int c2 = sti + lane;
-          evi = c2 < i && ((long long)xi > (long long)X[min(c2, i)] + P.max_dist_inner || i0 - c2 > P.cap);
+          evi = c2 < i && (xi - X[min(c2, i)] > max_dist_inner || i0 - c2 > cap);
           mi = __ballot_sync(FULL, evi);
           sti += __popc(mi);
         }
@@ -160,27 +180,27 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
       // Fast path: the smallest key of the whole window, ignoring the query range, is carried from step to step (a newly
       // visible anchor is folded in; it is recomputed when its holder is evicted).  Along a chain that holder is the
       // newest anchor, and when it is unique and inside the query range it is the answer.  Otherwise the window is scanned.
-      const int ylo = yi - P.max_dist;
+      const int ylo = yi - max_dist;
       if (cb_j >= 0 && cb_j < st) cb_valid = false;
       if (st >= i0) cb_valid = true, cb_tie = false, cb_j = -1, cb_key = ~0ull;
       int j = -1;
       bool fast = cb_valid && !cb_tie;
       if (fast && cb_j >= 0) {
-        const int y = Y[cb_j];
-        if (y > ylo && (y < yi || (y == yi && cb_j == qbase))) j = cb_j;
+        if (cb_y > ylo && (cb_y < yi || (cb_y == yi && cb_j == qbase))) j = cb_j;
         else fast = false;
       }
       if (!fast) {  // branch-free scan, eight independent loads in flight; both the filtered and the unfiltered minimum
         unsigned long long bk = ~0ull, uk = ~0ull;
         int bj = -1, uj = -1;
         bool tie = false, utie = false;
+#pragma unroll 1
         for (int jb = st + lane; jb < i0 + lane; jb += 32 * kScanUnroll) {
           int yv[kScanUnroll];
           unsigned long long kv[kScanUnroll];
 #pragma unroll
           for (int u = 0; u < kScanUnroll; ++u) {
             const int jc = min(jb + 32 * u, i0 - 1);
-            yv[u] = Y[jc], kv[u] = spri[jc & M];
+            yv[u] = Y[jc], kv[u] = lds64(a_pri + 8 * (jc & M));
           }
 #pragma unroll
           for (int u = 0; u < kScanUnroll; ++u) {
@@ -203,6 +223,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
           const unsigned hm = __ballot_sync(FULL, uj >= 0 && uk == cb_key);
           cb_tie = __popc(hm) > 1 || __any_sync(FULL, utie && uk == cb_key);
           cb_j = hm ? __shfl_sync(FULL, uj, __ffs(hm) - 1) : -1;
+          cb_y = cb_j >= 0 ? Y[cb_j] : 0;
           cb_valid = true;
         }
         const unsigned hi = (unsigned)(bk >> 32);
@@ -219,15 +240,19 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
         }
       }
       if (j >= 0) {
+        int xj, yj, qsj, fj;
+        if (j == i - 1) xj = last_x, yj = last_y, qsj = last_qs, fj = last_f;
+        else xj = X[j], yj = Y[j], qsj = QS[j], fj = lds32(a_f + 4 * (j & M));
         bool exact;
         int width;
-        const int sc = sf[j & M] + link_score_dev(xi, yi, X[j], Y[j], QS[j], P.pen_gap, P.pen_skip, exact, width);
-        if (width <= P.bw && sc > max_f) max_f = sc, max_j = j;
-        if (!exact && P.max_dist_inner > 0 && i0 > sti && yi > 0) {
+        const int sc = fj + link_score_dev(xi, yi, xj, yj, qsj, pen_gap, pen_skip, exact, width);
+        if (width <= bw && sc > max_f) max_f = sc, max_j = j;
+        if (!exact && max_dist_inner > 0 && i0 > sti && yi > 0) {
           // near neighbourhood (:319-348): members of [sti, i0) with query position in [yi - max_dist_inner, yi - 1],
           // visited in descending (query position, index) order
-          const int y_hi = yi - 1, y_lo = yi - P.max_dist_inner;
+          const int y_hi = yi - 1, y_lo = yi - max_dist_inner;
           int cnt = 0;
+#pragma unroll 1
           for (int base = i0 - 1; base >= sti; base -= 32) {
             const int j2 = base - lane;
             bool c = false;
@@ -235,7 +260,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
             if (j2 >= sti) y = Y[j2], c = y >= y_lo && y <= y_hi;
             const unsigned m = __ballot_sync(FULL, c);
             const int pos = cnt + __popc(m & lt_mask);
-            if (c && pos < ChainEngine::kInnerCap) keys[pos] = (unsigned long long)(unsigned)y << 32 | (unsigned)(j2 - s);
+            if (c && pos < ChainEngine::kInnerCap) sts64(a_keys + 8 * pos, (unsigned long long)(unsigned)y << 32 | (unsigned)(j2 - s));
             cnt += __popc(m);
           }
           if (cnt > ChainEngine::kInnerCap) {
@@ -244,43 +269,48 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
           }
           __syncwarp();
           bool unsorted = false;
-          for (int k = lane; k + 1 < cnt; k += 32) unsorted |= keys[k] < keys[k + 1];
+#pragma unroll 1
+          for (int k = lane; k + 1 < cnt; k += 32) unsorted |= lds64(a_keys + 8 * k) < lds64(a_keys + 8 * k + 8);
           if (__any_sync(FULL, unsorted)) {
             int n2 = 32;
             while (n2 < cnt) n2 <<= 1;
-            for (int k = cnt + lane; k < n2; k += 32) keys[k] = 0;  // smallest: pads end up behind every member
+            for (int k = cnt + lane; k < n2; k += 32) sts64(a_keys + 8 * k, 0);  // smallest: pads end up behind every member
             __syncwarp();
+#pragma unroll 1
             for (int k = 2; k <= n2; k <<= 1)
+#pragma unroll 1
               for (int d = k >> 1; d > 0; d >>= 1) {
+#pragma unroll 1
                 for (int w = lane; w < n2; w += 32) {
                   const int u = w ^ d;
                   if (u > w) {
-                    const unsigned long long ka = keys[w], kb = keys[u];
+                    const unsigned long long ka = lds64(a_keys + 8 * w), kb = lds64(a_keys + 8 * u);
                     const bool desc = (w & k) == 0;
-                    if (desc ? ka < kb : ka > kb) keys[w] = kb, keys[u] = ka;
+                    if (desc ? ka < kb : ka > kb) sts64(a_keys + 8 * w, kb), sts64(a_keys + 8 * u, ka);
                   }
                 }
                 __syncwarp();
               }
           }
           int n_skip = 0;
+#pragma unroll 1
           for (int c0 = 0; c0 < cnt; c0 += 32) {
             const int k = c0 + lane;
             int j2 = -1, sc2 = INT32_MIN;
             bool ok = false;
             if (k < cnt) {
-              j2 = s + (int)(unsigned)keys[k];
+              j2 = s + (int)(unsigned)lds64(a_keys + 8 * k);
               bool ex2;
               int w2;
-              sc2 = sf[j2 & M] + link_score_dev(xi, yi, X[j2], Y[j2], QS[j2], P.pen_gap, P.pen_skip, ex2, w2);
-              ok = w2 <= P.bw;
-              const int pj = sp[j2 & M];
+              sc2 = lds32(a_f + 4 * (j2 & M)) + link_score_dev(xi, yi, X[j2], Y[j2], QS[j2], pen_gap, pen_skip, ex2, w2);
+              ok = w2 <= bw;
+              const int pj = lds32(a_p + 4 * (j2 & M));
               // "a predecessor of something already seen in this walk" (:344); one outside the near window is never visited
-              if (ok && pj >= sti) stamp[pj & M] = i;
+              if (ok && pj >= sti) sts32(a_stamp + 4 * (pj & M), i);
             }
             __syncwarp();
             // every writer of an anchor's stamp sits earlier in the visiting order (a predecessor has a smaller query position)
-            const bool marked = ok && stamp[j2 & M] == i;
+            const bool marked = ok && lds32(a_stamp + 4 * (j2 & M)) == i;
             // running maximum before each lane's turn
             const int val = ok ? sc2 : INT32_MIN;
             int incl = val;
@@ -297,11 +327,11 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
             // the skip counter, event by event (:338-343)
             int brk = -1;
             if (um == 0) {
-              const int room = P.max_skip - n_skip;  // increments that still fit
+              const int room = max_skip - n_skip;  // increments that still fit
               if (__popc(im) > room) {
                 unsigned m2 = im;
                 for (int r = 0; r < room; ++r) m2 &= m2 - 1;
-                brk = __ffs(m2) - 1, n_skip = P.max_skip + 1;  // increment number room+1 trips the limit
+                brk = __ffs(m2) - 1, n_skip = max_skip + 1;  // increment number room+1 trips the limit
               } else n_skip += __popc(im);
             } else {
               unsigned evs = um | im;
@@ -310,7 +340,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
                 evs &= evs - 1;
                 if (um >> b & 1) {
                   if (n_skip > 0) --n_skip;
-                } else if (++n_skip > P.max_skip) {
+                } else if (++n_skip > max_skip) {
                   brk = b;
                   break;
                 }
@@ -327,22 +357,30 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
           }
         }
       }
-      last_key = pri_key(max_f, xi, yi, P.pen_gap);
+      {
+        const double pri = -__dadd_rn((double)max_f, __dmul_rn(half_pen, (double)(xi + yi)));  // lchain.c:285
+        const long long b = __double_as_longlong(pri);
+        last_key = b < 0 ? ~(unsigned long long)b : (unsigned long long)b | 0x8000000000000000ull;  // same order, unsigned
+      }
+      last_x = xi, last_y = yi, last_qs = qsi, last_f = max_f;
       if (lane == 0) {
         int vv = max_f;
         if (max_j >= 0) {
-          const int vm = sv[max_j & M];
+          const int vm = lds32(a_v + 4 * (max_j & M));
           if (vm > max_f) vv = vm;
         }
-        sf[i & M] = max_f, sp[i & M] = max_j, sv[i & M] = vv;
-        spri[i & M] = last_key;
+        const unsigned o = 4 * (i & M);
+        sts32(a_f + o, max_f), sts32(a_p + o, max_j), sts32(a_v + o, vv);
+        sts64(a_pri + 2 * o, last_key);
       }
       __syncwarp();
     }
     if (flag != ChainEngine::DONE) break;
     if (lane < nb) {  // this batch's results, coalesced
-      const int i = ib + lane, pj = sp[i & M];
-      F[i] = sf[i & M], V[i] = sv[i & M], PP[i] = pj >= 0 ? pj - qbase : -1;
+      const int i = ib + lane;
+      const unsigned o = 4 * (i & M);
+      const int pj = lds32(a_p + o);
+      F[i] = lds32(a_f + o), V[i] = lds32(a_v + o), PP[i] = pj >= 0 ? pj - qbase : -1;
     }
   }
   if (lane == 0) seg_flag[blockIdx.x] = flag;
