@@ -31,9 +31,14 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kScanUnroll = 8;
 
+// Read once from global memory at kernel start: values that arrive as kernel parameters are re-fetched from the constant
+// bank (and the shared-memory base / lane id re-derived from special registers) in front of almost every use, and on a
+// one-warp dependent chain each of those fetches is exposed latency.  `zero` is always 0: adding it makes the
+// shared-memory base and the lane id ordinary register values.
 struct ChainDevParams {
   int max_dist, max_dist_inner, bw, max_skip, cap;
   float pen_gap, pen_skip;
+  int zero;
 };
 
 // mmpriv.h:118-126, every operation rounded separately like the host build (-ffp-contract=off)
@@ -94,18 +99,19 @@ __device__ __forceinline__ void sts64(unsigned a, unsigned long long v) { asm vo
 // read-only coordinates stay in global memory (L1-resident after the first touch); the warp fetches its next 32
 // anchors one batch ahead and broadcasts them by shuffle; results leave in coalesced batches of 32.
 __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ X, const int *__restrict__ Y, const uint8_t *__restrict__ QS,
-                                                        const int4 *__restrict__ segs, const ChainDevParams P, int *__restrict__ F,
+                                                        const int4 *__restrict__ segs, const ChainDevParams *__restrict__ Pp, int *__restrict__ F,
                                                         int *__restrict__ PP, int *__restrict__ V, int *__restrict__ seg_flag) {
   constexpr int R = ChainEngine::kRing, M = R - 1;
   extern __shared__ unsigned long long smem_u64[];
-  const unsigned sm = (unsigned)__cvta_generic_to_shared(smem_u64);
+  const ChainDevParams P = *Pp;
+  const unsigned sm = (unsigned)__cvta_generic_to_shared(smem_u64) + (unsigned)P.zero;
   const unsigned a_pri = sm;                                   // [R] u64 priority keys
   const unsigned a_keys = a_pri + 8 * R;                       // [kInnerCap] u64 walk order
   const unsigned a_f = a_keys + 8 * ChainEngine::kInnerCap;    // [R] score
   const unsigned a_v = a_f + 4 * R;                            // [R] peak score
   const unsigned a_p = a_v + 4 * R;                            // [R] predecessor (batch-absolute index, -1 = none)
   const unsigned a_stamp = a_p + 4 * R;                        // [R] last step whose walk marked this anchor
-  const int lane = threadIdx.x;
+  const int lane = (int)threadIdx.x + P.zero;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int4 sg = segs[blockIdx.x];
   const int s = sg.x, e = sg.y, qbase = sg.z;
@@ -128,9 +134,13 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
     const int bx = nx, by = ny, bq = nq;
     if (ib + 32 + lane < e) nx = X[ib + 32 + lane], ny = Y[ib + 32 + lane], nq = QS[ib + 32 + lane];
     const int nb = min(32, e - ib);
+    // the broadcast of the next anchor and the loads the next eviction test needs are issued one step ahead
+    int xn = __shfl_sync(FULL, bx, 0), yn = __shfl_sync(FULL, by, 0), qn = __shfl_sync(FULL, bq, 0);
+    int xc = X[min(st + lane, ib)], xci = X[min(sti + lane, ib)];
     for (int t = 0; t < nb; ++t) {
       const int i = ib + t;
-      const int xi = __shfl_sync(FULL, bx, t), yi = __shfl_sync(FULL, by, t), qsi = __shfl_sync(FULL, bq, t);
+      const int xi = xn, yi = yn, qsi = qn;
+      xn = __shfl_sync(FULL, bx, (t + 1) & 31), yn = __shfl_sync(FULL, by, (t + 1) & 31), qn = __shfl_sync(FULL, bq, (t + 1) & 31);
       int max_f = qsi, max_j = -1;
       if (i == s) xi0 = xi;
       if (i0 < i && xi0 != xi) {  // the previous target position's anchors become visible together (:280-293)
@@ -152,7 +162,6 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
       // inside a segment the target coordinates differ by less than 2^31
       {
         const int c = st + lane, ci = sti + lane;
-        const int xc = X[min(c, i)], xci = X[min(ci, i)];
         bool ev = c < i && (xi - xc > max_dist || i0 - c > cap);
         bool evi = max_dist_inner > 0 && ci < i && (xi - xci > max_dist_inner || i0 - ci > cap);
         unsigned m = __ballot_sync(FULL, ev), mi = __ballot_sync(FULL, evi);
@@ -174,6 +183,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
         flag = ChainEngine::WINDOW;
         break;
       }
+      xc = X[min(st + lane, min(i + 1, e - 1))], xci = X[min(sti + lane, min(i + 1, e - 1))];
       // range minimum over [st, i0) with query position in (yi - max_dist, yi]; at yi itself only the query's first
       // anchor qualifies (the closed upper key is (yi, 0), :314).
       //
@@ -413,10 +423,12 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
   P.max_dist = cp.max_dist < cp.bw ? cp.bw : cp.max_dist;
   P.max_dist_inner = (cp.max_dist_inner <= 0 || cp.max_dist_inner >= P.max_dist) ? 0 : cp.max_dist_inner;
   P.bw = cp.bw, P.max_skip = cp.max_chn_skip, P.cap = cp.cap_rmq_size, P.pen_gap = cp.pen_gap, P.pen_skip = cp.pen_skip;
+  P.zero = 0;
 
   // staging: anchors query after query; segments longest first so that the long ones start first
   U128 *ha = h_a_.ensure(n_total);
-  int4 *hs = h_segs_.ensure(n_segs);
+  int4 *hs = h_segs_.ensure(n_segs + 2);  // the kernel's parameter block rides behind the segment list
+  static_assert(sizeof(ChainDevParams) <= 2 * sizeof(int4), "parameter block");
   struct Ref {
     int job, seg;
     int64_t len;
@@ -440,13 +452,15 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
     hs[k] = make_int4((int)(base[r.job] + sg.start), (int)(base[r.job] + sg.end), (int)base[r.job], 0);
   }
   d_a_.ensure(n_total), d_x_.ensure(n_total), d_y_.ensure(n_total), d_qs_.ensure(n_total), d_f_.ensure(3 * n_total);
-  d_segs_.ensure(n_segs), d_flag_.ensure(n_segs);
+  d_segs_.ensure(n_segs + 2), d_flag_.ensure(n_segs);
+  memcpy(hs + n_segs, &P, sizeof(P));
   int32_t *dF = d_f_.p, *dP = d_f_.p + n_total, *dV = d_f_.p + 2 * n_total;
   PGMM_CUDA(cudaMemcpyAsync(d_a_.p, ha, n_total * sizeof(U128), cudaMemcpyHostToDevice, st));
-  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, n_segs * sizeof(int4), cudaMemcpyHostToDevice, st));
+  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, (n_segs + 2) * sizeof(int4), cudaMemcpyHostToDevice, st));
   PGMM_CUDA(cudaEventRecord(ev0_, st));
   chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, d_x_.p, d_y_.p, d_qs_.p);
-  chain_fill_kernel<<<(unsigned)n_segs, 32, kFillSmem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_segs_.p, P, dF, dP, dV, d_flag_.p);
+  chain_fill_kernel<<<(unsigned)n_segs, 32, kFillSmem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_segs_.p, (const ChainDevParams *)(d_segs_.p + n_segs), dF, dP, dV,
+                                                            d_flag_.p);
   PGMM_CUDA(cudaGetLastError());
   PGMM_CUDA(cudaEventRecord(ev1_, st));
   int32_t *hfpv = h_fpv_.ensure(3 * n_total);
