@@ -916,7 +916,7 @@ KswEngine::KswEngine() : impl_(new Impl) {
     // the thousands of small fills soak up whatever is left
     const bool small = c == 20 || c < 4;
     PGMM_CUDA(cudaStreamCreateWithPriority(&impl_->cls_stream[c], cudaStreamNonBlocking, small ? prio_lo : prio_hi));
-    PGMM_CUDA(cudaEventCreateWithFlags(&impl_->cls_done[c], cudaEventDisableTiming));
+    PGMM_CUDA(cudaEventCreateWithFlags(&impl_->cls_done[c], cudaEventDisableTiming | cudaEventBlockingSync));
     PGMM_CUDA(cudaEventCreate(&impl_->cls_t0[c]));
     PGMM_CUDA(cudaEventCreate(&impl_->cls_t1[c]));
   }
@@ -959,6 +959,8 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
   }
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return geo[a].p_bytes > geo[b].p_bytes; });
 
+  // problems whose state is larger than this keep it in the global slab (L2-resident) instead of shared memory
+  static const size_t state_limit = getenv("PGMM_STATE_SMEM_KB") ? std::min(kSmemMax, (size_t)atoi(getenv("PGMM_STATE_SMEM_KB")) * 1024) : kSmemMax;
   size_t pos = 0;
   while (pos < order.size()) {
     // ---- carve one wave ----
@@ -969,7 +971,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       if (end > pos && p_used + pb > arena_budget_bytes) break;
       jobs[i].p_off = p_used, p_used += pb;
       jobs[i].cig_off = cig_used, cig_used += (size_t)jobs[i].qlen + jobs[i].tlen + 2;
-      if (geo[i].state_bytes > kSmemMax) jobs[i].scr_off = scr_used, scr_used += (geo[i].state_bytes + 255) / 256 * 256;
+      if (geo[i].state_bytes > state_limit) jobs[i].scr_off = scr_used, scr_used += (geo[i].state_bytes + 255) / 256 * 256;
       else jobs[i].scr_off = ~0ull;
       ++end;
     }
@@ -1007,7 +1009,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       if (sb <= 6 * 1024 && words <= 96) nt_tier = 0;  // small fills: one warp, a few words per lane
       else nt_tier = words <= 64 ? 1 : words <= 128 ? 2 : words <= 256 ? 3 : 4;
       if (nt_tier > max_nt_tier) nt_tier = max_nt_tier;
-      sm_tier = sb > kSmemMax ? 3 : sb <= 12 * 1024 ? 0 : sb <= 48 * 1024 ? 1 : 2;
+      sm_tier = sb > state_limit ? 3 : sb <= 12 * 1024 ? 0 : sb <= 48 * 1024 ? 1 : 2;
       const int c = nt_tier * 4 + sm_tier;
       cls[c].push_back((int)k);
       if (sm_tier < 3) cls_smem[c] = std::max(cls_smem[c], sb);
@@ -1034,10 +1036,11 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     // the size classes are independent launches: fork them onto their own streams so that the few long problems of the
     // large classes overlap with the many short ones instead of queueing behind each other
     PGMM_CUDA(cudaEventRecord(m.fork, stream));
+    static const bool no_fork = getenv("PGMM_NO_CLASS_STREAMS") != nullptr;
     for (int c = kClasses - 1; c >= 0; --c) {  // widest / longest first
       if (cls[c].empty()) continue;
-      cudaStream_t cs = m.cls_stream[c];
-      PGMM_CUDA(cudaStreamWaitEvent(cs, m.fork, 0));
+      cudaStream_t cs = no_fork ? stream : m.cls_stream[c];
+      if (!no_fork) PGMM_CUDA(cudaStreamWaitEvent(cs, m.fork, 0));
       PGMM_CUDA(cudaEventRecord(m.cls_t0[c], cs));
 #define PGMM_LAUNCH(NT, SMEM)                                                                                                     \
   launch_class<NT>(cls[c], SMEM, m.d_ids.p, cls_off[c], m.d_jobs.p, d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.scratch.p, m.d_outs.p, \
@@ -1088,8 +1091,16 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
 #undef PGMM_LAUNCH
       PGMM_CUDA(cudaEventRecord(m.cls_t1[c], cs));
       PGMM_CUDA(cudaEventRecord(m.cls_done[c], cs));
-      PGMM_CUDA(cudaStreamWaitEvent(stream, m.cls_done[c], 0));
       ++res.launches;
+    }
+    // The classes are joined on the HOST.  A cudaStreamWaitEvent on the main stream would park that wait at the head of
+    // one of the device's (at most 32) hardware queues for the whole wave, and the streams of other rounds that share the
+    // queue would stall behind it: with two dozen rounds in flight that serialises rounds against each other.
+    static const bool host_join = getenv("PGMM_DEVICE_JOIN") == nullptr;
+    for (int c = 0; c < kClasses && !no_fork; ++c) {
+      if (cls[c].empty()) continue;
+      if (host_join) PGMM_CUDA(cudaEventSynchronize(m.cls_done[c]));
+      else PGMM_CUDA(cudaStreamWaitEvent(stream, m.cls_done[c], 0));
     }
     PGMM_CUDA(cudaEventRecord(m.ev1, stream));
 
