@@ -117,13 +117,14 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
   const int s = sg.x, e = sg.y, qbase = sg.z;
   const int max_dist = P.max_dist, max_dist_inner = P.max_dist_inner, bw = P.bw, max_skip = P.max_skip, cap = P.cap;
   const float pen_gap = P.pen_gap, pen_skip = P.pen_skip;
-  const double half_pen = __dmul_rn(0.5, (double)pen_gap);
+  double half_pen = __dmul_rn(0.5, (double)pen_gap);
+  asm volatile("" : "+d"(half_pen));  // keep it in a register: it is recomputed in front of every use otherwise
   int st = s, sti = s, i0 = s, xi0 = 0, flag = ChainEngine::DONE;
   // smallest key of the visible window [st, i0) regardless of query position: its holder, the holder's query position,
   // whether the key is shared
   unsigned long long cb_key = ~0ull, last_key = ~0ull;
-  int cb_j = -1, cb_y = 0;
-  bool cb_tie = false, cb_valid = true;
+  int cb_j = -1, cb_y = 0;  // cb_j: holder, -1 = empty window, -2 = must be recomputed
+  bool cb_tie = false;
   int last_x = 0, last_y = 0, last_qs = 0, last_f = 0;  // the previous anchor, still in registers
   for (int k = lane; k < R; k += 32) sts32(a_stamp + 4 * k, -1);
   __syncwarp();
@@ -191,10 +192,10 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
       // visible anchor is folded in; it is recomputed when its holder is evicted).  Along a chain that holder is the
       // newest anchor, and when it is unique and inside the query range it is the answer.  Otherwise the window is scanned.
       const int ylo = yi - max_dist;
-      if (cb_j >= 0 && cb_j < st) cb_valid = false;
-      if (st >= i0) cb_valid = true, cb_tie = false, cb_j = -1, cb_key = ~0ull;
+      if ((unsigned)cb_j < (unsigned)st) cb_j = -2;  // the holder was evicted
+      if (st >= i0) cb_tie = false, cb_j = -1, cb_key = ~0ull;
       int j = -1;
-      bool fast = cb_valid && !cb_tie;
+      bool fast = cb_j != -2 && !cb_tie;
       if (fast && cb_j >= 0) {
         if (cb_y > ylo && (cb_y < yi || (cb_y == yi && cb_j == qbase))) j = cb_j;
         else fast = false;
@@ -234,7 +235,6 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
           cb_tie = __popc(hm) > 1 || __any_sync(FULL, utie && uk == cb_key);
           cb_j = hm ? __shfl_sync(FULL, uj, __ffs(hm) - 1) : -1;
           cb_y = cb_j >= 0 ? Y[cb_j] : 0;
-          cb_valid = true;
         }
         const unsigned hi = (unsigned)(bk >> 32);
         const unsigned mh = __reduce_min_sync(FULL, hi);
@@ -321,19 +321,22 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
             __syncwarp();
             // every writer of an anchor's stamp sits earlier in the visiting order (a predecessor has a smaller query position)
             const bool marked = ok && lds32(a_stamp + 4 * (j2 & M)) == i;
-            // running maximum before each lane's turn
-            const int val = ok ? sc2 : INT32_MIN;
-            int incl = val;
+            // running maximum before each lane's turn -- only needed when some candidate beats the score so far
+            int incl = INT32_MIN;
+            unsigned um = 0, im;
+            if (__any_sync(FULL, ok && sc2 > max_f)) {
+              incl = ok ? sc2 : INT32_MIN;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-              const int o = __shfl_up_sync(FULL, incl, d);
-              if (lane >= d) incl = max(incl, o);
-            }
-            int excl = __shfl_up_sync(FULL, incl, 1);
-            if (lane == 0) excl = INT32_MIN;
-            excl = max(excl, max_f);
-            const bool upd = ok && sc2 > excl;
-            const unsigned um = __ballot_sync(FULL, upd), im = __ballot_sync(FULL, ok && !upd && marked);
+              for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl = max(incl, o);
+              }
+              int excl = __shfl_up_sync(FULL, incl, 1);
+              if (lane == 0) excl = INT32_MIN;
+              excl = max(excl, max_f);
+              const bool upd = ok && sc2 > excl;
+              um = __ballot_sync(FULL, upd), im = __ballot_sync(FULL, ok && !upd && marked);
+            } else im = __ballot_sync(FULL, marked);
             // the skip counter, event by event (:338-343)
             int brk = -1;
             if (um == 0) {
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
               }
             }
             const int last = brk >= 0 ? brk : 31;
-            const int best = max(max_f, __shfl_sync(FULL, incl, last));
+            const int best = um ? max(max_f, __shfl_sync(FULL, incl, last)) : max_f;
             if (best > max_f) {
               const unsigned wm = __ballot_sync(FULL, ok && sc2 == best);  // the first lane reaching it made the last update
               max_j = __shfl_sync(FULL, j2, __ffs(wm) - 1);
