@@ -69,11 +69,52 @@ __device__ __forceinline__ int link_score_dev(int xi, int yi, int xj, int yj, in
   return sc;
 }
 
-__global__ void chain_prep_kernel(const U128 *__restrict__ a, int n, int *__restrict__ X, int *__restrict__ Y, uint8_t *__restrict__ QS) {
+// Everything about an anchor that depends on COORDINATES only is computed here, one thread per anchor, before the
+// sequential fill: the split coordinates, the start of its target-position group (when the group's predecessors become
+// visible, lchain.c:280-293), where both windows start once the evictions of lchain.c:295-312 have run (the conditions
+// are monotone in the index, so each start is a lower bound found by binary search), and the score of linking it to
+// the anchor right before it -- the predecessor the fill picks on most steps.
+// AUX[i] = (group start, outer window start, inner window start, link score << 2 | exact << 1 | width <= bw).
+__global__ void chain_prep_kernel(const U128 *__restrict__ a, int n, const int *__restrict__ seg_starts, int n_segs,
+                                  const ChainDevParams *__restrict__ Pp, int *__restrict__ X, int *__restrict__ Y, uint8_t *__restrict__ QS,
+                                  int4 *__restrict__ AUX) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const ChainDevParams P = *Pp;
   const U128 v = a[i];
-  X[i] = (int)(uint32_t)v.x, Y[i] = (int)(uint32_t)v.y, QS[i] = (uint8_t)(v.y >> 32 & 0xff);
+  const int x = (int)(uint32_t)v.x, y = (int)(uint32_t)v.y;
+  X[i] = x, Y[i] = y, QS[i] = (uint8_t)(v.y >> 32 & 0xff);
+  int lo = 0, hi = n_segs;  // the segment this anchor belongs to
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (seg_starts[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  const int s = seg_starts[lo];
+  // first index in [s, i] whose target coordinate is at least `bound`
+  const auto lower = [&](int bound) {
+    int l = s, h = i;  // a[i] itself always qualifies
+    while (l < h) {
+      const int mid = (l + h) >> 1;
+      if ((int)(uint32_t)a[mid].x >= bound) h = mid;
+      else l = mid + 1;
+    }
+    return l;
+  };
+  int i0 = i, scp = 0;
+  if (i > s) {
+    const U128 pv = a[i - 1];
+    const int px = (int)(uint32_t)pv.x;
+    if (px == x) i0 = lower(x);
+    bool exact;
+    int width;
+    const int sc = link_score_dev(x, y, px, (int)(uint32_t)pv.y, (int)(pv.y >> 32 & 0xff), P.pen_gap, P.pen_skip, exact, width);
+    scp = sc * 4 + (exact ? 2 : 0) + (width <= P.bw ? 1 : 0);
+  }
+  // x - a[c].x <= d  <=>  a[c].x >= x - d (no overflow: coordinates are below 2^31 and d is a distance)
+  const int st = min(i, max(lower(x - P.max_dist), i0 - P.cap));
+  const int sti = P.max_dist_inner > 0 ? min(i, max(lower(x - P.max_dist_inner), i0 - P.cap)) : s;
+  AUX[i] = make_int4(i0, st, sti, scp);
 }
 
 // Shared memory is addressed through 32-bit shared-space addresses computed once (plain pointers into dynamic shared
@@ -99,8 +140,8 @@ __device__ __forceinline__ void sts64(unsigned a, unsigned long long v) { asm vo
 // read-only coordinates stay in global memory (L1-resident after the first touch); the warp fetches its next 32
 // anchors one batch ahead and broadcasts them by shuffle; results leave in coalesced batches of 32.
 __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ X, const int *__restrict__ Y, const uint8_t *__restrict__ QS,
-                                                        const int4 *__restrict__ segs, const ChainDevParams *__restrict__ Pp, int *__restrict__ F,
-                                                        int *__restrict__ PP, int *__restrict__ V, int *__restrict__ seg_flag) {
+                                                        const int4 *__restrict__ AUX, const int4 *__restrict__ segs, const ChainDevParams *__restrict__ Pp,
+                                                        int *__restrict__ F, int *__restrict__ PP, int *__restrict__ V, int *__restrict__ seg_flag) {
   constexpr int R = ChainEngine::kRing, M = R - 1;
   extern __shared__ unsigned long long smem_u64[];
   const ChainDevParams P = *Pp;
@@ -111,40 +152,48 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
   const unsigned a_v = a_f + 4 * R;                            // [R] peak score
   const unsigned a_p = a_v + 4 * R;                            // [R] predecessor (batch-absolute index, -1 = none)
   const unsigned a_stamp = a_p + 4 * R;                        // [R] last step whose walk marked this anchor
+  const unsigned a_stage = a_stamp + 4 * R;                    // [32][8] this batch's anchors: x, y, i0, st | sti, link, q_span, -
   const int lane = (int)threadIdx.x + P.zero;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int4 sg = segs[blockIdx.x];
   const int s = sg.x, e = sg.y, qbase = sg.z;
-  const int max_dist = P.max_dist, max_dist_inner = P.max_dist_inner, bw = P.bw, max_skip = P.max_skip, cap = P.cap;
+  const int max_dist = P.max_dist, max_dist_inner = P.max_dist_inner, bw = P.bw, max_skip = P.max_skip;
   const float pen_gap = P.pen_gap, pen_skip = P.pen_skip;
   double half_pen = __dmul_rn(0.5, (double)pen_gap);
   asm volatile("" : "+d"(half_pen));  // keep it in a register: it is recomputed in front of every use otherwise
-  int st = s, sti = s, i0 = s, xi0 = 0, flag = ChainEngine::DONE;
+  int i0 = s, flag = ChainEngine::DONE;
   // smallest key of the visible window [st, i0) regardless of query position: its holder, the holder's query position,
   // whether the key is shared
   unsigned long long cb_key = ~0ull, last_key = ~0ull;
   int cb_j = -1, cb_y = 0;  // cb_j: holder, -1 = empty window, -2 = must be recomputed
   bool cb_tie = false;
-  int last_x = 0, last_y = 0, last_qs = 0, last_f = 0;  // the previous anchor, still in registers
+  int last_y = 0, last_f = 0;  // the previous anchor, still in registers
   for (int k = lane; k < R; k += 32) sts32(a_stamp + 4 * k, -1);
   __syncwarp();
 
   int nx = 0, ny = 0, nq = 0;
-  if (s + lane < e) nx = X[s + lane], ny = Y[s + lane], nq = QS[s + lane];
+  int4 na = make_int4(0, 0, 0, 0);
+  if (s + lane < e) nx = X[s + lane], ny = Y[s + lane], nq = QS[s + lane], na = AUX[s + lane];
   for (int ib = s; ib < e && flag == ChainEngine::DONE; ib += 32) {
-    const int bx = nx, by = ny, bq = nq;
-    if (ib + 32 + lane < e) nx = X[ib + 32 + lane], ny = Y[ib + 32 + lane], nq = QS[ib + 32 + lane];
+    // stage this batch (one 32-byte record per anchor, read back as two broadcast 16-byte loads per step), fetch the next
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + 32 * lane), "r"(nx), "r"(ny), "r"(na.x), "r"(na.y) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + 32 * lane + 16), "r"(na.z), "r"(na.w), "r"(nq), "r"(0) : "memory");
+    __syncwarp();
+    if (ib + 32 + lane < e) nx = X[ib + 32 + lane], ny = Y[ib + 32 + lane], nq = QS[ib + 32 + lane], na = AUX[ib + 32 + lane];
     const int nb = min(32, e - ib);
-    // the broadcast of the next anchor and the loads the next eviction test needs are issued one step ahead
-    int xn = __shfl_sync(FULL, bx, 0), yn = __shfl_sync(FULL, by, 0), qn = __shfl_sync(FULL, bq, 0);
-    int xc = X[min(st + lane, ib)], xci = X[min(sti + lane, ib)];
+    int4 ra, rb;  // the record of the next step, loaded one step ahead
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(a_stage));
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(a_stage + 16));
     for (int t = 0; t < nb; ++t) {
       const int i = ib + t;
-      const int xi = xn, yi = yn, qsi = qn;
-      xn = __shfl_sync(FULL, bx, (t + 1) & 31), yn = __shfl_sync(FULL, by, (t + 1) & 31), qn = __shfl_sync(FULL, bq, (t + 1) & 31);
+      const int xi = ra.x, yi = ra.y, i0n = ra.z, st = ra.w, sti = rb.x, link = rb.y, qsi = rb.z;
+      {
+        const unsigned nxt = a_stage + 32 * ((t + 1) & 31);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(nxt));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(nxt + 16));
+      }
       int max_f = qsi, max_j = -1;
-      if (i == s) xi0 = xi;
-      if (i0 < i && xi0 != xi) {  // the previous target position's anchors become visible together (:280-293)
+      if (i0n != i0) {  // the previous target position's anchors become visible together (:280-293)
         if (i0 == i - 1) {
           if (last_key < cb_key) cb_key = last_key, cb_j = i - 1, cb_y = last_y, cb_tie = false;
           else if (last_key == cb_key) cb_tie = true;
@@ -156,35 +205,12 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
             else if (k == cb_key) cb_tie = true;
           }
         }
-        i0 = i, xi0 = xi;
-      }
-      // evictions (:295-312): too far behind on the target, or the window is over the size cap.  Both conditions are
-      // monotone in the index, so one ballot finds how far each window start moves (both loads are issued first);
-      // inside a segment the target coordinates differ by less than 2^31
-      {
-        const int c = st + lane, ci = sti + lane;
-        bool ev = c < i && (xi - xc > max_dist || i0 - c > cap);
-        bool evi = max_dist_inner > 0 && ci < i && (xi - xci > max_dist_inner || i0 - ci > cap);
-        unsigned m = __ballot_sync(FULL, ev), mi = __ballot_sync(FULL, evi);
-        st += __popc(m), sti += __popc(mi);
-        while (m == FULL) {
-          const int c2 = st + lane;
-          ev = c2 < i && (xi - X[min(c2, i)] > max_dist || i0 - c2 > cap);
-          m = __ballot_sync(FULL, ev);
-          st += __popc(m);
-        }
-        while (mi == FULL) {
-          const int c2 = sti + lane;
-          evi = c2 < i && (xi - X[min(c2, i)] > max_dist_inner || i0 - c2 > cap);
-          mi = __ballot_sync(FULL, evi);
-          sti += __popc(mi);
-        }
+        i0 = i0n;
       }
       if (i - st >= R) {  // the ring no longer covers the window
         flag = ChainEngine::WINDOW;
         break;
       }
-      xc = X[min(st + lane, min(i + 1, e - 1))], xci = X[min(sti + lane, min(i + 1, e - 1))];
       // range minimum over [st, i0) with query position in (yi - max_dist, yi]; at yi itself only the query's first
       // anchor qualifies (the closed upper key is (yi, 0), :314).
       //
@@ -250,13 +276,15 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
         }
       }
       if (j >= 0) {
-        int xj, yj, qsj, fj;
-        if (j == i - 1) xj = last_x, yj = last_y, qsj = last_qs, fj = last_f;
-        else xj = X[j], yj = Y[j], qsj = QS[j], fj = lds32(a_f + 4 * (j & M));
-        bool exact;
-        int width;
-        const int sc = fj + link_score_dev(xi, yi, xj, yj, qsj, pen_gap, pen_skip, exact, width);
-        if (width <= bw && sc > max_f) max_f = sc, max_j = j;
+        bool exact, wok;
+        int sc;
+        if (j == i - 1) sc = last_f + (link >> 2), exact = link & 2, wok = link & 1;  // scored by the prep kernel
+        else {
+          int width;
+          sc = lds32(a_f + 4 * (j & M)) + link_score_dev(xi, yi, X[j], Y[j], QS[j], pen_gap, pen_skip, exact, width);
+          wok = width <= bw;
+        }
+        if (wok && sc > max_f) max_f = sc, max_j = j;
         if (!exact && max_dist_inner > 0 && i0 > sti && yi > 0) {
           // near neighbourhood (:319-348): members of [sti, i0) with query position in [yi - max_dist_inner, yi - 1],
           // visited in descending (query position, index) order
@@ -375,7 +403,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
         const long long b = __double_as_longlong(pri);
         last_key = b < 0 ? ~(unsigned long long)b : (unsigned long long)b | 0x8000000000000000ull;  // same order, unsigned
       }
-      last_x = xi, last_y = yi, last_qs = qsi, last_f = max_f;
+      last_y = yi, last_f = max_f;
       if (lane == 0) {
         int vv = max_f;
         if (max_j >= 0) {
@@ -401,7 +429,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
 
 }  // namespace
 
-constexpr size_t kFillSmem = (size_t)ChainEngine::kRing * (8 + 4 * 4) + (size_t)ChainEngine::kInnerCap * 8;
+constexpr size_t kFillSmem = (size_t)ChainEngine::kRing * (8 + 4 * 4) + (size_t)ChainEngine::kInnerCap * 8 + 32 * 32;
 
 ChainEngine::ChainEngine() {
   static const bool once = [] {
@@ -430,7 +458,9 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
 
   // staging: anchors query after query; segments longest first so that the long ones start first
   U128 *ha = h_a_.ensure(n_total);
-  int4 *hs = h_segs_.ensure(n_segs + 2);  // the kernel's parameter block rides behind the segment list
+  // behind the segment list ride the kernels' parameter block and the segment starts in ascending order
+  const size_t n_start4 = (n_segs + 3) / 4;
+  int4 *hs = h_segs_.ensure(n_segs + 2 + n_start4);
   static_assert(sizeof(ChainDevParams) <= 2 * sizeof(int4), "parameter block");
   struct Ref {
     int job, seg;
@@ -455,15 +485,22 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
     hs[k] = make_int4((int)(base[r.job] + sg.start), (int)(base[r.job] + sg.end), (int)base[r.job], 0);
   }
   d_a_.ensure(n_total), d_x_.ensure(n_total), d_y_.ensure(n_total), d_qs_.ensure(n_total), d_f_.ensure(3 * n_total);
-  d_segs_.ensure(n_segs + 2), d_flag_.ensure(n_segs);
+  d_segs_.ensure(n_segs + 2 + n_start4), d_flag_.ensure(n_segs), d_aux_.ensure(n_total);
   memcpy(hs + n_segs, &P, sizeof(P));
+  {
+    int *starts = (int *)(hs + n_segs + 2);
+    size_t k = 0;
+    for (size_t q = 0; q < jobs.size(); ++q)
+      for (const ChainSeg &sg : jobs[q].segs) starts[k++] = (int)(base[q] + sg.start);  // ascending by construction
+  }
   int32_t *dF = d_f_.p, *dP = d_f_.p + n_total, *dV = d_f_.p + 2 * n_total;
   PGMM_CUDA(cudaMemcpyAsync(d_a_.p, ha, n_total * sizeof(U128), cudaMemcpyHostToDevice, st));
-  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, (n_segs + 2) * sizeof(int4), cudaMemcpyHostToDevice, st));
+  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, (n_segs + 2 + n_start4) * sizeof(int4), cudaMemcpyHostToDevice, st));
   PGMM_CUDA(cudaEventRecord(ev0_, st));
-  chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, d_x_.p, d_y_.p, d_qs_.p);
-  chain_fill_kernel<<<(unsigned)n_segs, 32, kFillSmem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_segs_.p, (const ChainDevParams *)(d_segs_.p + n_segs), dF, dP, dV,
-                                                            d_flag_.p);
+  const ChainDevParams *dP_ = (const ChainDevParams *)(d_segs_.p + n_segs);
+  chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, (const int *)(d_segs_.p + n_segs + 2), (int)n_segs, dP_,
+                                                                       d_x_.p, d_y_.p, d_qs_.p, d_aux_.p);
+  chain_fill_kernel<<<(unsigned)n_segs, 32, kFillSmem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_aux_.p, d_segs_.p, dP_, dF, dP, dV, d_flag_.p);
   PGMM_CUDA(cudaGetLastError());
   PGMM_CUDA(cudaEventRecord(ev1_, st));
   int32_t *hfpv = h_fpv_.ensure(3 * n_total);

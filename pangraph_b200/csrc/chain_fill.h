@@ -26,7 +26,7 @@ class ChainEngine {
   DevBuf<U128> d_a_;
   DevBuf<int32_t> d_x_, d_y_, d_f_, d_flag_;
   DevBuf<uint8_t> d_qs_;
-  DevBuf<int4> d_segs_;
+  DevBuf<int4> d_segs_, d_aux_;
   PinBuf<U128> h_a_;
   PinBuf<int32_t> h_fpv_, h_flag_;
   PinBuf<int4> h_segs_;
