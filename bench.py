@@ -324,15 +324,32 @@ def ours(args):
             dp_kernels[name] = {"ms_total": ms, "launches": int(ln), "ms_per_launch": ms / max(1, ln), "cells": cells,
                                 "gb_per_s": (cells + bases) / (ms / 1e3) / 1e9 if ms > 0 else 0.0,
                                 "gcups": cells / (ms / 1e3) / 1e9 if ms > 0 else 0.0}
+        # K4 (chain score fill): one launch per round; algorithmic bytes per anchor = 25 read by the fill (x, y, q_span and
+        # the 16-byte window record the prep kernel leaves) + 12 written (f, p, v)
+        k4_ms, k4_anchors, k4_launches = st_res["chain_kernel_ms"], st_res["chain_anchors"], st_res["batches"]
+        dp_kernels["chain_fill_kernel (K4, chaining score fill)"] = {
+            "ms_total": k4_ms, "launches": int(k4_launches), "ms_per_launch": k4_ms / max(1, k4_launches), "anchors": k4_anchors,
+            "gb_per_s": 37.0 * k4_anchors / (k4_ms / 1e3) / 1e9 if k4_ms > 0 else 0.0,
+            "anchors_per_us": k4_anchors / (k4_ms * 1e3) if k4_ms > 0 else 0.0}
+        fams["chain_fill_kernel (K4, chaining score fill)"] = "k4"
         tot_ms = sum(v["ms_total"] for v in dp_kernels.values()) or 1.0
         for v in dp_kernels.values():
-            v["share_of_dp_time"] = v["ms_total"] / tot_ms
+            v["share_of_kernel_time"] = v["ms_total"] / tot_ms
         dom = max(dp_kernels, key=lambda k: dp_kernels[k]["ms_total"])
         achieved = dp_kernels[dom]["gb_per_s"]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dp_traffic.json")
         if os.path.exists(tp):  # dram bytes per launch from the committed `ncu --set full` captures
             traffic = json.load(open(tp)).get(fams[dom])
+        notes = {
+            "k4": "one warp per independent anchor segment walks a true dependent chain (each score feeds the next range minimum): "
+                  "the launch lasts as long as its longest segment (190 k of a query's 380 k anchors), 212 warp instructions per "
+                  "anchor at ~3.4 cycles each, no DRAM traffic to speak of (ncu: 3.9 MB) -- latency-bound, neither roofline applies; "
+                  "it is the longest kernel of a round by stream time while using one warp per segment "
+                  "(profiles/r01_k4_chain_fill_ncu_full.md)",
+            "dp": "the DP kernels are integer-issue bound, not HBM bound (K5a: ~4 instructions per cell against 1 traceback byte; "
+                  "ncu: 64 % of issue slots, 4 % of DRAM throughput), and a long fill runs on one SM: the HBM fraction is small "
+                  "by construction; launches of concurrent rounds share the GPU"}
         line = {
             "metric": METRIC, "value": bp_total / t_res / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -351,11 +368,9 @@ def ours(args):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "launches": dp_kernels[dom]["launches"], "ms_per_launch": dp_kernels[dom]["ms_per_launch"],
-                         "share_of_dp_time": dp_kernels[dom]["share_of_dp_time"],
-                         "note": "the DP kernels are integer-issue bound, not HBM bound (K5a: ~4 instructions per cell against 1 "
-                                 "traceback byte; ncu: 64 % of issue slots, 4 % of DRAM throughput), and a long fill runs on one "
-                                 "SM: the HBM fraction is small by construction; launches of concurrent rounds share the GPU"},
-            "dp_kernels": dp_kernels,
+                         "share_of_kernel_time": dp_kernels[dom]["share_of_kernel_time"],
+                         "note": notes["k4" if fams[dom] == "k4" else "dp"]},
+            "kernels": dp_kernels,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "phases_ms_per_round": {k: st_res[k] / (args.steps * P) for k in ("index_ms", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch",

@@ -39,6 +39,7 @@ struct ChainDevParams {
   int max_dist, max_dist_inner, bw, max_skip, cap;
   float pen_gap, pen_skip;
   int zero;
+  double half_pen;  // 0.5 * (double)pen_gap, the factor of lchain.c:285
 };
 
 // mmpriv.h:118-126, every operation rounded separately like the host build (-ffp-contract=off)
@@ -159,15 +160,14 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
   const int s = sg.x, e = sg.y, qbase = sg.z;
   const int max_dist = P.max_dist, max_dist_inner = P.max_dist_inner, bw = P.bw, max_skip = P.max_skip;
   const float pen_gap = P.pen_gap, pen_skip = P.pen_skip;
-  double half_pen = __dmul_rn(0.5, (double)pen_gap);
-  asm volatile("" : "+d"(half_pen));  // keep it in a register: it is recomputed in front of every use otherwise
+  const double half_pen = P.half_pen;
   int i0 = s, flag = ChainEngine::DONE;
   // smallest key of the visible window [st, i0) regardless of query position: its holder, the holder's query position,
   // whether the key is shared
   unsigned long long cb_key = ~0ull, last_key = ~0ull;
   int cb_j = -1, cb_y = 0;  // cb_j: holder, -1 = empty window, -2 = must be recomputed
   bool cb_tie = false;
-  int last_y = 0, last_f = 0;  // the previous anchor, still in registers
+  int last_y = 0, last_f = 0, last_v = 0;  // the previous anchor, still in registers
   for (int k = lane; k < R; k += 32) sts32(a_stamp + 4 * k, -1);
   __syncwarp();
 
@@ -177,20 +177,24 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
   for (int ib = s; ib < e && flag == ChainEngine::DONE; ib += 32) {
     // stage this batch (one 32-byte record per anchor, read back as two broadcast 16-byte loads per step), fetch the next
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + 32 * lane), "r"(nx), "r"(ny), "r"(na.x), "r"(na.y) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + 32 * lane + 16), "r"(na.z), "r"(na.w), "r"(nq), "r"(0) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + 32 * lane + 16), "r"(na.z), "r"(na.w), "r"(nq), "r"(ny - max_dist) : "memory");
     __syncwarp();
     if (ib + 32 + lane < e) nx = X[ib + 32 + lane], ny = Y[ib + 32 + lane], nq = QS[ib + 32 + lane], na = AUX[ib + 32 + lane];
     const int nb = min(32, e - ib);
-    int4 ra, rb;  // the record of the next step, loaded one step ahead
+    // records are loaded two steps ahead, so that nothing ever waits for the load it was just issued behind
+    int4 ra, rb, ra2, rb2;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(a_stage));
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(a_stage + 16));
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ra2.x), "=r"(ra2.y), "=r"(ra2.z), "=r"(ra2.w) : "r"(a_stage + 32));
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rb2.x), "=r"(rb2.y), "=r"(rb2.z), "=r"(rb2.w) : "r"(a_stage + 48));
     for (int t = 0; t < nb; ++t) {
       const int i = ib + t;
-      const int xi = ra.x, yi = ra.y, i0n = ra.z, st = ra.w, sti = rb.x, link = rb.y, qsi = rb.z;
+      const int xi = ra.x, yi = ra.y, i0n = ra.z, st = ra.w, sti = rb.x, link = rb.y, qsi = rb.z, ylo = rb.w;
+      ra = ra2, rb = rb2;
       {
-        const unsigned nxt = a_stage + 32 * ((t + 1) & 31);
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(nxt));
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(nxt + 16));
+        const unsigned nxt = a_stage + 32 * ((t + 2) & 31);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ra2.x), "=r"(ra2.y), "=r"(ra2.z), "=r"(ra2.w) : "r"(nxt));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rb2.x), "=r"(rb2.y), "=r"(rb2.z), "=r"(rb2.w) : "r"(nxt + 16));
       }
       int max_f = qsi, max_j = -1;
       if (i0n != i0) {  // the previous target position's anchors become visible together (:280-293)
@@ -217,7 +221,6 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
       // Fast path: the smallest key of the whole window, ignoring the query range, is carried from step to step (a newly
       // visible anchor is folded in; it is recomputed when its holder is evicted).  Along a chain that holder is the
       // newest anchor, and when it is unique and inside the query range it is the answer.  Otherwise the window is scanned.
-      const int ylo = yi - max_dist;
       if ((unsigned)cb_j < (unsigned)st) cb_j = -2;  // the holder was evicted
       if (st >= i0) cb_tie = false, cb_j = -1, cb_key = ~0ull;
       int j = -1;
@@ -399,17 +402,17 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
         }
       }
       {
-        const double pri = -__dadd_rn((double)max_f, __dmul_rn(half_pen, (double)(xi + yi)));  // lchain.c:285
-        const long long b = __double_as_longlong(pri);
+        const double sum = __dadd_rn((double)max_f, __dmul_rn(half_pen, (double)(xi + yi)));  // lchain.c:285: pri = -sum
+        const long long b = __double_as_longlong(sum) ^ (long long)0x8000000000000000ull;
         last_key = b < 0 ? ~(unsigned long long)b : (unsigned long long)b | 0x8000000000000000ull;  // same order, unsigned
       }
-      last_y = yi, last_f = max_f;
+      int vv = max_f;
+      if (max_j >= 0) {
+        const int vm = max_j == i - 1 ? last_v : lds32(a_v + 4 * (max_j & M));
+        if (vm > max_f) vv = vm;
+      }
+      last_y = yi, last_f = max_f, last_v = vv;
       if (lane == 0) {
-        int vv = max_f;
-        if (max_j >= 0) {
-          const int vm = lds32(a_v + 4 * (max_j & M));
-          if (vm > max_f) vv = vm;
-        }
         const unsigned o = 4 * (i & M);
         sts32(a_f + o, max_f), sts32(a_p + o, max_j), sts32(a_v + o, vv);
         sts64(a_pri + 2 * o, last_key);
@@ -454,14 +457,14 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
   P.max_dist = cp.max_dist < cp.bw ? cp.bw : cp.max_dist;
   P.max_dist_inner = (cp.max_dist_inner <= 0 || cp.max_dist_inner >= P.max_dist) ? 0 : cp.max_dist_inner;
   P.bw = cp.bw, P.max_skip = cp.max_chn_skip, P.cap = cp.cap_rmq_size, P.pen_gap = cp.pen_gap, P.pen_skip = cp.pen_skip;
-  P.zero = 0;
+  P.zero = 0, P.half_pen = 0.5 * (double)cp.pen_gap;
 
   // staging: anchors query after query; segments longest first so that the long ones start first
   U128 *ha = h_a_.ensure(n_total);
   // behind the segment list ride the kernels' parameter block and the segment starts in ascending order
   const size_t n_start4 = (n_segs + 3) / 4;
-  int4 *hs = h_segs_.ensure(n_segs + 2 + n_start4);
-  static_assert(sizeof(ChainDevParams) <= 2 * sizeof(int4), "parameter block");
+  int4 *hs = h_segs_.ensure(n_segs + 3 + n_start4);
+  static_assert(sizeof(ChainDevParams) <= 3 * sizeof(int4), "parameter block");
   struct Ref {
     int job, seg;
     int64_t len;
@@ -485,20 +488,20 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
     hs[k] = make_int4((int)(base[r.job] + sg.start), (int)(base[r.job] + sg.end), (int)base[r.job], 0);
   }
   d_a_.ensure(n_total), d_x_.ensure(n_total), d_y_.ensure(n_total), d_qs_.ensure(n_total), d_f_.ensure(3 * n_total);
-  d_segs_.ensure(n_segs + 2 + n_start4), d_flag_.ensure(n_segs), d_aux_.ensure(n_total);
+  d_segs_.ensure(n_segs + 3 + n_start4), d_flag_.ensure(n_segs), d_aux_.ensure(n_total);
   memcpy(hs + n_segs, &P, sizeof(P));
   {
-    int *starts = (int *)(hs + n_segs + 2);
+    int *starts = (int *)(hs + n_segs + 3);
     size_t k = 0;
     for (size_t q = 0; q < jobs.size(); ++q)
       for (const ChainSeg &sg : jobs[q].segs) starts[k++] = (int)(base[q] + sg.start);  // ascending by construction
   }
   int32_t *dF = d_f_.p, *dP = d_f_.p + n_total, *dV = d_f_.p + 2 * n_total;
   PGMM_CUDA(cudaMemcpyAsync(d_a_.p, ha, n_total * sizeof(U128), cudaMemcpyHostToDevice, st));
-  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, (n_segs + 2 + n_start4) * sizeof(int4), cudaMemcpyHostToDevice, st));
+  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, (n_segs + 3 + n_start4) * sizeof(int4), cudaMemcpyHostToDevice, st));
   PGMM_CUDA(cudaEventRecord(ev0_, st));
   const ChainDevParams *dP_ = (const ChainDevParams *)(d_segs_.p + n_segs);
-  chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, (const int *)(d_segs_.p + n_segs + 2), (int)n_segs, dP_,
+  chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, (const int *)(d_segs_.p + n_segs + 3), (int)n_segs, dP_,
                                                                        d_x_.p, d_y_.p, d_qs_.p, d_aux_.p);
   chain_fill_kernel<<<(unsigned)n_segs, 32, kFillSmem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_aux_.p, d_segs_.p, dP_, dF, dP, dV, d_flag_.p);
   PGMM_CUDA(cudaGetLastError());
