@@ -307,6 +307,13 @@ PGMM_API int64_t pgmm_chain_rmq(uint64_t *xy, int64_t n, int max_dist, int max_d
                                 int min_cnt, int min_sc, float pen_gap, float pen_skip, uint64_t *u, int64_t *n_a_out,
                                 int32_t *out_fpv, int64_t *seg_stats, int host_redo);
 
+/* CTA trace of the DP (K5/K5a/K5b) and chaining (K4) kernels: between begin and end every traced CTA appends one record
+ * of 40 bytes {uint64 t0, t1, t2 (%globaltimer ns: start, end of the main loop, end); uint32 kernel (1 K5a, 2 K5b first
+ * pass, 3 K5b exact pass, 4 K5 generic, 5 K4), block, smid, aux (rows or anchors)}.  begin: 0 ok, -1 already tracing.
+ * end: copies up to max_n records to out and returns how many the kernels produced. */
+PGMM_API int pgmm_cta_trace_begin(uint64_t capacity);
+PGMM_API int64_t pgmm_cta_trace_end(void *out, uint64_t max_n);
+
 /* counters since the last reset: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells
  * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] kernel launches [11..16] wall ms of the phases of
  * pgmm_map_batch (encode, seeding, sort+chain+plan, DP waves, stitching between waves, final filters)

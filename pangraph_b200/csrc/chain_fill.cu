@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
   const unsigned lt_mask = (1u << lane) - 1u;
   const int4 sg = segs[blockIdx.x];
   const int s = sg.x, e = sg.y, qbase = sg.z;
+  const unsigned long long tr0 = trace::begin();
   const int max_dist = P.max_dist, max_dist_inner = P.max_dist_inner, bw = P.bw, max_skip = P.max_skip;
   const float pen_gap = P.pen_gap, pen_skip = P.pen_skip;
   const double half_pen = P.half_pen;
@@ -427,10 +428,12 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
       F[i] = lds32(a_f + o), V[i] = lds32(a_v + o), PP[i] = pj >= 0 ? pj - qbase : -1;
     }
   }
-  if (lane == 0) seg_flag[blockIdx.x] = flag;
+  if (lane == 0) seg_flag[blockIdx.x] = flag, trace::emit(5, tr0, tr0, (unsigned)(e - s));
 }
 
 }  // namespace
+
+void trace_attach_chain(PgmmCtaTraceRec *buf, unsigned long long *cnt, unsigned long long cap) { trace::attach(buf, cnt, cap); }
 
 constexpr size_t kFillSmem = (size_t)ChainEngine::kRing * (8 + 4 * 4) + (size_t)ChainEngine::kInnerCap * 8 + 32 * 32;
 

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const K
   if (slot_id >= n_jobs) return;  // whole warp leaves together
   const int jid = job_ids[slot_id];
   const KswJob job = jobs[jid];
+  const unsigned long long tr0 = trace::begin();
   const int qlen = job.qlen, tlen = job.tlen;
   int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
   if (q2 + e2 < q + e) {
@@ -358,7 +359,9 @@ __global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const K
     ez.max = 0, ez.mqe = ez.mte = KSW_NEG_INF;
     ez.zdropped = 0, ez.reach_end = 0;
     ez.score = H0;  // the last anti-diagonal is the single cell (tlen-1, qlen-1)
+    const unsigned long long tr1 = trace::begin();
     finish_job(job, jid, ez, n_row, /*w=*/tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed, cig_counter, outs);
+    if (warp == 0) trace::emit(1, tr0, tr1, (unsigned)n_row);
   }
 }
 
@@ -391,6 +394,7 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int jid = job_ids[blockIdx.x];
   const KswJob job = jobs[jid];
+  const unsigned long long tr0 = trace::begin();
   const int qlen = job.qlen, tlen = job.tlen;
   int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
   if (q2 + e2 < q + e) {
@@ -586,9 +590,12 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
   }
   __threadfence_block();
   __syncthreads();
-  if (tid == 0)
+  if (tid == 0) {
+    const unsigned long long tr1 = trace::begin();
     finish_job(job, jid, ez, r_done + 1, tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed,
                cig_counter, outs);
+    trace::emit(EXACT ? 3 : 2, tr0, tr1, (unsigned)(r_done + 1));
+  }
 }
 
 template <int NT>
@@ -603,6 +610,7 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
   const int tid = threadIdx.x;
   const int jid = job_ids[blockIdx.x];  // index within this wave
   const KswJob job = jobs[jid];
+  const unsigned long long tr0 = trace::begin();
   const int qlen = job.qlen, tlen = job.tlen, flag = job.flag;
   int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
   if (q2 + e2 < q + e) {  // ksw2_extd2_sse.c:73
@@ -829,9 +837,12 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
     sw = X2c32, X2c32 = X2n32, X2n32 = sw;
   }
 
-  if (tid == 0)
+  if (tid == 0) {
+    const unsigned long long tr1 = trace::begin();
     finish_job(job, jid, ez, r_done + 1, w, /*abs_layout=*/false, stride, P, (const uint8_t *)TQ32, (const uint8_t *)QR32 + 4, sc,
                cig_arena, cig_packed, cig_counter, outs);
+    trace::emit(4, tr0, tr1, (unsigned)(r_done + 1));
+  }
 }
 
 constexpr size_t kSmemMax = 200 * 1024;
@@ -1144,5 +1155,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
   }
   res.cig_start[n] = res.cigar.size();
 }
+
+void trace_attach_ksw(PgmmCtaTraceRec *buf, unsigned long long *cnt, unsigned long long cap) { trace::attach(buf, cnt, cap); }
 
 }  // namespace pgmm

@@ -192,3 +192,44 @@ inline cudaError_t blocking_stream_sync(cudaStream_t st) {
 
 // every copy in the library goes through the counter
 #define cudaMemcpyAsync(dst, src, n, kind, st) pgmm::counted_memcpy_async((dst), (src), (n), (kind), (st))
+
+// ---- optional CTA trace (PGMM_CTA_TRACE / pgmm_cta_trace_begin): every traced CTA leaves (kernel, block, SM, start, end
+// of its main loop, end) in a device buffer, so that what actually overlaps on the GPU while many rounds are in flight
+// can be reconstructed without a timeline profiler.  Each translation unit has its own copy of the three device
+// variables; its attach function (trace_attach_*) points them at the shared buffer.
+struct PgmmCtaTraceRec {
+  unsigned long long t0, t1, t2;  // %globaltimer (ns): start, end of the main loop, end
+  unsigned kernel, block, smid, aux;
+};
+#ifdef __CUDACC__
+namespace pgmm {
+namespace trace {
+static __device__ PgmmCtaTraceRec *d_buf;
+static __device__ unsigned long long *d_cnt;
+static __device__ unsigned long long d_cap;
+__device__ __forceinline__ unsigned long long now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long begin() { return d_buf ? now() : 0ull; }
+__device__ __forceinline__ void emit(unsigned kernel, unsigned long long t0, unsigned long long t1, unsigned aux) {
+  if (!d_buf) return;
+  const unsigned long long idx = atomicAdd(d_cnt, 1ull);
+  if (idx >= d_cap) return;
+  unsigned sm;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+  PgmmCtaTraceRec r;
+  r.t0 = t0, r.t1 = t1, r.t2 = now(), r.kernel = kernel, r.block = blockIdx.x, r.smid = sm, r.aux = aux;
+  d_buf[idx] = r;
+}
+inline void attach(PgmmCtaTraceRec *buf, unsigned long long *cnt, unsigned long long cap) {
+  PGMM_CUDA(cudaMemcpyToSymbol(d_buf, &buf, sizeof(buf)));
+  PGMM_CUDA(cudaMemcpyToSymbol(d_cnt, &cnt, sizeof(cnt)));
+  PGMM_CUDA(cudaMemcpyToSymbol(d_cap, &cap, sizeof(cap)));
+}
+}  // namespace trace
+void trace_attach_ksw(PgmmCtaTraceRec *buf, unsigned long long *cnt, unsigned long long cap);
+void trace_attach_chain(PgmmCtaTraceRec *buf, unsigned long long *cnt, unsigned long long cap);
+}  // namespace pgmm
+#endif

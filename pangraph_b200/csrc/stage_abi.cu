@@ -5,6 +5,7 @@
 #include "ksw_extd2.h"
 #include "pgmm_cuda.h"
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -91,4 +92,35 @@ extern "C" int64_t pgmm_chain_rmq(uint64_t *xy, int64_t n, int max_dist, int max
   memcpy(u, uu.data(), uu.size() * 8);
   *n_a_out = (int64_t)a.size();
   return (int64_t)uu.size();
+}
+
+// ---- CTA trace (pgmm_cuda.h): begin allocates a device buffer of `capacity` records and attaches it to the DP and
+// chaining kernels; end detaches, copies up to max_n records (8 uint64 each: t0, t1, t2, kernel | block << 32,
+// smid | aux << 32 ... as laid out in PgmmCtaTraceRec) and returns how many were produced.
+static PgmmCtaTraceRec *g_trace_buf = nullptr;
+static unsigned long long *g_trace_cnt = nullptr;
+static unsigned long long g_trace_cap = 0;
+extern "C" int pgmm_cta_trace_begin(uint64_t capacity) {
+  require_device();
+  if (g_trace_buf) return -1;
+  PGMM_CUDA(cudaMalloc((void **)&g_trace_buf, capacity * sizeof(PgmmCtaTraceRec)));
+  PGMM_CUDA(cudaMalloc((void **)&g_trace_cnt, sizeof(unsigned long long)));
+  PGMM_CUDA(cudaMemset(g_trace_cnt, 0, sizeof(unsigned long long)));
+  g_trace_cap = capacity;
+  trace_attach_ksw(g_trace_buf, g_trace_cnt, capacity);
+  trace_attach_chain(g_trace_buf, g_trace_cnt, capacity);
+  return 0;
+}
+extern "C" int64_t pgmm_cta_trace_end(void *out, uint64_t max_n) {
+  if (!g_trace_buf) return -1;
+  PGMM_CUDA(cudaDeviceSynchronize());
+  trace_attach_ksw(nullptr, nullptr, 0);
+  trace_attach_chain(nullptr, nullptr, 0);
+  unsigned long long n = 0;
+  PGMM_CUDA(cudaMemcpy(&n, g_trace_cnt, sizeof(n), cudaMemcpyDeviceToHost));
+  const unsigned long long take = std::min<unsigned long long>(std::min<unsigned long long>(n, g_trace_cap), max_n);
+  if (take) PGMM_CUDA(cudaMemcpy(out, g_trace_buf, take * sizeof(PgmmCtaTraceRec), cudaMemcpyDeviceToHost));
+  cudaFree(g_trace_buf), cudaFree(g_trace_cnt);
+  g_trace_buf = nullptr, g_trace_cnt = nullptr;
+  return (int64_t)n;
 }
