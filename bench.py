@@ -4,9 +4,9 @@
 One ROUND = one find_matches call of a guide-tree leaf merge: two related synthetic 5-Mbp genomes (1 % divergence,
 10 rearrangements each) are indexed and aligned all-vs-all, i.e. mm_idx_str + mm_mapopt_update + one
 mm_map per sequence in the reference, index kernels + pgmm_map_batch here.
-One STEP = `--rounds-per-step` (default 108) such rounds, `--workers` (default 36) of them in flight at any moment: sibling leaf merges of the guide tree are independent
+One STEP = `--rounds-per-step` (default 192) such rounds, `--workers` (default 64) of them in flight at any moment: sibling leaf merges of the guide tree are independent
 (merge_graphs only reads its two children), so a rank keeps several of them in flight, one host thread and one CUDA
-stream each.  bp per step = total length of the genomes of its rounds.
+stream each; their DP waves are merged across rounds by the library's DP service (dp_service.cu).  bp per step = total length of the genomes of its rounds.
 
   python bench.py [--gpus N --steps K --warmup W]        our CUDA path (N>1: one rank per GPU under torchrun; every
                                                           rank aligns its own pairs -- leaf merges are independent --
@@ -396,8 +396,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--rounds-per-step", type=int, default=108, help="independent leaf-merge rounds a rank keeps in flight per step")
-    ap.add_argument("--workers", type=int, default=36, help="host threads driving rounds concurrently (one CUDA stream each)")
+    ap.add_argument("--rounds-per-step", type=int, default=192, help="independent leaf-merge rounds a rank keeps in flight per step")
+    ap.add_argument("--workers", type=int, default=64, help="host threads driving rounds concurrently (one CUDA stream each)")
     ap.add_argument("--pool", type=int, default=36, help="distinct genome pairs generated per rank (steps cycle through them)")
     ap.add_argument("--ref-sample-len", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -439,7 +439,7 @@ constexpr size_t kFillSmem = (size_t)ChainEngine::kRing * (8 + 4 * 4) + (size_t)
 
 ChainEngine::ChainEngine() {
   static const bool once = [] {
-    PGMM_CUDA(cudaFuncSetAttribute(chain_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFillSmem));
+    PGMM_CUDA(cudaFuncSetAttribute(chain_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     return true;
   }();
   (void)once;
@@ -506,7 +506,9 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
   const ChainDevParams *dP_ = (const ChainDevParams *)(d_segs_.p + n_segs);
   chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, (const int *)(d_segs_.p + n_segs + 3), (int)n_segs, dP_,
                                                                        d_x_.p, d_y_.p, d_qs_.p, d_aux_.p);
-  chain_fill_kernel<<<(unsigned)n_segs, 32, kFillSmem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_aux_.p, d_segs_.p, dP_, dF, dP, dV, d_flag_.p);
+  // PGMM_K4_SMEM_KB: shared memory a fill warp asks for at least (a large value keeps other CTAs off its SM)
+  static const size_t fill_smem = getenv("PGMM_K4_SMEM_KB") ? std::max(kFillSmem, (size_t)atoi(getenv("PGMM_K4_SMEM_KB")) * 1024) : kFillSmem;
+  chain_fill_kernel<<<(unsigned)n_segs, 32, fill_smem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_aux_.p, d_segs_.p, dP_, dF, dP, dV, d_flag_.p);
   PGMM_CUDA(cudaGetLastError());
   PGMM_CUDA(cudaEventRecord(ev1_, st));
   int32_t *hfpv = h_fpv_.ensure(3 * n_total);

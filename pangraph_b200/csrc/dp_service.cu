@@ -1,0 +1,182 @@
+// Cross-round batching of the DP waves (dp_service.h).
+#include "dp_service.h"
+
+#include <algorithm>
+#include <climits>
+#include <condition_variable>
+#include <cstdio>
+#include <ctime>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+#include "pgmm_cuda.h"
+
+namespace pgmm {
+
+namespace {
+struct Request {
+  std::vector<KswJob> jobs;   // this part's jobs (offsets relative to d_q / d_t)
+  std::vector<int> where;     // their positions in the caller's job list
+  const uint8_t *d_q, *d_t;
+  KswScoring sc;
+  std::shared_ptr<const KswBatchResult> merged;  // set by the worker
+  size_t base = 0;                               // first job of this request inside the merged wave
+  bool stats_owner = false, done = false;
+};
+}  // namespace
+
+// Two lanes with their own workers: a wave's few LONG problems (a fill across an inversion, a 10 kbp end extension:
+// one CTA for tens of milliseconds) must not hold back the thousands of short ones of other rounds that happen to be
+// merged with them, so they are batched separately; a round waits for both of its parts.
+struct DpService::Impl {
+  std::mutex mu;
+  std::condition_variable cv_work[2], cv_done;
+  std::deque<Request *> lane[2];
+  std::vector<std::thread> workers;
+  size_t arena_bytes[2] = {0, 0}, max_jobs = 0;
+
+  void worker(int L) {
+    std::deque<Request *> &pending = lane[L];
+    require_device();
+    cudaStream_t stream;
+    PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    KswEngine eng;
+    eng.arena_budget_bytes = arena_bytes[L];
+    std::vector<Request *> batch;
+    std::vector<KswJob> merged_jobs;
+    for (;;) {
+      batch.clear();
+      {
+        std::unique_lock<std::mutex> g(mu);
+        cv_work[L].wait(g, [&] { return !pending.empty(); });
+        // everything pending that scores like the first request (rounds of one build all do)
+        const KswScoring sc = pending.front()->sc;
+        size_t n = 0;
+        for (auto it = pending.begin(); it != pending.end();) {
+          if (memcmp(&(*it)->sc, &sc, sizeof(sc)) == 0 && (batch.empty() || n + (*it)->jobs.size() <= max_jobs)) {
+            n += (*it)->jobs.size();
+            batch.push_back(*it);
+            it = pending.erase(it);
+          } else ++it;
+        }
+      }
+      static const bool trace = getenv("PGMM_TRACE") != nullptr;
+      timespec ts0, ts1, ts2;
+      clock_gettime(CLOCK_MONOTONIC, &ts0);
+      merged_jobs.clear();
+      for (Request *r : batch) {
+        r->base = merged_jobs.size();
+        for (KswJob j : r->jobs) {  // absolute device addresses: the kernels add the offsets to a null base
+          j.q_off += (uint64_t)(uintptr_t)r->d_q, j.t_off += (uint64_t)(uintptr_t)r->d_t;
+          merged_jobs.push_back(j);
+        }
+      }
+      auto res = std::make_shared<KswBatchResult>();
+      clock_gettime(CLOCK_MONOTONIC, &ts1);
+      eng.run(merged_jobs, nullptr, nullptr, batch.front()->sc, *res, stream);
+      clock_gettime(CLOCK_MONOTONIC, &ts2);
+      if (trace)
+        fprintf(stderr, "[pgmm trace] dp batch (%s lane): %zu rounds, %zu jobs, merge %.1f ms, run %.1f ms (kernels %.1f ms, %d launches)\n", L ? "long" : "short", batch.size(),
+                merged_jobs.size(), (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6,
+                (ts2.tv_sec - ts1.tv_sec) * 1e3 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-6, res->kernel_ms, res->launches);
+      {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t k = 0; k < batch.size(); ++k) batch[k]->merged = res, batch[k]->stats_owner = k == 0, batch[k]->done = true;
+      }
+      cv_done.notify_all();
+    }
+  }
+};
+
+DpService::DpService() : impl_(new Impl) {
+  const char *e = getenv("PGMM_DP_ARENA_GB");
+  const double gb = e ? atof(e) : 6.0;  // per worker of the short lane; the long lane's workers take half of it each
+  impl_->arena_bytes[0] = (size_t)(gb * (double)(1ull << 30));
+  impl_->arena_bytes[1] = (size_t)(gb * 0.5 * (double)(1ull << 30));
+  e = getenv("PGMM_DP_MAX_JOBS");
+  impl_->max_jobs = e ? (size_t)atoll(e) : (size_t)300000;
+  // A batch lasts as long as its longest problem, and a worker runs one batch at a time: enough workers that a new
+  // wave rarely waits for a running batch (each owns one stream per size class and one arena).
+  e = getenv("PGMM_DP_WORKERS");  // "<short>x<long>"
+  int n_short = 6, n_long = 12;
+  if (e) sscanf(e, "%dx%d", &n_short, &n_long);
+  for (int i = 0; i < std::max(1, n_short); ++i) impl_->workers.emplace_back([this] { impl_->worker(0); });
+  for (int i = 0; i < std::max(1, n_long); ++i) impl_->workers.emplace_back([this] { impl_->worker(1); });
+  for (auto &t : impl_->workers) t.detach();
+}
+
+DpService &DpService::get() {
+  static DpService *s = new DpService;  // lives as long as the process
+  return *s;
+}
+
+bool DpService::enabled() {
+  static const bool on = [] {
+    const char *e = getenv("PGMM_DP_SERVICE");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+
+// A problem is LONG when a single CTA will spend milliseconds on it: anything but the small first-pass fills whose
+// wavefront or anti-diagonal count is large.
+static bool is_long_job(const KswJob &j) {
+  const int64_t rows = (int64_t)j.qlen + j.tlen;
+  const int64_t front = std::min<int64_t>(std::min(j.qlen, j.tlen), j.w < 0 ? INT32_MAX : (int64_t)j.w + 1);
+  return rows > 1500 && front > 300;
+}
+
+void DpService::run(const std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t *d_t, const KswScoring &sc, KswBatchResult &res) {
+  static const bool split = getenv("PGMM_DP_NO_SPLIT") == nullptr;
+  Request part[2];
+  for (int L = 0; L < 2; ++L) part[L].d_q = d_q, part[L].d_t = d_t, part[L].sc = sc;
+  const size_t n = jobs.size();
+  for (size_t i = 0; i < n; ++i) {
+    Request &r = part[split && is_long_job(jobs[i]) ? 1 : 0];
+    r.jobs.push_back(jobs[i]), r.where.push_back((int)i);
+  }
+  {
+    std::unique_lock<std::mutex> g(impl_->mu);
+    for (int L = 0; L < 2; ++L) {
+      if (part[L].jobs.empty()) part[L].done = true;
+      else impl_->lane[L].push_back(&part[L]), impl_->cv_work[L].notify_one();
+    }
+    impl_->cv_done.wait(g, [&] { return part[0].done && part[1].done; });
+  }
+  // this round's slices of the merged waves, back in the caller's job order (copied by the round's own thread)
+  res.out.assign(n, KswOut{});
+  res.cig_start.assign(n + 1, 0);
+  res.cells = 0, res.launches = 0, res.kernel_ms = 0.f;
+  for (int f = 0; f < 3; ++f) res.fam_ms[f] = 0.f, res.fam_cells[f] = 0, res.fam_bases[f] = 0, res.fam_launches[f] = 0;
+  std::vector<const uint32_t *> src(n, nullptr);
+  size_t words = 0;
+  for (int L = 0; L < 2; ++L) {
+    const Request &r = part[L];
+    if (!r.merged) continue;
+    const KswBatchResult &m = *r.merged;
+    for (size_t k = 0; k < r.where.size(); ++k) {
+      const size_t i = (size_t)r.where[k];
+      res.out[i] = m.out[r.base + k];
+      src[i] = m.cigar.data() + m.cig_start[r.base + k];
+      words += (size_t)res.out[i].n_cigar;
+    }
+    if (r.stats_owner) {  // a merged wave's counters are booked once
+      res.cells += m.cells, res.launches += m.launches, res.kernel_ms += m.kernel_ms;
+      for (int f = 0; f < 3; ++f)
+        res.fam_ms[f] += m.fam_ms[f], res.fam_cells[f] += m.fam_cells[f], res.fam_bases[f] += m.fam_bases[f], res.fam_launches[f] += m.fam_launches[f];
+    }
+  }
+  res.cigar.resize(words);
+  size_t pos = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const size_t nc = (size_t)res.out[i].n_cigar;
+    res.cig_start[i] = pos;
+    if (nc) memcpy(res.cigar.data() + pos, src[i], nc * sizeof(uint32_t));
+    pos += nc;
+  }
+  res.cig_start[n] = pos;
+}
+
+}  // namespace pgmm

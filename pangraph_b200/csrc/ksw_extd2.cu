@@ -1038,7 +1038,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     m.d_jobs.ensure(nw), m.d_outs.ensure(nw), m.d_ids.ensure(nw), m.d_counter.ensure(1);
     // the traceback arena is taken once at its full budget: growing it later would mean a cudaMalloc, which stalls
     // every stream of the device
-    m.p_arena.ensure(std::max(p_used + 256, arena_budget_bytes + 256));
+    m.p_arena.ensure_exact(std::max(p_used + 256, arena_budget_bytes + 256));
     m.cig_arena.ensure(2 * cig_used + 4), m.cig_packed.ensure(2 * cig_used + 4), m.scratch.ensure(scr_used + 256);
     PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, hj, nw * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
     PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, hid, nw * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1048,6 +1048,8 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     // large classes overlap with the many short ones instead of queueing behind each other
     PGMM_CUDA(cudaEventRecord(m.fork, stream));
     static const bool no_fork = getenv("PGMM_NO_CLASS_STREAMS") != nullptr;
+    // PGMM_WIDE_SMEM_KB: shared memory a long fill asks for at least (a large value keeps other CTAs off its SM)
+    static const size_t wide_min_smem = getenv("PGMM_WIDE_SMEM_KB") ? std::min(kSmemMax, (size_t)atoi(getenv("PGMM_WIDE_SMEM_KB")) * 1024) : 0;
     for (int c = kClasses - 1; c >= 0; --c) {  // widest / longest first
       if (cls[c].empty()) continue;
       cudaStream_t cs = no_fork ? stream : m.cls_stream[c];
@@ -1076,7 +1078,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       PGMM_CUDA(cudaFuncSetAttribute(ksw_fill_wide_kernel<NW, KP, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); \
       attr_set = true;                                                                                                          \
     }                                                                                                                           \
-    ksw_fill_wide_kernel<NW, KP, EX><<<(unsigned)cls[c].size(), NW * 32, cls_smem[c], cs>>>(                                    \
+    ksw_fill_wide_kernel<NW, KP, EX><<<(unsigned)cls[c].size(), NW * 32, std::max(cls_smem[c], wide_min_smem), cs>>>(                                    \
         m.d_jobs.p, m.d_ids.p + cls_off[c], d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p); \
     PGMM_CUDA(cudaGetLastError());                                                                                              \
   } while (0)

@@ -6,12 +6,14 @@
 #include <algorithm>
 #include <cstring>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "chain_fill.h"
+#include "dp_service.h"
 #include "ksw_extd2.h"
 #include "mapper.h"
 #include "pgmm_cuda.h"
@@ -53,15 +55,18 @@ struct PgmmIndex {
 struct DeviceCtx {
   SeedEngine seeder;
   ChainEngine chainer;
-  KswEngine ksw;
+  std::unique_ptr<KswEngine> ksw;  // only when the DP service is off (its 29 streams and its arena are per engine)
   DevBuf<uint8_t> d_qcodes;
   DeviceSeqSet qset;
   cudaStream_t stream = nullptr;
   DeviceCtx() {
     PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    const char *e = getenv("PGMM_ARENA_GB");
-    const double gb = e ? atof(e) : 8.0;
-    ksw.arena_budget_bytes = (size_t)(gb * (1ull << 30));
+    if (!DpService::enabled()) {
+      const char *e = getenv("PGMM_ARENA_GB");
+      const double gb = e ? atof(e) : 8.0;
+      ksw.reset(new KswEngine);
+      ksw->arena_budget_bytes = (size_t)(gb * (1ull << 30));
+    }
   }
 };
 class CtxPool {
@@ -178,7 +183,8 @@ struct CudaBackend : Backend {
   }
   void chain_fill(const ChainParams &cp, std::vector<ChainFillJob> &jobs) override { cx.chainer.run(cp, jobs, cx.stream, &stats.chain); }
   void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) override {
-    cx.ksw.run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res, cx.stream);
+    if (cx.ksw) cx.ksw->run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res, cx.stream);
+    else DpService::get().run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res);
   }
 };
 

@@ -116,6 +116,16 @@ struct DevBuf {
     p = nullptr;
     cap = 0, cls = 0;
   }
+  // for buffers whose size is a fixed budget (the traceback arenas): no headroom, 2 MB granularity
+  T *ensure_exact(size_t n) {
+    if (n > cap) {
+      release();
+      cls = (n * sizeof(T) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+      p = (T *)DevicePool::get().alloc(cls);
+      cap = cls / sizeof(T);
+    }
+    return p;
+  }
   T *ensure(size_t n) {
     if (n > cap) {
       release();
