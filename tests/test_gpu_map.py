@@ -113,3 +113,23 @@ def test_many_short_blocks():
     names.append("7")
     n = compare(seqs, names, "asm10")
     assert n > 50
+
+
+def test_rounds_without_the_dp_service(ref):
+    """PGMM_DP_SERVICE=0 keeps every round on its own DP engine (one arena and one set of streams per context): the same
+    hits as through the cross-round service, which every other test in this file uses."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys; sys.path.insert(0, '.');"
+        "from pangraph_b200 import abi, synth; from oracle import refmm2;"
+        "gs = synth.genomes(3, length=60_000, n_rearr=5, len_lo=300, len_hi=6000);"
+        "seqs, names = [g for _, g in gs], ['0', '1', '2'];"
+        "idx = abi.Index(seqs, names, 'asm10', None, 90); got = idx.map_batch(); idx.close();"
+        "want, _ = refmm2.ref_map_all(seqs, names, 'asm10', None, 90);"
+        "assert got == want and sum(len(g) for g in got) > 0; print('ok')"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PGMM_DP_SERVICE="0")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
