@@ -370,6 +370,15 @@ def ours(args):
                          "launches": dp_kernels[dom]["launches"], "ms_per_launch": dp_kernels[dom]["ms_per_launch"],
                          "share_of_kernel_time": dp_kernels[dom]["share_of_kernel_time"],
                          "note": notes["k4" if fams[dom] == "k4" else "dp"]},
+            # the same figures for the kernel that does most of the GPU's WORK (85 % of all DP cells; CTA trace: 243 of its CTAs
+            # resident on average against 14 warps of K4): bound by integer issue, not by HBM
+            "roofline_by_gpu_work": {"bound": "hbm", "kernel": "ksw_fill_small_kernel (K5a, first-pass gap fills)",
+                                     "achieved": dp_kernels["ksw_fill_small_kernel (K5a, first-pass gap fills)"]["gb_per_s"],
+                                     "peak": peak, "unit": "GB/s",
+                                     "frac": dp_kernels["ksw_fill_small_kernel (K5a, first-pass gap fills)"]["gb_per_s"] / peak if peak else None,
+                                     "traffic": json.load(open(tp)).get("k5a") if os.path.exists(tp) else None,
+                                     "note": notes["dp"] + "; launches of concurrent rounds overlap, so the per-launch rate under load "
+                                             "is a fraction of the 240 GCUPS a launch reaches alone (profiles/r01_k5a_ncu_full.md)"},
             "kernels": dp_kernels,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
