@@ -757,7 +757,9 @@ struct Mapper {
         q2[k] = (uint8_t)(c >= 4 ? 4 : 3 - c);
       }
       int q_off, t_off;
-      const int sc = ll_local_score(q_len, q2.data(), t_len, tseq + ez.zd_t0, mat, opt.q, opt.e, &q_off, &t_off);
+      // only "does the local score reach both thresholds" matters here (align.c:62-64): the scan stops as soon as it does
+      const int need = std::max(std::max(opt.min_chain_score * opt.a, opt.min_dp_max), 1);
+      const int sc = ll_local_score(q_len, q2.data(), t_len, tseq + ez.zd_t0, mat, opt.q, opt.e, &q_off, &t_off, need);
       if (sc >= opt.min_chain_score * opt.a && sc >= opt.min_dp_max) return 2;
     }
     return max_zdrop > opt.zdrop ? 1 : 0;
@@ -1066,7 +1068,7 @@ void parallel_for(int n, int n_threads, const std::function<void(int)> &fn);
 // position j + l*slen.  Written with the SSE2 intrinsics on x86-64 hosts and lane by lane elsewhere.
 #if defined(__SSE2__)
 int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,
-                   int *qe, int *te) {
+                   int *qe, int *te, int stop_at) {
   *qe = *te = -1;
   const int slen = (qlen + 7) / 8;
   if (slen == 0) {
@@ -1123,6 +1125,7 @@ int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
     const int imax = _mm_extract_epi16(m, 0);
     if (imax >= gmax) {
       gmax = imax, *te = i;
+      if (stop_at > 0 && gmax >= stop_at) return gmax;  // the caller only asks whether the score reaches stop_at
       memcpy(Hmax, H1, (size_t)slen * sizeof(__m128i));
     }
     std::swap(H0, H1);
@@ -1136,7 +1139,8 @@ int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
 // striped local alignment score with 16-bit lanes, restated lane by lane (ksw2_ll_sse.c:37-152): the result depends on
 // the striped layout (ties for the end positions, saturation), so the layout is kept: vector j, lane l <-> query j+l*slen
 int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,
-                   int *qe, int *te) {
+                   int *qe, int *te, int stop_at) {
+  (void)stop_at;
   typedef int16_t v8 __attribute__((vector_size(16)));
   *qe = *te = -1;
   const int slen = (qlen + 7) / 8;
@@ -1279,13 +1283,28 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     clock_gettime(CLOCK_MONOTONIC, &t);
     return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
   };
+  const auto cpu_ms = []() {  // CPU time of the whole process (meaningful per phase when one round runs alone)
+    timespec t;
+    clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &t);
+    return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+  };
+  const bool trace_cpu = getenv("PGMM_TRACE") != nullptr;
+  double cpu0 = cpu_ms();
+  const auto cpu_mark = [&](const char *what) {
+    if (!trace_cpu) return;
+    const double c = cpu_ms();
+    fprintf(stderr, "[pgmm trace] cpu %-28s %8.1f ms\n", what, c - cpu0);
+    cpu0 = c;
+  };
   double t0 = now(), t1;
   encode_queries(qb, ts, n_threads);
+  cpu_mark("encode");
   t1 = now(), be.stats.t_encode += t1 - t0, t0 = t1;
   be.begin_batch(ts, qb);
   std::vector<QuerySeeds> seeds;
   be.seed_batch(ts, qb, opt, seeds);
   t1 = now(), be.stats.t_seed += t1 - t0, t0 = t1;
+  cpu_mark("seeding (host side)");
 
   std::vector<QCtx> Q(qb.n);
   const float pen_gap = (float)(opt.chain_gap_scale * 0.01 * ts.k), pen_skip = (float)(opt.chain_skip_scale * 0.01 * ts.k);
@@ -1314,7 +1333,9 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
   });
   const double tc0 = now();
   be.stats.t_chain_sort += tc0 - t0;
+  cpu_mark("anchor sort + segments");
   be.chain_fill(cp, cjobs);
+  cpu_mark("chain fill (host side)");
   const double tc1 = now();
   be.stats.t_chain_fill += tc1 - tc0;
   parallel_for(qb.n, n_threads, [&](int i) {
@@ -1353,6 +1374,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
               q.regs.size(), q.jobs.size());
   });
   be.stats.t_chain_rest += now() - tc1;
+  cpu_mark("backtrack + regs + plan");
 
   t1 = now(), be.stats.t_chain += t1 - t0, t0 = t1;
   // ---- DP waves ----
@@ -1378,8 +1400,10 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
       for (auto &R : q.regs) any_waiting |= R->state != Region::DONE;
     if (!any_waiting) break;
     t1 = now(), be.stats.t_stitch += t1 - t0, t0 = t1;
+    cpu_mark("  wave: collect jobs");
     if (!jobs.empty()) {
       be.run_dp(jobs, sc, res);
+      cpu_mark("  wave: run_dp (host side)");
       t1 = now(), be.stats.t_dp += t1 - t0, t0 = t1;
       be.stats.jobs += jobs.size(), be.stats.cells += res.cells, be.stats.waves += 1;
       for (const KswJob &j : jobs) be.stats.seq_bytes += (uint64_t)j.qlen + j.tlen;
@@ -1441,9 +1465,11 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
       if (getenv("PGMM_TRACE") && tr_p1 + tr_fin + tr_plan > 1.0)
         fprintf(stderr, "[pgmm trace] query %d wave: test_zdrop+queue %.1f ms, finish %.1f ms, plan %.1f ms\n", qi, tr_p1, tr_fin, tr_plan);
     });
+    cpu_mark("  wave: stitch + next plan");
   }
   be.end_batch();
   t1 = now(), be.stats.t_stitch += t1 - t0, t0 = t1;
+  cpu_mark("  last wave: results");
 
   // ---- final filters, order, mapq, and the malloc()-owned result the boundary promises (minimap.h:353-366) ----
   parallel_for(qb.n, n_threads, [&](int qi) {
@@ -1475,6 +1501,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     n_regs[qi] = n, regs[qi] = out;
   });
   t1 = now(), be.stats.t_final += t1 - t0;
+  cpu_mark("final");
 }
 
 }  // namespace pgmm

@@ -83,7 +83,8 @@ extern const uint8_t kNt4[256];
 void encode_queries(QueryBatch &qb, const TargetSet &ts, int n_threads);
 
 // --- pieces exposed for stage-level tests ---
+// stop_at > 0: return as soon as the score reaches it (the end coordinates are then meaningless)
 int ll_local_score(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape,
-                   int *qe, int *te);
+                   int *qe, int *te, int stop_at = 0);
 
 }  // namespace pgmm
