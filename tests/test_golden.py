@@ -89,3 +89,25 @@ def test_cuda_path_reproduces_golden(name):
     blocks = {int(n): s for n, s in zip(names, seqs)}
     got = abi.find_filtered_matches(blocks, args)
     assert norm_matches(got, host_half.cigar_str) == norm_matches(g["matches"], None)
+
+
+def test_host_chainer_against_chain_fixture():
+    """The product's host chainer (segments + AVL arbiter + backtrack) on the committed mg_lchain_rmq fixtures
+    (tests/golden/golden_chain.npz, made by make_golden_chain.py from the unmodified reference)."""
+    import ctypes as C
+
+    import numpy as np
+
+    import hostlogic
+    hl = hostlogic.load()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_chain.npz"))
+    p = g["params"]
+    hl.pgmm_test_chain_rmq.restype = C.c_int64
+    for name in ("noisy", "colinear", "repeat_array"):
+        a = g[name + "_in"].copy()
+        u = np.zeros(len(a) + 1, dtype=np.uint64)
+        n_a = C.c_int64(0)
+        n_u = hl.pgmm_test_chain_rmq(C.c_void_p(a.ctypes.data), C.c_int64(len(a)), int(p[0]), int(p[1]), int(p[2]), int(p[3]), int(p[4]),
+                                     int(p[5]), int(p[6]), C.c_float(p[7]), C.c_float(p[8]), C.c_void_p(u.ctypes.data), C.byref(n_a))
+        assert n_u == len(g[name + "_u"]) and n_a.value == len(g[name + "_kept"]), name
+        assert np.array_equal(u[:n_u], g[name + "_u"]) and np.array_equal(a[:n_a.value], g[name + "_kept"]), name

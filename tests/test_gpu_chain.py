@@ -58,3 +58,16 @@ def test_dense_repeat_windows_go_to_the_host_arbiter(ref):
     a = np.stack([xs, (np.uint64(19) << np.uint64(32)) | ys], axis=1).copy()
     n_u, seg = check(ref, a)
     assert seg[1] >= 1
+
+
+def test_chain_fixture_without_the_reference_library():
+    """K4 + backtrack on the committed mg_lchain_rmq fixtures (tests/golden/golden_chain.npz): no oracle/_ref needed."""
+    import os
+
+    from pangraph_b200 import abi
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_chain.npz"))
+    p = g["params"]
+    for name in ("noisy", "colinear", "repeat_array"):
+        u, kept, fpv, seg = abi.chain_rmq(g[name + "_in"], int(p[0]), int(p[1]), int(p[2]), int(p[3]), int(p[4]), int(p[5]), int(p[6]),
+                                          np.float32(p[7]), float(p[8]))
+        assert np.array_equal(u, g[name + "_u"]) and np.array_equal(kept, g[name + "_kept"]), name
