@@ -27,15 +27,18 @@ struct Request {
 };
 }  // namespace
 
-// Two lanes with their own workers: a wave's few LONG problems (a fill across an inversion, a 10 kbp end extension:
-// one CTA for tens of milliseconds) must not hold back the thousands of short ones of other rounds that happen to be
-// merged with them, so they are batched separately; a round waits for both of its parts.
+// Three lanes with their own workers.  A merged wave lasts as long as its longest problem, so problems are batched with
+// their likes: SHORT (the thousands of small fills, < 1 ms each), MEDIUM (one CTA for a few ms: mid-size fills, end
+// extensions that cannot run long) and LONG (a fill across an inversion, a 10 kbp end extension: one CTA for tens of
+// milliseconds).  A round waits for all of its parts; a late wave that only carries a 3-ms problem no longer waits for
+// somebody else's 40-ms one.
+constexpr int kLanes = 3;
 struct DpService::Impl {
   std::mutex mu;
-  std::condition_variable cv_work[2], cv_done;
-  std::deque<Request *> lane[2];
+  std::condition_variable cv_work[kLanes], cv_done;
+  std::deque<Request *> lane[kLanes];
   std::vector<std::thread> workers;
-  size_t arena_bytes[2] = {0, 0}, max_jobs = 0;
+  size_t arena_bytes[kLanes] = {0, 0, 0}, max_jobs = 0;
 
   void worker(int L) {
     std::deque<Request *> &pending = lane[L];
@@ -78,7 +81,7 @@ struct DpService::Impl {
       eng.run(merged_jobs, nullptr, nullptr, batch.front()->sc, *res, stream);
       clock_gettime(CLOCK_MONOTONIC, &ts2);
       if (trace)
-        fprintf(stderr, "[pgmm trace] dp batch (%s lane): %zu rounds, %zu jobs, merge %.1f ms, run %.1f ms (kernels %.1f ms, %d launches)\n", L ? "long" : "short", batch.size(),
+        fprintf(stderr, "[pgmm trace] dp batch (%s lane): %zu rounds, %zu jobs, merge %.1f ms, run %.1f ms (kernels %.1f ms, %d launches)\n", L == 0 ? "short" : L == 1 ? "medium" : "long", batch.size(),
                 merged_jobs.size(), (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6,
                 (ts2.tv_sec - ts1.tv_sec) * 1e3 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-6, res->kernel_ms, res->launches);
       {
@@ -92,18 +95,19 @@ struct DpService::Impl {
 
 DpService::DpService() : impl_(new Impl) {
   const char *e = getenv("PGMM_DP_ARENA_GB");
-  const double gb = e ? atof(e) : 6.0;  // per worker of the short lane; the long lane's workers take half of it each
+  const double gb = e ? atof(e) : 6.0;  // per worker of the short lane; medium and long workers take a third / half of it
   impl_->arena_bytes[0] = (size_t)(gb * (double)(1ull << 30));
-  impl_->arena_bytes[1] = (size_t)(gb * 0.5 * (double)(1ull << 30));
+  impl_->arena_bytes[1] = (size_t)(gb / 3 * (double)(1ull << 30));
+  impl_->arena_bytes[2] = (size_t)(gb / 2 * (double)(1ull << 30));
   e = getenv("PGMM_DP_MAX_JOBS");
   impl_->max_jobs = e ? (size_t)atoll(e) : (size_t)300000;
   // A batch lasts as long as its longest problem, and a worker runs one batch at a time: enough workers that a new
   // wave rarely waits for a running batch (each owns one stream per size class and one arena).
-  e = getenv("PGMM_DP_WORKERS");  // "<short>x<long>"
-  int n_short = 6, n_long = 12;
-  if (e) sscanf(e, "%dx%d", &n_short, &n_long);
-  for (int i = 0; i < std::max(1, n_short); ++i) impl_->workers.emplace_back([this] { impl_->worker(0); });
-  for (int i = 0; i < std::max(1, n_long); ++i) impl_->workers.emplace_back([this] { impl_->worker(1); });
+  e = getenv("PGMM_DP_WORKERS");  // "<short>x<medium>x<long>"
+  int n[kLanes] = {6, 8, 10};
+  if (e) sscanf(e, "%dx%dx%d", &n[0], &n[1], &n[2]);
+  for (int L = 0; L < kLanes; ++L)
+    for (int i = 0; i < std::max(1, n[L]); ++i) impl_->workers.emplace_back([this, L] { impl_->worker(L); });
   for (auto &t : impl_->workers) t.detach();
 }
 
@@ -120,30 +124,42 @@ bool DpService::enabled() {
   return on;
 }
 
-// A problem is LONG when a single CTA will spend milliseconds on it: anything but the small first-pass fills whose
-// wavefront or anti-diagonal count is large.
-static bool is_long_job(const KswJob &j) {
+// Lane of a problem, from its shape alone.  Anything but a small fill occupies one CTA for its whole duration:
+// ~0.65 ms per million cells when the band cannot bind (K5b), up to ~3 us per anti-diagonal for a band-limited end
+// extension (K5), which stops early at a z-drop or runs through all qlen + tlen anti-diagonals.
+static int lane_of(const KswJob &j) {
   const int64_t rows = (int64_t)j.qlen + j.tlen;
   const int64_t front = std::min<int64_t>(std::min(j.qlen, j.tlen), j.w < 0 ? INT32_MAX : (int64_t)j.w + 1);
-  return rows > 1500 && front > 300;
+  if (!(rows > 1500 && front > 300)) return 0;
+  const bool banded = j.w >= 0 && j.w < std::max(j.qlen, j.tlen);
+  const double worst_ms = banded ? (double)rows * 0.003 : (double)j.qlen * (double)j.tlen * 0.65e-6;
+  return worst_ms <= 8.0 ? 1 : 2;
 }
 
 void DpService::run(const std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t *d_t, const KswScoring &sc, KswBatchResult &res) {
   static const bool split = getenv("PGMM_DP_NO_SPLIT") == nullptr;
-  Request part[2];
-  for (int L = 0; L < 2; ++L) part[L].d_q = d_q, part[L].d_t = d_t, part[L].sc = sc;
+  Request part[kLanes];
+  for (int L = 0; L < kLanes; ++L) part[L].d_q = d_q, part[L].d_t = d_t, part[L].sc = sc;
   const size_t n = jobs.size();
   for (size_t i = 0; i < n; ++i) {
-    Request &r = part[split && is_long_job(jobs[i]) ? 1 : 0];
+    Request &r = part[split ? lane_of(jobs[i]) : 0];
     r.jobs.push_back(jobs[i]), r.where.push_back((int)i);
   }
+  static const bool trace = getenv("PGMM_TRACE") != nullptr;
+  timespec w0, w1;
+  clock_gettime(CLOCK_MONOTONIC, &w0);
   {
     std::unique_lock<std::mutex> g(impl_->mu);
-    for (int L = 0; L < 2; ++L) {
+    for (int L = 0; L < kLanes; ++L) {
       if (part[L].jobs.empty()) part[L].done = true;
       else impl_->lane[L].push_back(&part[L]), impl_->cv_work[L].notify_one();
     }
-    impl_->cv_done.wait(g, [&] { return part[0].done && part[1].done; });
+    impl_->cv_done.wait(g, [&] { return part[0].done && part[1].done && part[2].done; });
+  }
+  if (trace) {
+    clock_gettime(CLOCK_MONOTONIC, &w1);
+    fprintf(stderr, "[pgmm trace] dp wave: %zu short, %zu medium, %zu long jobs, waited %.1f ms\n", part[0].jobs.size(), part[1].jobs.size(),
+            part[2].jobs.size(), (w1.tv_sec - w0.tv_sec) * 1e3 + (w1.tv_nsec - w0.tv_nsec) * 1e-6);
   }
   // this round's slices of the merged waves, back in the caller's job order (copied by the round's own thread)
   res.out.assign(n, KswOut{});
@@ -152,7 +168,7 @@ void DpService::run(const std::vector<KswJob> &jobs, const uint8_t *d_q, const u
   for (int f = 0; f < 3; ++f) res.fam_ms[f] = 0.f, res.fam_cells[f] = 0, res.fam_bases[f] = 0, res.fam_launches[f] = 0;
   std::vector<const uint32_t *> src(n, nullptr);
   size_t words = 0;
-  for (int L = 0; L < 2; ++L) {
+  for (int L = 0; L < kLanes; ++L) {
     const Request &r = part[L];
     if (!r.merged) continue;
     const KswBatchResult &m = *r.merged;
