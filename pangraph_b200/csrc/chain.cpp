@@ -12,6 +12,9 @@
 #include <cassert>
 #include <cstring>
 #include <set>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 
 namespace pgmm {
 
@@ -354,18 +357,19 @@ inline int32_t link_score(const U128 &ai, const U128 &aj, float pen_gap, float p
 }
 
 // where a chain ending at z[k] stops when walked backwards (lchain.c:9-25)
-int64_t chain_stop(int32_t max_drop, const U128 *z, const int32_t *f, const int32_t *p, int32_t *t, int64_t k) {
-  int64_t i = (int64_t)z[k].y, end_i = -1, max_i = i;
+// (zx = the chain end's score, zy = its anchor)
+int64_t chain_stop(int32_t max_drop, int32_t zx, int64_t zy, const int32_t *f, const int32_t *p, int32_t *t) {
+  int64_t i = zy, end_i = -1, max_i = i;
   int32_t max_s = 0;
   if (i < 0 || t[i] != 0) return i;
   do {
     t[i] = 2;
     end_i = i = p[i];
-    const int32_t s = i < 0 ? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+    const int32_t s = i < 0 ? zx : zx - f[i];
     if (s > max_s) max_s = s, max_i = i;
     else if (max_s - s > max_drop) break;
   } while (i >= 0 && t[i] == 0);
-  for (i = (int64_t)z[k].y; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
+  for (i = zy; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
   return max_i;
 }
 
@@ -500,28 +504,51 @@ void chain_backtrack(const ChainParams &cp, std::vector<U128> &a, const int32_t 
   const int64_t n = (int64_t)a.size();
   if (n == 0) return;
   const int bw = cp.bw;
+  static const bool tr__ = getenv("PGMM_TRACE_BT") != nullptr;
+  const auto now__ = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+  double t0__ = now__(), t1__;
+#define BT_MARK(what) if (tr__) { t1__ = now__(); fprintf(stderr, "[bt] %-10s %.1f ms\n", what, t1__ - t0__); t0__ = t1__; }
   // ---- backtrack (lchain.c:27-76): best end points first, each anchor used once ----
   const int32_t min_sc = cp.min_sc, min_cnt = cp.min_cnt, max_drop = bw;
-  std::vector<U128> z;
-  for (int64_t i = 0; i < n; ++i)
-    if (f[i] >= min_sc) z.push_back(U128{(uint64_t)(int64_t)f[i], (uint64_t)i});
+  // chain ends as score << 32 | anchor, sorted by score like the reference's (score, anchor) pairs: the unstable radix
+  // sort's moves depend on the key digits only, so packing the pair into 8 bytes leaves the permutation unchanged
+  std::vector<uint64_t> z;
+  {
+    int64_t n_z = 0;
+    for (int64_t i = 0; i < n; ++i) n_z += f[i] >= min_sc;
+    z.resize((size_t)n_z);
+    uint64_t *zp = z.data();
+    for (int64_t i = 0; i < n; ++i)
+      if (f[i] >= min_sc) *zp++ = (uint64_t)(uint32_t)f[i] << 32 | (uint64_t)i;
+  }
   if (z.empty()) {
     a.clear();
     return;
   }
-  flag_sort_128x(z.data(), z.data() + z.size());
+  BT_MARK("z build");
+  if (min_sc >= 0) flag_sort(z.data(), z.data() + z.size(), [](uint64_t v) { return v >> 32; });
+  else {  // negative scores sign-extend into the upper key bytes (lchain.c:41): sort the reference's 16-byte pairs, then pack
+    std::vector<U128> zz(z.size());
+    for (size_t k = 0; k < z.size(); ++k) zz[k] = U128{(uint64_t)(int64_t)(int32_t)(z[k] >> 32), (uint64_t)(uint32_t)z[k]};
+    flag_sort_128x(zz.data(), zz.data() + zz.size());
+    for (size_t k = 0; k < z.size(); ++k) z[k] = (uint64_t)(uint32_t)(int32_t)zz[k].x << 32 | zz[k].y;
+  }
+  BT_MARK("z sort");
   std::fill(t, t + n, 0);
   int64_t n_v = 0;
   for (int64_t k = (int64_t)z.size() - 1; k >= 0; --k) {
-    if (t[z[k].y] != 0) continue;
+    const int32_t zx = (int32_t)(z[k] >> 32);
+    const int64_t zy = (int64_t)(uint32_t)z[k];
+    if (t[zy] != 0) continue;
     const int64_t n_v0 = n_v;
-    const int64_t end_i = chain_stop(max_drop, z.data(), f, p, t, k);
+    const int64_t end_i = chain_stop(max_drop, zx, zy, f, p, t);
     int64_t i;
-    for (i = (int64_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = (int32_t)i, t[i] = 1;
-    const int32_t sc = i < 0 ? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+    for (i = zy; i != end_i; i = p[i]) v[n_v++] = (int32_t)i, t[i] = 1;
+    const int32_t sc = i < 0 ? zx : zx - f[i];
     if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u.push_back((uint64_t)sc << 32 | (uint64_t)(n_v - n_v0));
     else n_v = n_v0;
   }
+  BT_MARK("walk");
   if (u.empty()) {
     a.clear();
     return;
@@ -547,6 +574,7 @@ void chain_backtrack(const ChainParams &cp, std::vector<U128> &a, const int32_t 
     k += cnt;
   }
   u.swap(u2);
+  BT_MARK("compact");
 }
 
 void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t> &u) {

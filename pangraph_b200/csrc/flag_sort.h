@@ -29,7 +29,21 @@ void flag_sort_pass(T *beg, T *end, int shift, Key key) {
   constexpr ptrdiff_t kSmall = 64;
   T *head[kDigits], *tail[kDigits];
   size_t count[kDigits] = {0};
-  for (T *i = beg; i != end; ++i) ++count[(key(*i) >> shift) & 0xff];
+  uint64_t all_or = 0, all_and = ~0ull;
+  for (T *i = beg; i != end; ++i) {
+    const uint64_t k = key(*i);
+    ++count[(k >> shift) & 0xff], all_or |= k, all_and &= k;
+  }
+  // A digit every key of the range shares puts the whole range into one bucket: the reference's pass moves nothing and
+  // recurses on the same range with the next digit.  Such passes (the zero bytes above a chain score, the bytes between
+  // the strand / target id and the position of an anchor) are skipped in one step.
+  if (const uint64_t varies = all_or ^ all_and; ((varies >> shift) & 0xff) == 0) {
+    int s2 = shift;
+    while (s2 > 0 && ((varies >> s2) & 0xff) == 0) s2 -= 8;
+    if (s2 < 0) s2 = 0;
+    if (((varies >> s2) & 0xff) != 0) flag_sort_pass(beg, end, s2, key);
+    return;
+  }
   {
     T *p = beg;
     for (int d = 0; d < kDigits; ++d) head[d] = p, p += count[d], tail[d] = p;

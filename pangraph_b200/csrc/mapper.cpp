@@ -79,11 +79,21 @@ void encode_queries(QueryBatch &qb, const TargetSet &ts, int n_threads) {
       while (vstart[i + 1] <= p) ++i;
       const uint64_t L = (uint64_t)qb.lens[i], j0 = p - vstart[i], j1 = std::min(L, hi - vstart[i]);
       uint8_t *f = qb.codes.data() + qb.base[i], *r = f + L;
-      if (qb.from_targets) {
+      if (qb.from_targets) {  // codes are there already: copy, and reverse-complement eight bases at a time
         const uint8_t *s = ts.codes.data() + ts.offs[i];
-        for (uint64_t j = j0; j < j1; ++j) {
+        memcpy(f + j0, s + j0, (size_t)(j1 - j0));
+        uint64_t j = j0;
+        for (; j + 8 <= j1; j += 8) {
+          uint64_t x;
+          memcpy(&x, s + j, 8);
+          x = __builtin_bswap64(x);                                // base j lands in the last byte
+          const uint64_t amb = (x & 0x0404040404040404ull) >> 2;   // 1 where the code is 4
+          x = (x ^ 0x0303030303030303ull) ^ (amb * 3);             // 0..3 -> 3 - c, 4 stays 4
+          memcpy(r + (L - 8 - j), &x, 8);
+        }
+        for (; j < j1; ++j) {
           const uint8_t c = s[j];
-          f[j] = c, r[L - 1 - j] = c < 4 ? 3 - c : 4;
+          r[L - 1 - j] = c < 4 ? 3 - c : 4;
         }
       } else {
         const uint8_t *s = (const uint8_t *)qb.seqs[i];
@@ -1297,7 +1307,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     cpu0 = c;
   };
   double t0 = now(), t1;
-  encode_queries(qb, ts, n_threads);
+  encode_queries(qb, ts, std::min(n_threads, 4));
   cpu_mark("encode");
   t1 = now(), be.stats.t_encode += t1 - t0, t0 = t1;
   be.begin_batch(ts, qb);

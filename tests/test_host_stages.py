@@ -56,6 +56,16 @@ def test_chain_rmq_matches_reference(ref, hl):
         assert np.array_equal(mine[:len(want_a)], want_a)
         if n >= 2000:
             assert len(want_u) > 0
+    # a negative score threshold: chain ends with negative scores sort above all others (sign-extended keys, lchain.c:41)
+    a = chainref.synth_anchors(rng, 3000, noise=0.5)
+    chainref.ref_sort(ref, a)
+    want_u, want_a = chainref.ref_chain(ref, a, 10000, 1000, 1000, 25, 100000, 1, -50, pen_gap, 0.0)
+    mine = a.copy()
+    u = np.zeros(len(a) + 1, dtype=np.uint64)
+    n_a_out = C.c_int64(0)
+    got_n_u = hl.pgmm_test_chain_rmq(C.c_void_p(mine.ctypes.data), C.c_int64(len(a)), 10000, 1000, 1000, 25, 100000, 1, -50,
+                                     C.c_float(pen_gap), C.c_float(0.0), C.c_void_p(u.ctypes.data), C.byref(n_a_out))
+    assert got_n_u == len(want_u) and np.array_equal(u[:got_n_u], want_u) and np.array_equal(mine[:len(want_a)], want_a)
 
 
 def test_ll_local_score_matches_reference(ref, hl):
