@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "chain_fill.h"
+#include "chain_service.h"
 #include "dp_service.h"
 #include "ksw_extd2.h"
 #include "mapper.h"
@@ -181,7 +182,11 @@ struct CudaBackend : Backend {
     cx.seeder.collect(ix.didx, cx.qset, q_rank, opt, out, cx.stream);
     t_seed += now_ms() - t0;
   }
-  void chain_fill(const ChainParams &cp, std::vector<ChainFillJob> &jobs) override { cx.chainer.run(cp, jobs, cx.stream, &stats.chain); }
+  std::shared_ptr<std::vector<int32_t>> chain_keep;  // f / p / v of this round when they came from the chain service
+  void chain_fill(const ChainParams &cp, std::vector<ChainFillJob> &jobs) override {
+    if (ChainService::enabled()) ChainService::get().run(cp, jobs, chain_keep, &stats.chain);
+    else cx.chainer.run(cp, jobs, cx.stream, &stats.chain);
+  }
   void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) override {
     if (cx.ksw) cx.ksw->run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res, cx.stream);
     else DpService::get().run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res);

@@ -115,9 +115,10 @@ def test_many_short_blocks():
     assert n > 50
 
 
-def test_rounds_without_the_dp_service(ref):
-    """PGMM_DP_SERVICE=0 keeps every round on its own DP engine (one arena and one set of streams per context): the same
-    hits as through the cross-round service, which every other test in this file uses."""
+def test_rounds_without_the_dp_service_and_with_the_chain_service(ref):
+    """PGMM_DP_SERVICE=0 keeps every round on its own DP engine (one arena and one set of streams per context) and
+    PGMM_CHAIN_SERVICE=1 sends the chaining fill through the cross-round chain service: the same hits as with the
+    defaults (DP service on, chain fill on the round's own stream), which every other test in this file uses."""
     import subprocess
     import sys
     code = (
@@ -130,6 +131,6 @@ def test_rounds_without_the_dp_service(ref):
         "assert got == want and sum(len(g) for g in got) > 0; print('ok')"
     )
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PGMM_DP_SERVICE="0")
+    env = dict(os.environ, PGMM_DP_SERVICE="0", PGMM_CHAIN_SERVICE="1")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
