@@ -575,6 +575,7 @@ void chain_backtrack(const ChainParams &cp, std::vector<U128> &a, const int32_t 
   }
   u.swap(u2);
   BT_MARK("compact");
+#undef BT_MARK
 }
 
 void chain_rmq(const ChainParams &cp, std::vector<U128> &a, std::vector<uint64_t> &u) {
