@@ -209,3 +209,27 @@ extern "C" __attribute__((visibility("default"))) int pgmm_test_ll_score(int qle
                                                                          const int8_t *mat, int gapo, int gape, int *qe, int *te) {
   return ll_local_score(qlen, q, tlen, t, mat, gapo, gape, qe, te);
 }
+
+// encode_queries in its two modes: from ASCII, and from the resident target codes (pgmm_map_self); out gets both results
+// back to back (2 * total bases each).  Returns 0 when they agree.
+extern "C" __attribute__((visibility("default"))) int pgmm_test_encode_modes(int n, const char *const *seqs, const int *lens, int n_threads) {
+  TargetSet ts;
+  uint64_t sum = 0;
+  for (int i = 0; i < n; ++i) {
+    ts.lens.push_back((uint32_t)lens[i]), ts.offs.push_back(sum), ts.names.push_back("");
+    sum += (uint64_t)lens[i];
+  }
+  ts.codes.resize(sum + 64);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < lens[i]; ++j) ts.codes[ts.offs[i] + j] = kNt4[(uint8_t)seqs[i][j]];
+  QueryBatch a, b;
+  a.n = b.n = n;
+  a.seqs.assign(seqs, seqs + n), b.seqs.assign(n, nullptr);
+  a.lens.assign(lens, lens + n), b.lens.assign(lens, lens + n);
+  a.names.assign(n, nullptr), b.names.assign(n, nullptr);
+  b.from_targets = true;
+  encode_queries(a, ts, n_threads);
+  encode_queries(b, ts, n_threads);
+  if (a.base != b.base) return 1;
+  return memcmp(a.codes.data(), b.codes.data(), 2 * sum) == 0 ? 0 : 2;
+}

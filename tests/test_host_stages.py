@@ -91,3 +91,17 @@ def test_ll_local_score_matches_reference(ref, hl):
         got = hl.pgmm_test_ll_score(ql, C.c_void_p(q.ctypes.data), tl, C.c_void_p(t.ctypes.data), C.c_void_p(mat.ctypes.data), 16, 2,
                                     C.byref(qe2), C.byref(te2))
         assert (got, qe2.value, te2.value) == (want, qe.value, te.value), (i, ql, tl)
+
+
+def test_resident_queries_are_encoded_like_ascii_queries(hl):
+    """encode_queries builds the forward and reverse-complement codes of the queries either from ASCII (kNt4) or, for
+    pgmm_map_self, from the resident target codes eight bases at a time: same bytes, ambiguous bases and odd lengths included."""
+    rng = np.random.default_rng(12)
+    seqs = []
+    for n in (0, 1, 7, 8, 9, 63, 64, 1000, 4097, 250_001):
+        s = np.frombuffer(b"ACGTNacgtnRYK", dtype=np.uint8)[rng.integers(0, 13, size=n)]
+        seqs.append(s.tobytes())
+    arr = (C.c_char_p * len(seqs))(*seqs)
+    lens = (C.c_int * len(seqs))(*[len(s) for s in seqs])
+    for threads in (1, 4):
+        assert hl.pgmm_test_encode_modes(len(seqs), arr, lens, threads) == 0
