@@ -447,3 +447,123 @@ long orc_sketch(const char *str, int len, int w, int k, uint32_t rid, uint64_t *
 	if (min_x != MAXV) ORC_EMIT(min_x, min_y);
 	return n;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * orc_chain_fill -- the score fill of mg_lchain_rmq (C/lchain.c:276-358) WITHOUT its two balanced trees.
+ *
+ * What the trees hold at anchor i is a contiguous window of the sorted anchor array: [st, i0) for the range-minimum
+ * tree and [st_in, i0) for the near-neighbourhood tree (anchors enter group by group when the target position changes,
+ * :280-293, and leave from the front, :295-312).  So the fill can be stated with plain scans over those windows:
+ *   - the RMQ (:313-316) is "smallest priority among window members whose query position lies in (y - max_dist, y], at y
+ *     itself only the very first anchor (closed upper key (y, 0))";
+ *   - the walk (:319-348) visits the members of the inner window with query position in [y - max_dist_inner, y - 1] in
+ *     descending (query position, index) order with the reference's skip counter and t[] marks.
+ * The one thing a scan cannot know is which of several EQUAL priorities the reference's tree would return (that depends
+ * on its rotation history): such an anchor is reported in *n_tied and the caller must not compare beyond it.
+ * f, p (-1 = none), v as in the reference; t is scratch of n int32.  undet[i] (optional) is set for every anchor from a
+ * non-unique RMQ minimum to the end of its independent segment (the trees are empty wherever the target / strand changes
+ * or two neighbours are more than max_dist apart, so nothing carries over).  Returns the index of the first such anchor,
+ * or n when there was none.
+ * ------------------------------------------------------------------------------------------------------------------ */
+static float orc_log2(float x) /* C/mmpriv.h:118-126 */
+{
+	union { float f; uint32_t i; } z = { x };
+	float log_2 = ((z.i >> 23) & 255) - 128;
+	z.i &= ~(255 << 23);
+	z.i += 127 << 23;
+	log_2 += (-0.34484843f * z.f + 2.02466578f) * z.f - 0.67487759f;
+	return log_2;
+}
+
+static int32_t orc_link(uint64_t xi, uint64_t yi, uint64_t xj, uint64_t yj, float pen_gap, float pen_skip, int *exact, int32_t *width)
+{ /* C/lchain.c:232-248 */
+	int32_t dq = (int32_t)yi - (int32_t)yj, dr = (int32_t)(xi - xj), dd, dg, q_span, sc;
+	*width = dd = dr > dq ? dr - dq : dq - dr;
+	dg = dr < dq ? dr : dq;
+	q_span = yj >> 32 & 0xff;
+	sc = q_span < dg ? q_span : dg;
+	if (exact) *exact = (dd == 0 && dg <= q_span);
+	if (dd || dq > q_span) {
+		float lin_pen = pen_gap * (float)dd + pen_skip * (float)dg;
+		float log_pen = dd >= 1 ? orc_log2(dd + 1) : 0.0f;
+		sc -= (int)(lin_pen + .5f * log_pen);
+	}
+	return sc;
+}
+
+typedef struct { int32_t y; int64_t i; } orc_key_t;
+static int orc_key_desc(const void *a, const void *b)
+{
+	const orc_key_t *p = (const orc_key_t *)a, *q = (const orc_key_t *)b;
+	if (p->y != q->y) return p->y > q->y ? -1 : 1;
+	return p->i > q->i ? -1 : p->i < q->i ? 1 : 0;
+}
+
+int64_t orc_chain_fill(int64_t n, const uint64_t *xy, int max_dist, int max_dist_inner, int bw, int max_skip, int cap,
+                       float pen_gap, float pen_skip, int32_t *f, int32_t *p, int32_t *v, int32_t *t, uint8_t *undet)
+{
+	int64_t i, j, i0 = 0, st = 0, st_in = 0, first_tie = n;
+	int tainted = 0;
+	orc_key_t *cand = (orc_key_t *)malloc(sizeof(orc_key_t) * (size_t)(n > 0 ? n : 1));
+	if (max_dist < bw) max_dist = bw; /* :262-263 */
+	if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
+	for (i = 0; i < n; ++i) t[i] = 0;
+	for (i = 0; i < n; ++i) {
+		const uint64_t xi = xy[2 * i], yi = xy[2 * i + 1];
+		const int32_t y = (int32_t)yi, q_span = yi >> 32 & 0xff;
+		int32_t max_f = q_span;
+		int64_t max_j = -1, best = -1, n_best = 0;
+		double best_pri = 0;
+		if (i0 < i && xy[2 * i0] != xi) i0 = i; /* :280-293: the previous group becomes visible */
+		/* :295-312, both windows: too far behind, other target / strand, or more members than the cap */
+		while (st < i && (xi >> 32 != xy[2 * st] >> 32 || xi > xy[2 * st] + (uint64_t)max_dist || (i0 > st ? i0 - st : 0) > cap)) ++st;
+		if (max_dist_inner > 0)
+			while (st_in < i && (xi >> 32 != xy[2 * st_in] >> 32 || xi > xy[2 * st_in] + (uint64_t)max_dist_inner || (i0 > st_in ? i0 - st_in : 0) > cap)) ++st_in;
+		/* :313-316 */
+		for (j = st; j < i0; ++j) {
+			const int32_t yj = (int32_t)xy[2 * j + 1];
+			double pri;
+			if (!(yj > y - max_dist && (yj < y || (yj == y && j == 0)))) continue;
+			pri = -(f[j] + 0.5 * pen_gap * ((int32_t)xy[2 * j] + (int32_t)xy[2 * j + 1])); /* :285 */
+			if (best < 0 || pri < best_pri) best = j, best_pri = pri, n_best = 1;
+			else if (pri == best_pri) ++n_best;
+		}
+		if (i > 0 && (xi >> 32 != xy[2 * (i - 1)] >> 32 || xi > xy[2 * (i - 1)] + (uint64_t)max_dist)) tainted = 0; /* a new segment */
+		if (n_best > 1) {
+			tainted = 1;
+			if (first_tie == n) first_tie = i;
+		}
+		if (undet) undet[i] = (uint8_t)tainted;
+		if (best >= 0) {
+			int exact;
+			int32_t width, n_skip = 0;
+			int32_t sc = f[best] + orc_link(xi, yi, xy[2 * best], xy[2 * best + 1], pen_gap, pen_skip, &exact, &width);
+			if (width <= bw && sc > max_f) max_f = sc, max_j = best;
+			if (!exact && max_dist_inner > 0 && i0 > st_in && y > 0) { /* :319-348 */
+				int64_t m = 0, k;
+				for (j = st_in; j < i0; ++j) {
+					const int32_t yj = (int32_t)xy[2 * j + 1];
+					if (yj <= y - 1 && yj >= y - max_dist_inner) cand[m].y = yj, cand[m].i = j, ++m;
+				}
+				qsort(cand, (size_t)m, sizeof(orc_key_t), orc_key_desc);
+				for (k = 0; k < m; ++k) {
+					j = cand[k].i;
+					sc = f[j] + orc_link(xi, yi, xy[2 * j], xy[2 * j + 1], pen_gap, pen_skip, 0, &width);
+					if (width <= bw) {
+						if (sc > max_f) {
+							max_f = sc, max_j = j;
+							if (n_skip > 0) --n_skip;
+						} else if (t[j] == (int32_t)i) {
+							if (++n_skip > max_skip) break;
+						}
+						if (p[j] >= 0) t[p[j]] = (int32_t)i;
+					}
+				}
+			}
+		}
+		f[i] = max_f, p[i] = (int32_t)max_j;
+		v[i] = max_j >= 0 && v[max_j] > max_f ? v[max_j] : max_f; /* :354 */
+	}
+	free(cand);
+	return first_tie;
+}

@@ -233,3 +233,14 @@ extern "C" __attribute__((visibility("default"))) int pgmm_test_encode_modes(int
   if (a.base != b.base) return 1;
   return memcmp(a.codes.data(), b.codes.data(), 2 * sum) == 0 ? 0 : 2;
 }
+
+// the product's host arbiter on every segment: f, p, v (n int32 each) of sorted anchors
+extern "C" __attribute__((visibility("default"))) void pgmm_test_chain_fill_host(const uint64_t *xy, int64_t n, int max_dist, int max_dist_inner,
+                                                                                 int bw, int max_skip, int cap, float pen_gap, float pen_skip,
+                                                                                 int32_t *f, int32_t *p, int32_t *v) {
+  ChainParams cp{max_dist, max_dist_inner, bw, max_skip, cap, 0, 0, pen_gap, pen_skip};
+  std::vector<ChainSeg> segs;
+  chain_find_segments(cp, (const U128 *)xy, n, segs);
+  std::vector<int32_t> t((size_t)n + 1, 0);
+  for (const ChainSeg &sg : segs) chain_fill_host(cp, (const U128 *)xy, n, sg.start, sg.end, f, p, v, t.data());
+}

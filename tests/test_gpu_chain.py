@@ -71,3 +71,33 @@ def test_chain_fixture_without_the_reference_library():
         u, kept, fpv, seg = abi.chain_rmq(g[name + "_in"], int(p[0]), int(p[1]), int(p[2]), int(p[3]), int(p[4]), int(p[5]), int(p[6]),
                                           np.float32(p[7]), float(p[8]))
         assert np.array_equal(u, g[name + "_u"]) and np.array_equal(kept, g[name + "_kept"]), name
+
+
+def test_fill_arrays_against_the_tree_free_oracle():
+    """f, p, v of every anchor as K4 fills them (segments it hands back are filled by the host arbiter) against
+    oracle/pgmm_oracle.c::orc_chain_fill, wherever the oracle's answer is determined (unique RMQ minima)."""
+    import ctypes as C
+
+    import kswref
+    from pangraph_b200 import abi
+    orc = kswref.load_oracle()
+    orc.orc_chain_fill.restype = C.c_int64
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "golden_chain.npz"))
+    rng = np.random.default_rng(99)
+    sets = [g["noisy_in"], g["colinear_in"], g["repeat_array_in"]]
+    big = chainref.colinear_anchors(rng, 60000)
+    sets.append(big[np.argsort(big[:, 0], kind="stable")])
+    checked = 0
+    for a in sets:
+        a = np.ascontiguousarray(a)
+        n = len(a)
+        u, kept, fpv, seg = abi.chain_rmq(a, 10000, 1000, 1000, 25, 100000, 3, 40, PEN_GAP, 0.0)
+        f, p, v, t = (np.zeros(n + 1, dtype=np.int32) for _ in range(4))
+        undet = np.zeros(n + 1, dtype=np.uint8)
+        orc.orc_chain_fill(C.c_int64(n), C.c_void_p(a.ctypes.data), 10000, 1000, 1000, 25, 100000, C.c_float(PEN_GAP), C.c_float(0.0),
+                           C.c_void_p(f.ctypes.data), C.c_void_p(p.ctypes.data), C.c_void_p(v.ctypes.data), C.c_void_p(t.ctypes.data),
+                           C.c_void_p(undet.ctypes.data))
+        ok = undet[:n] == 0
+        assert np.array_equal(fpv[0][ok], f[:n][ok]) and np.array_equal(fpv[1][ok], p[:n][ok]) and np.array_equal(fpv[2][ok], v[:n][ok])
+        checked += int(ok.sum())
+    assert checked > 60000
