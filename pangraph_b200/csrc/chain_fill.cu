@@ -436,6 +436,8 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
 void trace_attach_chain(PgmmCtaTraceRec *buf, unsigned long long *cnt, unsigned long long cap) { trace::attach(buf, cnt, cap); }
 
 constexpr size_t kFillSmem = (size_t)ChainEngine::kRing * (8 + 4 * 4) + (size_t)ChainEngine::kInnerCap * 8 + 32 * 32;
+static_assert(kFillSmem <= 227 * 1024, "the ring must fit the shared memory of one SM");
+static_assert((ChainEngine::kRing & (ChainEngine::kRing - 1)) == 0, "ring slots are addressed with a mask");
 
 ChainEngine::ChainEngine() {
   static const bool once = [] {

@@ -13,7 +13,10 @@ namespace pgmm {
 class ChainEngine {
  public:
   // limits beyond which a segment is handed back to the host (chain_fill_host)
-  static constexpr int kRing = 2048;        // anchors between the oldest window member and the current one
+  // anchors between the oldest window member and the current one.  Synthetic 1 %-divergent genomes need ~800 (10 kbp of
+  // target at one anchor per ~13 bp); a real E. coli pair reaches 2835 in its repeats (18 % of its anchors sit in segments
+  // that overflow a ring of 2048; measured with the oracle on the CPU), hence 4096 (105 KB of shared memory per warp).
+  static constexpr int kRing = 4096;
   static constexpr int kInnerCap = 1024;    // candidates of one near-neighbourhood walk
   enum Redo : uint8_t { DONE = 0, TIE = 1, WINDOW = 2, INNER = 3 };
 

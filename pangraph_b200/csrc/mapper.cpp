@@ -1340,6 +1340,14 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     ChainFillJob &cj = cjobs[i];
     cj.a = q.a.data(), cj.n = (int64_t)q.a.size();
     chain_find_segments(cp, cj.a, cj.n, cj.segs);
+    if (const char *dump = getenv("PGMM_DUMP_ANCHORS")) {  // profiling aid: sorted anchors of every query, 16 bytes each
+      char path[4096];
+      snprintf(path, sizeof(path), "%s.%d", dump, i);
+      if (FILE *fp = fopen(path, "wb")) {
+        fwrite(q.a.data(), sizeof(U128), q.a.size(), fp);
+        fclose(fp);
+      }
+    }
   });
   const double tc0 = now();
   be.stats.t_chain_sort += tc0 - t0;
