@@ -74,3 +74,11 @@ def test_reference_bundled_plasmids(ref, hl):
     assert check(hl, [s for _, s in recs], [str(i) for i in range(len(recs))]) == 18
     recs = read_fa(os.path.join(REF_DATA, "packages", "pypangraph", "tests", "data", "plasmids.fa.gz"), limit=6)
     assert check(hl, [s for _, s in recs], [str(i * 7919) for i in range(len(recs))]) > 100
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DATA, "data", "ecoli.fa.gz")), reason="reference data not mounted")
+def test_reference_bundled_ecoli_pair(ref, hl):
+    """BASELINE config 2 at full size on the CPU: the first two genomes of data/ecoli.fa.gz (4.6 + 4.8 Mbp, 494 k anchors,
+    ~36 k DP problems, inversion rescues, z-drop splits): all 2002 hits identical to the reference's."""
+    recs = read_fa(os.path.join(REF_DATA, "data", "ecoli.fa.gz"), limit=2)
+    assert check(hl, [s for _, s in recs], ["0", "1"], threads=8) == 2002
