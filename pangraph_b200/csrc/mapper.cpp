@@ -174,7 +174,8 @@ struct Fill {
   int32_t rs, qs, re, qe;
   int bw1;
   DpCall pass1, pass2;
-  int code = 0;  // mm_test_zdrop verdict on pass 1
+  int code = 0;        // mm_test_zdrop verdict on pass 1
+  bool spec2 = false;  // the exact second pass was queued together with the first one
 };
 
 struct Region {
@@ -216,7 +217,10 @@ struct Mapper {
   const QueryBatch &qb;
   const mm_mapopt_t &opt;
   int8_t mat[25];
+  // fills at least this long get their exact second pass queued with the first one (0 = never; PGMM_SPEC_FILL_LEN)
+  int spec_fill_len = 2000;
   Mapper(const TargetSet &t, const QueryBatch &q, const mm_mapopt_t &o) : ts(t), qb(q), opt(o) {
+    if (const char *e = getenv("PGMM_SPEC_FILL_LEN")) spec_fill_len = atoi(e);
     // ksw_gen_simple_mat(5, mat, a, b, sc_ambi), align.c:9-22
     const int a = opt.a < 0 ? -opt.a : opt.a, b = opt.b > 0 ? -opt.b : opt.b, amb = opt.sc_ambi > 0 ? -opt.sc_ambi : opt.sc_ambi;
     for (int i = 0; i < 4; ++i) {
@@ -713,6 +717,15 @@ struct Mapper {
       }
       for (Fill &f : R.fills)
         submit(q, f.pass1, rev, f.qs, f.qe - f.qs, rid, f.rs, f.re - f.rs, f.bw1, opt.zdrop, -1, KSW_APPROX_MAX);
+      // A long fill spans a big indel or an inversion and all but always fails mm_test_zdrop: its exact second pass
+      // (align.c:757-759) is queued together with the first one instead of one wave later -- speculative like the end
+      // extensions, and only when both z-drop thresholds agree, so that the pass does not depend on the verdict.
+      if (opt.zdrop == opt.zdrop_inv && spec_fill_len > 0)
+        for (Fill &f : R.fills)
+          if (std::max(f.qe - f.qs, f.re - f.rs) >= spec_fill_len) {
+            submit(q, f.pass2, rev, f.qs, f.qe - f.qs, rid, f.rs, f.re - f.rs, f.bw1, opt.zdrop, -1, 0);
+            f.spec2 = true;
+          }
     }
     if (qe < qe0 && re < re0) {  // right extension; speculative: unused if a fill z-drops (align.c:789-805)
       R.has_right = true;
@@ -776,22 +789,25 @@ struct Mapper {
   }
 
   // after the first wave: collect results, test every fill, queue the exact second passes (align.c:757-759)
-  void after_pass1(QCtx &q, Region &R, const std::shared_ptr<const KswBatchResult> &res) const {
+  // returns whether a second wave is needed for this hit
+  bool after_pass1(QCtx &q, Region &R, const std::shared_ptr<const KswBatchResult> &res) const {
     if (R.has_left) collect(q, R.left, res);
     if (R.has_right) collect(q, R.right, res);
     bool any = false;
+    for (Fill &f : R.fills)
+      if (f.spec2) collect(q, f.pass2, res);  // all of them: their slots belong to this wave
     for (Fill &f : R.fills) {
       collect(q, f.pass1, res);
       if (f.pass1.ez.zd_max < 0) zdrop_scan(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.cigar, f.pass1.ez.n_cigar, f.pass1.ez);
       f.code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.ez);
-      if (f.code != 0) {
+      if (f.code != 0 && !f.spec2) {
         submit(q, f.pass2, R.rev, f.qs, f.qe - f.qs, R.rid, f.rs, f.re - f.rs, f.bw1, f.code == 2 ? opt.zdrop_inv : opt.zdrop, -1, 0);
-        any = true;
+        any |= f.pass2.job >= 0;
       }
       if ((f.code ? f.pass2.job < 0 && f.pass2.ez.zdropped : f.pass1.ez.zdropped)) break;  // later fills can never be used
     }
-    (void)any;
-    R.state = Region::WAIT2;  // finishing happens in one place, after the (possibly empty) second wave
+    R.state = Region::WAIT2;  // finishing happens in one place: right away when nothing is pending, else after the second wave
+    return any;
   }
 
   // splits a hit at its n-th anchor (hit.c:106-123)
@@ -1396,6 +1412,9 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
 
   t1 = now(), be.stats.t_chain += t1 - t0, t0 = t1;
   // ---- DP waves ----
+  // a hit with nothing pending after its first wave is finished in that wave instead of waiting for the next one
+  // (hits only depend on their own DP results and on the finished hit in front of them); PGMM_EARLY_FINISH=0 disables
+  const bool early_finish = getenv("PGMM_EARLY_FINISH") == nullptr || atoi(getenv("PGMM_EARLY_FINISH")) != 0;
   KswScoring sc;
   sc.sc_mch = (int8_t)(opt.a < 0 ? -opt.a : opt.a), sc.sc_mis = (int8_t)(opt.b > 0 ? -opt.b : opt.b), sc.sc_ambi = (int8_t)opt.sc_ambi;
   sc.q = (int8_t)opt.q, sc.e = (int8_t)opt.e, sc.q2 = (int8_t)opt.q2, sc.e2 = (int8_t)opt.e2;
@@ -1419,6 +1438,15 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     if (!any_waiting) break;
     t1 = now(), be.stats.t_stitch += t1 - t0, t0 = t1;
     cpu_mark("  wave: collect jobs");
+    if (trace_cpu) {
+      int64_t big = 0, n_big = 0;
+      for (const KswJob &j : jobs) {
+        big = std::max<int64_t>(big, (int64_t)j.qlen * j.tlen);
+        n_big += (int64_t)j.qlen + j.tlen > 1500;
+      }
+      fprintf(stderr, "[pgmm trace]   wave: %zu jobs, %lld with more than 1500 anti-diagonals, largest %lld cells\n", jobs.size(), (long long)n_big,
+              (long long)big);
+    }
     if (!jobs.empty()) {
       be.run_dp(jobs, sc, res);
       cpu_mark("  wave: run_dp (host side)");
@@ -1438,11 +1466,13 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
       for (size_t k = 0; k < q.regs.size(); ++k) {
         Region &R = *q.regs[k];
         switch (R.state) {
-          case Region::WAIT1:
+          case Region::WAIT1: {
             s0 = now();
-            M.after_pass1(q, R, res_sp);
+            const bool second_wave = M.after_pass1(q, R, res_sp);
             tr_p1 += now() - s0;
-            break;
+            if (second_wave || !early_finish) break;
+          }
+          // fall through: nothing is pending for this hit, it is finished in the same wave
           case Region::WAIT2: {
             s0 = now();
             mm_reg1_t r2 = M.finish_region(q, R, res_sp);
@@ -1454,9 +1484,9 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
               q.regs.insert(q.regs.begin() + k + 1, std::move(N));
             }
             // inversion rescue between the previous hit and this one (align.c:1005-1010)
-            if (k > 0 && R.r.split_inv && !(opt.flag & MM_F_NO_INV)) {
+            if (k > 0 && q.regs[k]->r.split_inv && !(opt.flag & MM_F_NO_INV)) {
               auto I = std::make_unique<Region>();
-              if (M.plan_inversion(q, *q.regs[k - 1], R, *I)) {
+              if (M.plan_inversion(q, *q.regs[k - 1], *q.regs[k], *I)) {
                 I->state = Region::WAIT_INV;
                 q.regs.insert(q.regs.begin() + k + 1, std::move(I));
                 ++k;  // the inversion slot sits between this hit and its remainder

@@ -82,3 +82,16 @@ def test_reference_bundled_ecoli_pair(ref, hl):
     ~36 k DP problems, inversion rescues, z-drop splits): all 2002 hits identical to the reference's."""
     recs = read_fa(os.path.join(REF_DATA, "data", "ecoli.fa.gz"), limit=2)
     assert check(hl, [s for _, s in recs], ["0", "1"], threads=8) == 2002
+
+
+def test_wave_scheduler_variants(ref, hl, monkeypatch):
+    """The two latency measures of the DP scheduler -- the exact second pass of a long fill queued with its first pass,
+    hits finished in the wave after which nothing is pending for them -- change when work is done, not what comes out:
+    the same hits with both on (default, every other test), both off, and with every fill speculated."""
+    from pangraph_b200 import synth
+    anc = synth.ancestor(150_000, 5)
+    gs = [synth.mutate(anc, 900 + i, n_rearr=10, len_lo=500, len_hi=12000).tobytes() for i in range(3)]
+    for early, spec in (("0", "0"), ("1", "0"), ("0", "1"), ("1", "1")):
+        monkeypatch.setenv("PGMM_EARLY_FINISH", early)
+        monkeypatch.setenv("PGMM_SPEC_FILL_LEN", spec)
+        assert check(hl, gs, ["0", "1", "2"], threads=2) > 10
