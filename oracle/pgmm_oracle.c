@@ -4,7 +4,7 @@
  * and bench.py's cpu_baseline leg may load it.  Nothing under pangraph_b200/ links or calls it, and it must never be
  * the thing that is measured or shipped.
  *
- * Parity status: PINNED.  Every function here is checked (tests/test_oracle_vs_ref.py) against the unmodified
+ * Parity status: PINNED.  Every function here is checked (tests/test_oracle_ksw.py, test_oracle_sketch.py, test_oracle_chain.py) against the unmodified
  * vendored minimap2 C of the reference, compiled from /root/reference by oracle/Makefile into
  * oracle/_ref/libmm2ref.so, which itself reproduces the reference's only boundary golden vector
  * (packages/pangraph/src/align/minimap2_lib/align_with_minimap2_lib.rs:135-204).
