@@ -13,7 +13,8 @@ stream each; their DP waves are merged across rounds by the library's DP service
                                                           and the match lists are gathered on rank 0 over NCCL)
   python bench.py --impl reference [...]                  the reference's own C (oracle/_ref) on the host cores
 
-`value`  : inputs resident in HBM before the timed region (pgmm_idx_upload done; timed: index kernels + pgmm_map_self)
+`value`  : inputs resident in HBM before the timed region (one pgmm_idx_upload per round of a step, done ONCE and reused by
+           every step -- device memory is O(rounds per step), independent of --steps; timed: index kernels + pgmm_map_self)
 `e2e`    : the same round through the reference-facing C-ABI with HOST buffers (mm_idx_str, mm_mapopt_update,
            pgmm_map_batch), host->device and device->host copies inside the timed region.
 """
@@ -46,14 +47,13 @@ def env_int(name, default):
 
 def make_pairs(n_pairs, first_pair, length):
     """Pair p = genomes (2p, 2p+1) of the star family around the PCG64(42) ancestor (seeds 20260+i)."""
+    from concurrent.futures import ThreadPoolExecutor
     from pangraph_b200 import synth
     anc = synth.ancestor(length, 42)
-    pairs = []
-    for p in range(first_pair, first_pair + n_pairs):
-        a = synth.mutate(anc, 20260 + 2 * p).tobytes()
-        b = synth.mutate(anc, 20260 + 2 * p + 1).tobytes()
-        pairs.append(([a, b], [str(2 * p), str(2 * p + 1)]))
-    return pairs
+    ids = [2 * p + h for p in range(first_pair, first_pair + n_pairs) for h in (0, 1)]
+    with ThreadPoolExecutor(4) as ex:  # numpy drops the GIL in the large array operations
+        gs = list(ex.map(lambda i: synth.mutate(anc, 20260 + i).tobytes(), ids))
+    return [([gs[2 * j], gs[2 * j + 1]], [str(ids[2 * j]), str(ids[2 * j + 1])]) for j in range(n_pairs)]
 
 
 class ClockSampler:
@@ -106,36 +106,49 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def reference_round(refmm2, lib, seqs, names):
+    """One find_matches round the way the reference runs it: mm_idx_str + mm_mapopt_update, then mm_map per sequence."""
+    ix = refmm2.Index(lib, seqs, names, "asm10", None, 90)
+    try:
+        return [ix.map_one(i) for i in range(len(ix.seqs))]
+    finally:
+        ix.close()
+
+
 def run_reference_step(refmm2, rounds, threads):
-    """The reference's path for every round of a step: index, mid_occ, then one mm_map per query; the queries of all
-    rounds share one pool of `threads` host threads (ctypes drops the GIL inside the C calls)."""
+    """The reference's path for every round of a step; rounds share one pool of `threads` host threads (sibling merges
+    of the guide tree run concurrently in the reference too; ctypes drops the GIL inside the C calls)."""
     from concurrent.futures import ThreadPoolExecutor
     lib = refmm2.load_ref()
-    idxs = [refmm2.Index(lib, seqs, names, "asm10", None, 90) for seqs, names in rounds]
-    try:
-        work = [(ix, i) for ix in idxs for i in range(len(ix.seqs))]
-        with ThreadPoolExecutor(max(1, threads)) as ex:
-            return list(ex.map(lambda t: len(t[0].map_one(t[1])), work))
-    finally:
-        for ix in idxs:
-            ix.close()
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        return list(ex.map(lambda r: sum(len(h) for h in reference_round(refmm2, lib, r[0], r[1])), rounds))
+
+
+def reference_sample(args, pairs, cores):
+    """The bounded sample of the workload the CPU arm runs per step: FULL-SIZE rounds of the same pair family (same bytes
+    per round as the CUDA arm), only fewer of them: 2 per host thread."""
+    n = args.ref_rounds_per_step if args.ref_rounds_per_step > 0 else 2 * cores
+    n = max(1, min(n, args.rounds_per_step))
+    return [pairs[j % len(pairs)] for j in range(n)]
 
 
 def reference_arm(args):
     """The reference's own CPU implementation (oracle/_ref = its vendored minimap2 C, unmodified) on a bounded sample of
-    the same workload: the first `ref_sample_len` bases of each genome of the pair, all host threads it can use
-    (one mm_map per sequence: the reference parallelises over queries, align_with_minimap2_lib.rs:64-74)."""
-    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    the same workload, with all host threads it can use."""
+    rank = env_int("RANK", 0)
     if rank != 0:
         return 0
     from oracle import refmm2
     cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
     P = args.rounds_per_step
-    n_pool = min(P, max(args.workers, args.pool))
-    pairs = make_pairs(n_pool, 0, args.genome_len)
-    sample = args.ref_sample_len
-    rounds = [([x[:sample] for x in pairs[j % n_pool][0]], pairs[j % n_pool][1]) for j in range(P)]
-    threads = min(cores, 2 * P)
+    n_ref = args.ref_rounds_per_step if args.ref_rounds_per_step > 0 else 2 * cores
+    pairs = make_pairs(min(args.pool, max(1, min(n_ref, P))), 0, args.genome_len)
+    rounds = reference_sample(args, pairs, cores)
+    threads = min(cores, len(rounds))
     times, bp = [], 0
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -146,15 +159,16 @@ def reference_arm(args):
             bp += sum(len(x) for seqs, _ in rounds for x in seqs)
     total = sum(times)
     value = bp / total / 1e9
+    sample = (f"{len(rounds)} full-size rounds per step (2 x {args.genome_len} bp each, the same pair family and the same bytes per "
+              f"round as the CUDA arm's {P} rounds per step), one host thread per round in flight, {threads} threads "
+              f"({cores} cores available)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8/int32 (SSE2 lanes)", "data": "synthetic",
-        "config": {"workload": f"{P} leaf-merge alignment rounds per step, each 2 x {args.genome_len} bp synthetic genomes at 1% "
-                               f"divergence, 10 rearrangements (asm10, k=19 w=19)", "sample": f"first {sample} bp of each genome"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-                         "sample": f"first {sample} bp of each genome of the {P} pairs of a step; the {2 * P} mm_map calls of a step "
-                                   f"share {threads} host threads ({cores} cores available)"},
+        "config": {"workload": f"{P} leaf-merge alignment rounds per rank per step, each 2 x {args.genome_len} bp synthetic genomes at 1% "
+                               f"divergence, 10 rearrangements (asm10, k=19 w=19)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -186,6 +200,25 @@ def pack_regs(n_regs, regs):
     return b"".join(out)
 
 
+def regs_to_tuples(abi, n_regs, regs):
+    """Every field of every hit of one round, like oracle.refmm2.reg_to_tuple (parity gate only; does not free)."""
+    return [[abi.reg_to_tuple(regs[i][j]) for j in range(n_regs[i])] for i in range(len(n_regs))]
+
+
+def device_footprint_gb(rounds_per_step, workers, genome_len, steps=None, dp_arena_frac=0.4, total_gb=178.0):
+    """Upper estimate of the device memory one rank of the CUDA arm holds (GB).  Independent of --steps by construction:
+    the resident arm keeps one uploaded pair per round OF A STEP and reuses it every step.
+      resident pairs: rounds_per_step x (coded bases 1.25 B/bp + index and minimizer arrays ~5 B/bp)
+      contexts      : workers x ~110 B/bp of seeding / chaining workspace for one round (2 genomes)
+      DP service    : at most dp_arena_frac of what is free when it starts (arenas grow on demand)."""
+    bp = 2.0 * genome_len
+    resident = rounds_per_step * bp * (1.25 + 5.0) / 1e9
+    contexts = workers * bp * 110.0 / 1e9
+    arenas = dp_arena_frac * max(0.0, total_gb - resident * 0.2 - contexts * 0.5)
+    return {"resident_gb": resident, "contexts_gb": contexts, "dp_arenas_gb": arenas, "total_gb": resident + contexts + arenas,
+            "depends_on_steps": False}
+
+
 def ours(args):
     import torch
     from pangraph_b200 import abi
@@ -203,7 +236,7 @@ def ours(args):
     abi.set_device(local)
     from concurrent.futures import ThreadPoolExecutor
     P = args.rounds_per_step
-    n_pool = min(P, max(args.workers, args.pool))
+    n_pool = max(1, min(P, args.pool))
     pairs = make_pairs(n_pool, rank * n_pool, args.genome_len)
     bp_pair = [sum(len(x) for x in seqs) for seqs, _ in pairs]
     pool = ThreadPoolExecutor(min(P, args.workers))  # rounds in flight at any moment
@@ -213,7 +246,7 @@ def ours(args):
 
     from pangraph_b200 import sharding
 
-    def round_e2e(p):
+    def round_e2e(p, keep=False):
         seqs, names = pairs[p]
         idx = abi.Index(seqs, names, "asm10", None, 90)  # mm_idx_str + mm_mapopt_update (host buffers)
         n = len(seqs)
@@ -225,10 +258,8 @@ def ours(args):
         return n_regs, regs
 
     def round_resident(idx):
-        idx.build()
-        out = idx.map_self(raw=True)
-        idx.close()  # device blocks go back to the pool for the next round
-        return out
+        idx.build()  # K1 + K2 on the resident bases + mm_mapopt_update; rebuilds in place every step
+        return idx.map_self(raw=True)
 
     def finish(results):
         """Rank 0 receives the match lists of every rank's rounds, in round order, over NCCL."""
@@ -253,6 +284,33 @@ def ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- parity gate (outside every timed region): round 0 of this rank through BOTH call paths against the reference's
+    # own C (oracle/_ref).  A run whose results differ does not produce a number.
+    parity = {"parity_checked": False}
+    from oracle import refmm2
+    have_ref = os.path.exists(refmm2.REF_SO)
+    if have_ref and not args.no_parity and (rank == 0 or args.parity_all_ranks):
+        seqs, names = pairs[0]
+        t0 = time.perf_counter()
+        want, mid = refmm2.ref_map_all(seqs, names, "asm10", None, 90, threads=2)
+        t_ref = time.perf_counter() - t0
+        n_regs, regs = round_e2e(0)
+        got_e2e = regs_to_tuples(abi, n_regs, regs)
+        free_regs(abi, n_regs, regs)
+        ix = abi.Index(*pairs[0], "asm10", None, 90, resident_only=True)
+        n_regs, regs = round_resident(ix)
+        got_res = regs_to_tuples(abi, n_regs, regs)
+        free_regs(abi, n_regs, regs)
+        assert ix.mo.mid_occ == mid, f"mid_occ {ix.mo.mid_occ} != reference {mid}"
+        ix.close()
+        if got_e2e != want or got_res != want:
+            raise SystemExit("bench.py: PARITY FAILURE -- the CUDA path's hits differ from the reference's on round 0; no number reported")
+        parity = {"parity_checked": True, "parity_round": f"pair 0 of rank {rank} (2 x {args.genome_len} bp), host-buffer and resident call "
+                  f"paths, every mm_reg1_t field + CIGAR + de equal to oracle/_ref ({sum(len(w) for w in want)} hits)",
+                  "reference_seconds_one_round_2_threads": round(t_ref, 2)}
+    elif not have_ref:
+        parity["parity_note"] = "oracle/_ref/libmm2ref.so not present on this box"
+
     cpu_used = {}
 
     def timed(fn, items):
@@ -275,124 +333,140 @@ def ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), hits
 
+    # ---- inputs of the resident arm: ONE uploaded pair per round of a step, reused by every step (O(P) device memory) ----
+    resident = [abi.Index(*pairs[p], "asm10", None, 90, resident_only=True) for p in pairs_of_step(0)]
     for s in range(args.warmup):
-        step_e2e(s)
+        if s % 2 == 0:
+            step_e2e(s)
+        else:
+            step_resident(resident)
     abi.get_stats(reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
 
     # ---- value: inputs resident in HBM ----
-    resident = [[abi.Index(*pairs[p], "asm10", None, 90, resident_only=True) for p in pairs_of_step(args.warmup + s)]
-                for s in range(args.steps)]
-    abi.get_stats(reset=True)
-    t_res, hits_res = timed(step_resident, resident)
+    free0 = torch.cuda.mem_get_info()[0]
+    t_res, hits_res = timed(step_resident, [resident] * args.steps)
     st_res = abi.get_stats(reset=True)
     # ---- e2e: host buffers through the C-ABI ----
     t_e2e, hits_e2e = timed(step_e2e, [args.warmup + s for s in range(args.steps)])
     st_e2e = abi.get_stats(reset=True)
     clocks = sampler.stop() if sampler else None
+    free1, total_mem = torch.cuda.mem_get_info()
 
-    bp_rank = sum(bp_pair[p] for s in range(args.steps) for p in pairs_of_step(args.warmup + s))
-    bp_all = torch.tensor([bp_rank], dtype=torch.float64, device="cuda")
+    bp_rank = args.steps * sum(bp_pair[p] for p in pairs_of_step(0))
+    bp_rank_e2e = sum(bp_pair[p] for s in range(args.steps) for p in pairs_of_step(args.warmup + s))
+    bp_all = torch.tensor([bp_rank, bp_rank_e2e], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(bp_all)
-    bp_total = float(bp_all.item())
+    bp_total, bp_total_e2e = float(bp_all[0].item()), float(bp_all[1].item())
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import refmm2
-        if os.path.exists(refmm2.REF_SO):
-            sample = args.ref_sample_len
-            rounds = [([x[:sample] for x in pairs[p][0]], pairs[p][1]) for p in pairs_of_step(0)]
-            threads = min(os.cpu_count() or 1, 2 * P)
-            t0 = time.perf_counter()
-            run_reference_step(refmm2, rounds, threads)
-            dt = time.perf_counter() - t0
-            cpu_baseline = {"value": sum(len(x) for r in rounds for x in r[0]) / dt / 1e9, "unit": UNIT, "cores": threads,
-                            "kind": "reference",
-                            "sample": f"one step on the first {sample} bp of each genome ({dt:.1f} s; the {2 * P} mm_map calls share "
-                                      f"{threads} host threads, {os.cpu_count()} cores available)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and have_ref:
+        cores = os.cpu_count() or 1
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            pass
+        rounds = reference_sample(args, pairs, cores)
+        threads = min(cores, len(rounds))
+        t0 = time.perf_counter()
+        run_reference_step(refmm2, rounds, threads)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sum(len(x) for r in rounds for x in r[0]) / dt / 1e9, "unit": UNIT, "cores": threads,
+                        "kind": "reference",
+                        "sample": f"{len(rounds)} full-size rounds of the same pair family (2 x {args.genome_len} bp each, same bytes per "
+                                  f"round as the CUDA arm), one host thread per round in flight, {threads} threads, {dt:.1f} s "
+                                  f"({cores} cores available)"}
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # DP kernel families, each timed with CUDA events on the streams its launches go to.  Algorithmic bytes per launch:
-        # one traceback byte per in-band cell + the bases each problem reads.  The roofline entry
-        # is the family with the largest share of the kernel time (what the ncu launch list shows too).
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        int_peak = n_sm * 128 * sm_mhz * 1e6 / 1e9  # G int32-lane-ops/s at the clock sampled under load
+        # DP kernel families, each launch timed with CUDA events on the stream it is launched on.  Algorithmic work per
+        # launch: 50 integer lane-ops per cell and, for the HBM reading, one traceback byte per in-band cell
+        # plus the bases each problem reads.
         fams = {"ksw_extd2_kernel (K5, band-limited extensions)": "k5", "ksw_fill_small_kernel (K5a, first-pass gap fills)": "k5a",
                 "ksw_fill_wide_kernel (K5b, long fills across inversions / big indels)": "k5b"}
+        tp = os.path.join(ROOT, "profiles", "dp_traffic.json")
+        traffic_tbl = json.load(open(tp)) if os.path.exists(tp) else {}
         dp_kernels = {}
         for name, key in fams.items():
             ms, cells, bases, ln = (st_res[f"{key}_{x}"] for x in ("ms", "cells", "bases", "launches"))
+            sec = ms / 1e3
             dp_kernels[name] = {"ms_total": ms, "launches": int(ln), "ms_per_launch": ms / max(1, ln), "cells": cells,
-                                "gb_per_s": (cells + bases) / (ms / 1e3) / 1e9 if ms > 0 else 0.0,
-                                "gcups": cells / (ms / 1e3) / 1e9 if ms > 0 else 0.0}
-        # K4 (chain score fill): one launch per round; algorithmic bytes per anchor = 25 read by the fill (x, y, q_span and
-        # the 16-byte window record the prep kernel leaves) + 12 written (f, p, v)
-        k4_ms, k4_anchors, k4_launches = st_res["chain_kernel_ms"], st_res["chain_anchors"], st_res["batches"]
-        dp_kernels["chain_fill_kernel (K4, chaining score fill)"] = {
-            "ms_total": k4_ms, "launches": int(k4_launches), "ms_per_launch": k4_ms / max(1, k4_launches), "anchors": k4_anchors,
-            "gb_per_s": 37.0 * k4_anchors / (k4_ms / 1e3) / 1e9 if k4_ms > 0 else 0.0,
-            "anchors_per_us": k4_anchors / (k4_ms * 1e3) if k4_ms > 0 else 0.0}
-        fams["chain_fill_kernel (K4, chaining score fill)"] = "k4"
-        tot_ms = sum(v["ms_total"] for v in dp_kernels.values()) or 1.0
-        for v in dp_kernels.values():
+                                "cells_per_launch": cells / max(1, ln),
+                                "gcups": cells / sec / 1e9 if ms > 0 else 0.0,
+                                "achieved_int_gops": 50.0 * cells / sec / 1e9 if ms > 0 else 0.0,
+                                "int_frac": 50.0 * cells / sec / 1e9 / int_peak if ms > 0 else 0.0,
+                                "gb_per_s": (cells + bases) / sec / 1e9 if ms > 0 else 0.0,
+                                "hbm_frac": (cells + bases) / sec / 1e9 / peak if ms > 0 else 0.0,
+                                "traffic_bytes_per_launch_ncu": traffic_tbl.get(key)}
+        # K4 (chain score fill): latency-bound dependent chain; reported as anchors/us.  Algorithmic bytes per anchor = 25
+        # read by the fill (x, y, q_span and the 16-byte window record of the prep kernel) + 12 written (f, p, v)
+        k4_ms, k4_anchors, k4_launches = st_res["chain_kernel_ms"], st_res["chain_anchors"], max(1.0, st_res["chain_launches"])
+        k4 = {"ms_total": k4_ms, "launches": int(k4_launches), "ms_per_launch": k4_ms / k4_launches, "anchors": k4_anchors,
+              "bound": "latency (dependent chain per anchor segment)",
+              "anchors_per_us": k4_anchors / (k4_ms * 1e3) if k4_ms > 0 else 0.0,
+              "gb_per_s": 37.0 * k4_anchors / (k4_ms / 1e3) / 1e9 if k4_ms > 0 else 0.0}
+        tot_ms = (sum(v["ms_total"] for v in dp_kernels.values()) + k4_ms) or 1.0
+        tot_cells = sum(v["cells"] for v in dp_kernels.values()) or 1.0
+        for v in list(dp_kernels.values()) + [k4]:
             v["share_of_kernel_time"] = v["ms_total"] / tot_ms
-        dom = max(dp_kernels, key=lambda k: dp_kernels[k]["ms_total"])
-        achieved = dp_kernels[dom]["gb_per_s"]
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "dp_traffic.json")
-        if os.path.exists(tp):  # dram bytes per launch from the committed `ncu --set full` captures
-            traffic = json.load(open(tp)).get(fams[dom])
-        notes = {
-            "k4": "one warp per independent anchor segment walks a true dependent chain (each score feeds the next range minimum): "
-                  "the launch lasts as long as its longest segment (190 k of a query's 380 k anchors), 212 warp instructions per "
-                  "anchor at ~3.4 cycles each, no DRAM traffic to speak of (ncu: 3.9 MB) -- latency-bound, neither roofline applies; "
-                  "it is the longest kernel of a round by stream time while using one warp per segment "
-                  "(profiles/r01_k4_chain_fill_ncu_full.md)",
-            "dp": "the DP kernels are integer-issue bound, not HBM bound (K5a: ~4 instructions per cell against 1 traceback byte; "
-                  "ncu: 64 % of issue slots, 4 % of DRAM throughput), and a long fill runs on one SM: the HBM fraction is small "
-                  "by construction; launches of concurrent rounds share the GPU"}
+        for v in dp_kernels.values():
+            v["share_of_cells"] = v["cells"] / tot_cells
+        dom = max(dp_kernels, key=lambda k: dp_kernels[k]["cells"])  # the kernel that does most of the DP cells
+        d = dp_kernels[dom]
+        rounds_timed = args.steps * P
         line = {
             "metric": METRIC, "value": bp_total / t_res / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8x4 (DP) / u64 (seeding)", "data": "synthetic",
+            "dtype": "int16x2 / int8x4 lanes (DP), u64 (seeding), f32+f64 (chain scores)", "data": "synthetic",
             "config": {"workload": f"{P} leaf-merge alignment rounds per rank per step, each 2 x {args.genome_len} bp synthetic genomes "
                                    f"at 1% divergence, 10 rearrangements (asm10, k=19 w=19)",
-                       "l2": f"working set > L2: {n_pool} distinct genome pairs per rank, rounds in flight work on different pairs, "
-                             f"> 1 GB of traceback written per round",
-                       "rounds_per_step": P, "rounds_in_flight": min(P, args.workers),
+                       "l2": f"working set > L2: {n_pool} distinct genome pairs per rank ({n_pool * 2 * args.genome_len / 1e6:.0f} MB of bases), "
+                             f"rounds in flight work on different pairs, > 1 GB of traceback written per round",
+                       "rounds_per_step": P, "rounds_in_flight": min(P, args.workers), "distinct_pairs_per_rank": n_pool,
                        "busy_host_cores": {"value": round(cpu_used.get("step_resident", 0), 1), "e2e": round(cpu_used.get("step_e2e", 0), 1)},
-                       "hits_per_round": hits_res / max(1, args.steps * P), "host_threads": os.cpu_count()},
-            "e2e": {"value": bp_total / t_e2e / 1e9, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
+                       "hits_per_round": hits_res / max(1, rounds_timed), "host_threads": os.cpu_count(),
+                       "device_memory_gb": {"total": total_mem / 1e9, "free_before_timed": free0 / 1e9, "free_after_timed": free1 / 1e9},
+                       "device_footprint_model": device_footprint_gb(P, min(P, args.workers), args.genome_len)},
+            "e2e": {"value": bp_total_e2e / t_e2e / 1e9, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
             "gpu_launches": int(st_res["launches"]),
             "device_mallocs_in_timed_region": {"value": int(st_res["device_mallocs"]), "e2e": int(st_e2e["device_mallocs"])},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "launches": dp_kernels[dom]["launches"], "ms_per_launch": dp_kernels[dom]["ms_per_launch"],
-                         "share_of_kernel_time": dp_kernels[dom]["share_of_kernel_time"],
-                         "note": notes["k4" if fams[dom] == "k4" else "dp"]},
-            # the same figures for the kernel that does most of the GPU's WORK (85 % of all DP cells; CTA trace: 243 of its CTAs
-            # resident on average against 14 warps of K4): bound by integer issue, not by HBM
-            "roofline_by_gpu_work": {"bound": "hbm", "kernel": "ksw_fill_small_kernel (K5a, first-pass gap fills)",
-                                     "achieved": dp_kernels["ksw_fill_small_kernel (K5a, first-pass gap fills)"]["gb_per_s"],
-                                     "peak": peak, "unit": "GB/s",
-                                     "frac": dp_kernels["ksw_fill_small_kernel (K5a, first-pass gap fills)"]["gb_per_s"] / peak if peak else None,
-                                     "traffic": json.load(open(tp)).get("k5a") if os.path.exists(tp) else None,
-                                     "note": notes["dp"] + "; launches of concurrent rounds overlap, so the per-launch rate under load "
-                                             "is a fraction of the 240 GCUPS a launch reaches alone (profiles/r01_k5a_ncu_full.md)"},
+            # headline roofline: the DP kernel that does most cells.  The DP is integer-issue bound (ncu: K5a 64 % of issue
+            # slots, 4 % of DRAM throughput), so `achieved`/`peak` are integer lane-ops; the HBM reading north_star asks
+            # for is given next to it and is small by construction (1 traceback byte per ~50 lane-ops).
+            "roofline": {"bound": "int-issue", "kernel": dom, "achieved": d["achieved_int_gops"], "peak": int_peak,
+                         "unit": "G int32-lane-ops/s", "frac": d["int_frac"],
+                         "definition": "achieved = 50 lane-ops x cells of the family / its summed per-launch CUDA-event time; "
+                                       f"peak = {n_sm} SMs x 128 lanes x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
+                         "gcups": d["gcups"], "launches": d["launches"], "ms_per_launch": d["ms_per_launch"],
+                         "cells_per_launch": d["cells_per_launch"], "share_of_cells": d["share_of_cells"],
+                         "share_of_kernel_time": d["share_of_kernel_time"],
+                         "hbm": {"achieved": d["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": d["hbm_frac"], "peak_source": peak_src,
+                                 "algorithmic_bytes": "1 traceback byte per in-band cell + the bases each problem reads"},
+                         "traffic": d["traffic_bytes_per_launch_ncu"],
+                         "note": "launches of concurrent rounds share the GPU, so a launch's event time under load is longer than alone; "
+                                 "per-launch solo figures: profiles/"},
             "kernels": dp_kernels,
+            "chain_fill_kernel (K4)": k4,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
-            "phases_ms_per_round": {k: st_res[k] / (args.steps * P) for k in ("index_ms", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch",
+            "phases_ms_per_round": {k: st_res[k] / rounds_timed for k in ("index_ms", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch",
                                                                        "t_final", "dp_kernel_ms", "total_ms", "t_chain_sort", "t_chain_fill",
                                                                        "t_chain_rest", "chain_kernel_ms")},
-            "chain": {"anchors_per_round": st_res["chain_anchors"] / (args.steps * P), "segments_per_round": st_res["chain_segments"] / (args.steps * P),
-                      "segments_to_host_arbiter": st_res["chain_redo_segments"] / (args.steps * P),
-                      "anchors_to_host_arbiter": st_res["chain_redo_anchors"] / (args.steps * P),
-                      "fill_kernel_ms_per_round": st_res["chain_kernel_ms"] / (args.steps * P)},
-            "dp": {"jobs_per_round": st_res["dp_jobs"] / (args.steps * P), "cells_per_round": st_res["dp_cells"] / (args.steps * P),
-                   "waves_per_round": st_res["dp_waves"] / (args.steps * P)},
+            "chain": {"anchors_per_round": st_res["chain_anchors"] / rounds_timed, "segments_per_round": st_res["chain_segments"] / rounds_timed,
+                      "segments_to_host_arbiter": st_res["chain_redo_segments"] / rounds_timed,
+                      "anchors_to_host_arbiter": st_res["chain_redo_anchors"] / rounds_timed,
+                      "fill_kernel_ms_per_round": st_res["chain_kernel_ms"] / rounds_timed},
+            "dp": {"jobs_per_round": st_res["dp_jobs"] / rounds_timed, "cells_per_round": st_res["dp_cells"] / rounds_timed,
+                   "cells_per_bp": st_res["dp_cells"] / max(1.0, bp_rank), "waves_per_round": st_res["dp_waves"] / rounds_timed},
         }
+        line.update(parity)
         print(json.dumps(line))
+    for ix in resident:
+        ix.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -401,15 +475,17 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--rounds-per-step", type=int, default=192, help="independent leaf-merge rounds a rank keeps in flight per step")
+    ap.add_argument("--rounds-per-step", type=int, default=192, help="independent leaf-merge rounds of one rank per step")
     ap.add_argument("--workers", type=int, default=64, help="host threads driving rounds concurrently (one CUDA stream each)")
-    ap.add_argument("--pool", type=int, default=36, help="distinct genome pairs generated per rank (steps cycle through them)")
-    ap.add_argument("--ref-sample-len", type=int, default=1_000_000)
+    ap.add_argument("--pool", type=int, default=32, help="distinct genome pairs generated per rank (rounds cycle through them)")
+    ap.add_argument("--ref-rounds-per-step", type=int, default=0, help="reference arm / cpu_baseline: full-size rounds per step (0 = 2 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against oracle/_ref (profiling runs only)")
+    ap.add_argument("--parity-all-ranks", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

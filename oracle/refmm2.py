@@ -224,3 +224,47 @@ def ref_sketch(lib, seq, w, k, rid=0):
     if v.a:
         _libc.free(C.cast(v.a, C.c_void_p))
     return out
+
+
+# ---- the seeding stage of the reference on its own (for the K1+K3 parity test) ----
+STAGE_SO = os.path.join(HERE, "_ref", "libmm2ref_stage.so")
+
+
+def load_ref_stage():
+    """oracle/_ref/libmm2ref_stage.so: the same unmodified sources with map.c's file-local functions visible."""
+    if not os.path.exists(STAGE_SO):
+        raise RuntimeError(f"{STAGE_SO} missing: run `make -C oracle ref` where /root/reference is mounted")
+    return bind(C.CDLL(STAGE_SO))
+
+
+def ref_collect_seed_hits(lib, idx, seq, name):
+    """What mm_map_frag does up to the chaining call (map.c:250-253): collect_minimizers, mm_seed_mz_flt,
+    collect_seed_hits.  -> (anchors [(x, y)] as the reference's radix sort leaves them, mini_pos [u64], rep_len)."""
+    seq = seq if isinstance(seq, bytes) else seq.encode()
+    name = name if isinstance(name, bytes) else name.encode()
+    mv = mm128_v(0, 0, None)
+    qlen = C.c_int(len(seq))
+    sp = C.c_char_p(seq)
+    lib.collect_minimizers.argtypes = [C.c_void_p, C.POINTER(mm_mapopt_t), C.POINTER(mm_idx_t), C.c_int, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_char_p), C.POINTER(mm128_v)]
+    lib.collect_minimizers.restype = None
+    lib.collect_minimizers(None, C.byref(idx.mo), idx.mi, 1, C.byref(qlen), C.byref(sp), C.byref(mv))
+    if idx.mo.q_occ_frac > 0.0:
+        lib.mm_seed_mz_flt.argtypes = [C.c_void_p, C.POINTER(mm128_v), C.c_int32, C.c_float]
+        lib.mm_seed_mz_flt.restype = None
+        lib.mm_seed_mz_flt(None, C.byref(mv), idx.mo.mid_occ, idx.mo.q_occ_frac)
+    n_a, rep_len, n_mini = C.c_int64(0), C.c_int(0), C.c_int(0)
+    mini = C.POINTER(C.c_uint64)()
+    lib.collect_seed_hits.argtypes = [C.c_void_p, C.POINTER(mm_mapopt_t), C.c_int, C.POINTER(mm_idx_t), C.c_char_p, C.POINTER(mm128_v),
+                                      C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.POINTER(C.c_uint64))]
+    lib.collect_seed_hits.restype = C.POINTER(mm128_t)
+    a = lib.collect_seed_hits(None, C.byref(idx.mo), idx.mo.mid_occ, idx.mi, name, C.byref(mv), len(seq), C.byref(n_a),
+                              C.byref(rep_len), C.byref(n_mini), C.byref(mini))
+    import numpy as np
+    anchors = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_uint64)), shape=(n_a.value, 2)).copy() if n_a.value else np.zeros((0, 2), np.uint64)
+    mp = np.ctypeslib.as_array(mini, shape=(n_mini.value,)).copy() if n_mini.value else np.zeros(0, np.uint64)
+    for ptr in (a, mini, mv.a):
+        if ptr:
+            _libc.free(C.cast(ptr, C.c_void_p))
+    return anchors, mp, rep_len.value

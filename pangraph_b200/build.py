@@ -28,7 +28,7 @@ def build(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
     hdrs = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    objs = []
+    objs, jobs = [], []
     for s in srcs:
         o = os.path.join(OBJ, os.path.basename(s) + ".o")
         objs.append(o)
@@ -37,11 +37,14 @@ def build(verbose=False, force=False):
                 cmd = [NVCC] + ARCH + FLAGS + ["-c", s, "-o", o]
             else:  # host-only translation units go straight to the host compiler (no fused multiply-add contraction)
                 cmd = [CXX] + HOST_FLAGS + ["-c", s, "-o", o]
-            r = subprocess.run(cmd, capture_output=True, text=True)
+            jobs.append((s, cmd))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, min(len(jobs), os.cpu_count() or 1))) as ex:  # translation units compile in parallel
+        for (s, cmd), r in zip(jobs, ex.map(lambda j: subprocess.run(j[1], capture_output=True, text=True), jobs)):
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:
-                raise RuntimeError(f"nvcc failed on {s}")
+                raise RuntimeError(f"compiler failed on {s}")
     if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -94,20 +94,38 @@ struct DpService::Impl {
 };
 
 DpService::DpService() : impl_(new Impl) {
-  const char *e = getenv("PGMM_DP_ARENA_GB");
-  const double gb = e ? atof(e) : 6.0;  // per worker of the short lane; medium and long workers take a third / half of it
+  // A batch lasts as long as its longest problem, and a worker runs one batch at a time: enough workers that a new
+  // wave rarely waits for a running batch (each owns one stream per size class and one arena).
+  const char *e = getenv("PGMM_DP_WORKERS");  // "<short>x<medium>x<long>"
+  int n[kLanes] = {6, 8, 10};
+  if (e) sscanf(e, "%dx%dx%d", &n[0], &n[1], &n[2]);
+  for (int L = 0; L < kLanes; ++L) n[L] = std::max(1, n[L]);
+  // Traceback arena budget per worker: PGMM_DP_ARENA_GB for the short lane, a third / half of it for the medium / long
+  // lane -- scaled down so that all arenas together never exceed PGMM_DP_ARENA_FRAC (default 0.4) of the memory that is
+  // free on the device when the service starts.  Arenas grow on demand up to their budget (KswEngine::run); a wave that
+  // needs more is split.
+  e = getenv("PGMM_DP_ARENA_GB");
+  double gb = e ? atof(e) : 6.0;
+  e = getenv("PGMM_DP_ARENA_FRAC");
+  const double frac = e ? std::min(0.9, std::max(0.01, atof(e))) : 0.4;
+  require_device();
+  size_t free_b = 0, total_b = 0;
+  PGMM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const double all_gb = gb * n[0] + gb / 3 * n[1] + gb / 2 * n[2], cap_gb = frac * (double)free_b / (double)(1ull << 30);
+  if (all_gb > cap_gb) gb *= cap_gb / all_gb;
+  if (gb * (double)(1ull << 30) / 3 < (double)(64u << 20))
+    PGMM_FATAL("DP service: %.1f GB free on the device leave less than 64 MB of traceback arena per worker (budget = %.2f of free "
+               "memory over %d+%d+%d workers; see PGMM_DP_ARENA_FRAC / PGMM_DP_WORKERS)", (double)free_b / (1ull << 30), frac, n[0], n[1], n[2]);
   impl_->arena_bytes[0] = (size_t)(gb * (double)(1ull << 30));
   impl_->arena_bytes[1] = (size_t)(gb / 3 * (double)(1ull << 30));
   impl_->arena_bytes[2] = (size_t)(gb / 2 * (double)(1ull << 30));
+  if (getenv("PGMM_TRACE"))
+    fprintf(stderr, "[pgmm trace] dp service: %.1f of %.1f GB free, arena budgets %.2f / %.2f / %.2f GB x %d / %d / %d workers\n",
+            (double)free_b / (1ull << 30), (double)total_b / (1ull << 30), gb, gb / 3, gb / 2, n[0], n[1], n[2]);
   e = getenv("PGMM_DP_MAX_JOBS");
   impl_->max_jobs = e ? (size_t)atoll(e) : (size_t)300000;
-  // A batch lasts as long as its longest problem, and a worker runs one batch at a time: enough workers that a new
-  // wave rarely waits for a running batch (each owns one stream per size class and one arena).
-  e = getenv("PGMM_DP_WORKERS");  // "<short>x<medium>x<long>"
-  int n[kLanes] = {6, 8, 10};
-  if (e) sscanf(e, "%dx%dx%d", &n[0], &n[1], &n[2]);
   for (int L = 0; L < kLanes; ++L)
-    for (int i = 0; i < std::max(1, n[L]); ++i) impl_->workers.emplace_back([this, L] { impl_->worker(L); });
+    for (int i = 0; i < n[L]; ++i) impl_->workers.emplace_back([this, L] { impl_->worker(L); });
   for (auto &t : impl_->workers) t.detach();
 }
 

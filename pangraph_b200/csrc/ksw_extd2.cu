@@ -1036,9 +1036,12 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       for (int k : cls[c]) hid[nid++] = k;
     }
     m.d_jobs.ensure(nw), m.d_outs.ensure(nw), m.d_ids.ensure(nw), m.d_counter.ensure(1);
-    // the traceback arena is taken once at its full budget: growing it later would mean a cudaMalloc, which stalls
-    // every stream of the device
-    m.p_arena.ensure_exact(std::max(p_used + 256, arena_budget_bytes + 256));
+    // the traceback arena grows on demand up to its budget, in steps of at least half its size: a cudaMalloc stalls every
+    // stream of the device, so growth has to stop after the first few waves
+    if (p_used + 256 > m.p_arena.cap) {
+      const size_t want = std::max<size_t>(p_used + 256, std::min<size_t>(arena_budget_bytes + 256, std::max<size_t>(m.p_arena.cap + m.p_arena.cap / 2, size_t(256) << 20)));
+      m.p_arena.ensure_exact(want);
+    }
     m.cig_arena.ensure(2 * cig_used + 4), m.cig_packed.ensure(2 * cig_used + 4), m.scratch.ensure(scr_used + 256);
     PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, hj, nw * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
     PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, hid, nw * sizeof(int), cudaMemcpyHostToDevice, stream));

@@ -436,7 +436,8 @@ int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *c
                        const mm_mapopt_t *opt, uint64_t *out_anchor, uint64_t anchor_cap, uint64_t *out_mini, uint64_t mini_cap,
                        int64_t *out_n) {
   require_device();
-  PgmmIndex *ix = (PgmmIndex *)mi->h;
+  PgmmIndex *ix = mi ? (PgmmIndex *)mi->h : nullptr;
+  if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200 (no device index attached)");
   CtxLease cx;
   QueryBatch qb;
   qb.n = n;

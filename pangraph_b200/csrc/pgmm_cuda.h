@@ -78,7 +78,12 @@ class DevicePool {
       trim();
       e = cudaMalloc(&p, cls);
     }
-    if (e != cudaSuccess) PGMM_FATAL("cudaMalloc of %zu bytes failed: %s", cls, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      size_t fr = 0, tot = 0;
+      cudaMemGetInfo(&fr, &tot);
+      PGMM_FATAL("cudaMalloc of %zu bytes failed: %s (%zu of %zu bytes free on the device; the library's budget is set by "
+                 "PGMM_DP_ARENA_GB, PGMM_CONTEXTS and what the caller keeps resident)", cls, cudaGetErrorString(e), fr, tot);
+    }
     return p;
   }
   void release(void *p, size_t cls) {
@@ -112,17 +117,35 @@ struct DevBuf {
   DevBuf &operator=(const DevBuf &) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) DevicePool::get().release(p, cls);
+    if (p) {
+      if (exact_) cudaFree(p);
+      else DevicePool::get().release(p, cls);
+    }
     p = nullptr;
-    cap = 0, cls = 0;
+    cap = 0, cls = 0, exact_ = false;
   }
-  // for buffers whose size is a fixed budget (the traceback arenas): no headroom, 2 MB granularity
+  bool exact_ = false;  // block came straight from cudaMalloc (ensure_exact), not from the pool
+  // for the traceback arenas: exact size (2 MB granularity), allocated from and returned to the DRIVER -- a cached old
+  // arena of another size would be dead weight in the pool.  Growing costs a cudaFree + cudaMalloc (both synchronise the
+  // device), which only happens while the arenas find their steady-state size.
   T *ensure_exact(size_t n) {
     if (n > cap) {
       release();
-      cls = (n * sizeof(T) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
-      p = (T *)DevicePool::get().alloc(cls);
-      cap = cls / sizeof(T);
+      const size_t bytes = (n * sizeof(T) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+      void *q = nullptr;
+      __atomic_fetch_add(&DevicePool::misses(), 1, __ATOMIC_RELAXED);
+      cudaError_t e = cudaMalloc(&q, bytes);
+      if (e != cudaSuccess) {
+        DevicePool::get().trim();
+        e = cudaMalloc(&q, bytes);
+      }
+      if (e != cudaSuccess) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        PGMM_FATAL("cudaMalloc of a %zu-byte traceback arena failed: %s (%zu of %zu bytes free on the device; lower PGMM_DP_ARENA_GB "
+                   "or PGMM_CONTEXTS)", bytes, cudaGetErrorString(e), fr, tot);
+      }
+      p = (T *)q, cap = bytes / sizeof(T), cls = 0, exact_ = true;
     }
     return p;
   }
