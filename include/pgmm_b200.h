@@ -320,7 +320,8 @@ PGMM_API int64_t pgmm_cta_trace_end(void *out, uint64_t max_n);
  * [17] host->device bytes [18] device->host bytes [19] bases read by the DP kernels [20] cudaMalloc calls
  * [21..32] per DP kernel family (K5 generic, K5a small fills, K5b wide fills): ms on the launch streams, cells, bases read,
  * launches [33..41] chaining: host sort ms, device fill ms (with copies), host rest ms (redo + backtrack + hit skeletons +
- * plan), fill kernel ms, anchors, segments, segments handed back to the host, their anchors, launches */
+ * plan), fill kernel ms, anchors, segments, segments handed back to the host, their anchors, launches 
+ * [42] fixed-point iterations of the chain fill summed over its batches, [43] those batches */
 PGMM_API void pgmm_get_stats(double *out, int n, int reset);
 
 #ifdef __cplusplus

@@ -53,6 +53,7 @@ struct ChainFillStats {
   uint64_t anchors = 0, segments = 0, redo_segments = 0, redo_anchors = 0;
   int launches = 0;
   double kernel_ms = 0;
+  uint64_t iterations = 0, batches = 0;  // K4p: fixed-point iterations summed over the fills (batches)
 };
 
 // segments + host fill + backtrack in one call (stage tests, CPU-only seam)

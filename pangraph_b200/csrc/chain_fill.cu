@@ -78,7 +78,7 @@ __device__ __forceinline__ int link_score_dev(int xi, int yi, int xj, int yj, in
 // AUX[i] = (group start, outer window start, inner window start, link score << 2 | exact << 1 | width <= bw).
 __global__ void chain_prep_kernel(const U128 *__restrict__ a, int n, const int *__restrict__ seg_starts, int n_segs,
                                   const ChainDevParams *__restrict__ Pp, int *__restrict__ X, int *__restrict__ Y, uint8_t *__restrict__ QS,
-                                  int4 *__restrict__ AUX) {
+                                  int4 *__restrict__ AUX, int *__restrict__ SEG) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const ChainDevParams P = *Pp;
@@ -92,6 +92,7 @@ __global__ void chain_prep_kernel(const U128 *__restrict__ a, int n, const int *
     else hi = mid;
   }
   const int s = seg_starts[lo];
+  if (SEG) SEG[i] = lo;
   // first index in [s, i] whose target coordinate is at least `bound`
   const auto lower = [&](int bound) {
     int l = s, h = i;  // a[i] itself always qualifies
@@ -431,6 +432,371 @@ __global__ void __launch_bounds__(32) chain_fill_kernel(const int *__restrict__ 
   if (lane == 0) seg_flag[blockIdx.x] = flag, trace::emit(5, tr0, tr0, (unsigned)(e - s));
 }
 
+
+// =====================================================================================================================
+// K4p: the same score fill as a PARALLEL FIXED-POINT iteration (default; the one-warp-per-segment kernel above is kept
+// as the PGMM_K4_SERIAL=1 variant).
+//
+// In mg_lchain_rmq the decision of anchor i (its predecessor p[i]) is a pure function of the coordinates and of (f, p)
+// of EARLIER anchors; f and v then follow from p alone: f[i] = f[p[i]] + link(p[i], i) (q_span for a chain start),
+// v[i] = max(v[p[i]], f[i]).  So the fill is the unique fixed point of
+//     decide:    p'  = D(f, p)      -- every anchor at once, one warp each, reading the previous iterate
+//     propagate: f,v = prefix sums / prefix maxima along the predecessor forest p'  (pointer jumping, log2(n) rounds)
+// (unique by induction on the anchor index).  Starting from "every anchor links to the one right before it", a 5-Mbp
+// query of the benchmark reaches the fixed point in 6 iterations and a real E. coli query in 15 -- instead of a dependent
+// chain of 190 000 steps on one warp.  Everything below the first anchor of a segment whose decision changed in an
+// iteration is final (its inputs are), so later iterations only touch what lies behind that frontier.
+//
+// decide answers the range minimum from block minima (32 anchors per block) plus the ragged ends of the window; when
+// the smallest key of the whole window is unique and inside the query range it IS the reference's answer, otherwise the
+// window is scanned with the range filter.  Equal smallest priorities inside the range still cannot be arbitrated
+// without the reference's tree: the anchor is marked and its segment goes to the host arbiter, as before.
+// =====================================================================================================================
+struct ParArgs {
+  const int *X, *Y;
+  const uint8_t *QS;
+  const int4 *AUX;      // i0, st, sti, link with the previous anchor
+  const int *SEG;       // segment of every anchor
+  const int4 *segs;     // per segment: start, end, first anchor of its query, -
+  int *F, *P, *V, *Pn, *G;
+  int *PX;              // exported predecessors (relative to the query's first anchor)
+  unsigned long long *KEY;
+  int4 *BM;             // per block of 32 anchors: key lo, key hi, holder (absolute index), tie
+  int4 *JA, *JB;        // pointer-jumping state (ancestor, sum, prefix maximum, -), two copies
+  int *frontier;        // [2][n_segs] first anchor whose decision changed in iteration t (t & 1), INT_MAX = none
+  unsigned char *TIE;   // per anchor: the last evaluation found equal smallest priorities inside the range
+  int *seg_flag;        // per segment: ChainEngine::INNER when a walk exceeded the device limits
+  int *changed;         // [kMaxIter + 2] decisions changed per iteration ([0] preset to 1)
+  int n, n_segs;
+};
+
+constexpr int kMaxIter = 64;        // iterations before the segments that still change go to the host arbiter
+constexpr int kParWarps = 4;        // warps (= anchors in flight) per CTA of the decide kernel
+constexpr int kMarkBits = 4096;     // anchors of a near window that can carry a walk mark
+
+__device__ __forceinline__ unsigned long long pri_key(int f, int x, int y, double half_pen) {
+  const double sum = __dadd_rn((double)f, __dmul_rn(half_pen, (double)(x + y)));  // lchain.c:285: pri = -sum
+  const long long b = __double_as_longlong(sum) ^ (long long)0x8000000000000000ull;
+  return b < 0 ? ~(unsigned long long)b : (unsigned long long)b | 0x8000000000000000ull;  // same order, unsigned
+}
+
+// iteration 0: every anchor whose left neighbour is visible and gives a positive link starts out chained to it
+__global__ void par_init_kernel(ParArgs A, const ChainDevParams *__restrict__ Pp) {
+  const int bw = Pp->bw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
+    const int4 aux = A.AUX[i];
+    int p = -1, g = A.QS[i];
+    const int link = aux.w;
+    (void)bw;
+    if (aux.x == i && aux.y < i && (link & 1) && (link >> 2) > 0) p = i - 1, g = link >> 2;
+    A.Pn[i] = p, A.G[i] = g, A.P[i] = -2, A.TIE[i] = 0;
+  }
+}
+
+// start of the propagation of iteration t: anchors below their segment's frontier keep their final values
+__global__ void par_jump_init_kernel(ParArgs A, int t) {
+  if (t > 0 && A.changed[t] == 0) return;  // nothing changed in this iteration: the iterate is the fixed point
+  const int *fr = A.frontier + (size_t)(t & 1) * A.n_segs;
+  int *fr_next = A.frontier + (size_t)((t + 1) & 1) * A.n_segs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
+    if (i < A.n_segs) fr_next[i] = INT32_MAX;
+    const int sg = A.SEG[i];
+    if (t > 0 && i < fr[sg]) A.JA[i] = make_int4(-1, A.F[i], A.V[i], 0);
+    else {
+      const int g = A.G[i];
+      A.JA[i] = make_int4(A.Pn[i], g, g, 0);
+    }
+  }
+}
+
+// one round of pointer jumping: F[i] = F[J] + S, V[i] = max(V[J], F[J] + D)
+__global__ void par_jump_kernel(ParArgs A, int t, int flip) {
+  if (t > 0 && A.changed[t] == 0) return;  // nothing changed in this iteration: the iterate is the fixed point
+  const int4 *src = flip ? A.JB : A.JA;
+  int4 *dst = flip ? A.JA : A.JB;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
+    int4 a = src[i];
+    if (a.x >= 0) {
+      const int4 b = src[a.x];
+      a.z = max(b.z, b.y + a.z), a.y += b.y, a.x = b.x;
+    }
+    dst[i] = a;
+  }
+}
+
+// end of iteration t: scores, peak scores, priority keys and the block minima the next decide reads
+__global__ void par_finalize_kernel(ParArgs A, const ChainDevParams *__restrict__ Pp, int t, int flip) {
+  if (t > 0 && A.changed[t] == 0) return;  // nothing changed in this iteration: the iterate is the fixed point
+  const double half_pen = Pp->half_pen;
+  const int4 *src = flip ? A.JB : A.JA;
+  const int lane = threadIdx.x & 31;
+  const int n32 = (A.n + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < A.n) {
+      const int4 a = src[i];
+      A.F[i] = a.y, A.V[i] = a.z, A.P[i] = A.Pn[i];
+      key = pri_key(a.y, A.X[i], A.Y[i], half_pen);
+      A.KEY[i] = key;
+    }
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? (unsigned)key : 0xffffffffu);
+    const unsigned long long mk = (unsigned long long)mh << 32 | ml;
+    const unsigned hm = __ballot_sync(FULL, key == mk && i < A.n);
+    if (lane == 0) A.BM[i >> 5] = make_int4((int)ml, (int)mh, hm ? i + __ffs(hm) - 1 : -1, __popc(hm) > 1);
+  }
+}
+
+// The decision of every anchor from the previous iterate (lchain.c:313-351), one warp per anchor.
+__global__ void __launch_bounds__(kParWarps * 32) par_decide_kernel(ParArgs A, const ChainDevParams *__restrict__ Pp, int t) {
+  if (A.changed[t - 1] == 0) return;  // the fixed point was reached
+  __shared__ unsigned long long s_keys[kParWarps][ChainEngine::kInnerCap];
+  __shared__ unsigned s_mark[kParWarps][kMarkBits / 32];
+  const ChainDevParams P = *Pp;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long *keys = s_keys[wid];
+  unsigned *mark = s_mark[wid];
+  const int max_dist = P.max_dist, max_dist_inner = P.max_dist_inner, bw = P.bw, max_skip = P.max_skip;
+  const float pen_gap = P.pen_gap, pen_skip = P.pen_skip;
+  const int *fr_prev = A.frontier + (size_t)((t - 1) & 1) * A.n_segs;
+  int *fr_cur = A.frontier + (size_t)(t & 1) * A.n_segs;
+  const int *__restrict__ X = A.X, *__restrict__ Y = A.Y, *__restrict__ F = A.F, *__restrict__ PO = A.P;
+  const uint8_t *__restrict__ QS = A.QS;
+  const unsigned long long *__restrict__ KEY = A.KEY;
+  int n_changed = 0;
+  for (int i = blockIdx.x * kParWarps + wid; i < A.n; i += gridDim.x * kParWarps) {
+    const int sgi = A.SEG[i];
+    if (t > 1 && i <= fr_prev[sgi]) continue;  // final already (its inputs did not change in the last iteration)
+    const int4 aux = A.AUX[i];
+    const int i0 = aux.x, st = aux.y, sti = aux.z, link = aux.w;
+    const int xi = X[i], yi = Y[i], qsi = QS[i], ylo = yi - max_dist;
+    const int qbase = A.segs[sgi].z;
+    int max_f = qsi, max_j = -1;
+    int j = -1;
+    bool tie_here = false;
+    if (st < i0) {
+      // ---- smallest key of the whole window from block minima and the ragged ends ----
+      const int b0 = (st + 31) >> 5, b1 = i0 >> 5;
+      const bool blocks = b0 < b1;
+      const int nh = blocks ? (b0 << 5) - st : i0 - st, nb = blocks ? b1 - b0 : 0, nt = blocks ? i0 - (b1 << 5) : 0;
+      unsigned long long uk = ~0ull;
+      int uj = -1;
+      bool utie = false;
+      for (int c = lane; c < nh + nb + nt; c += 32) {
+        unsigned long long k;
+        int h;
+        bool tf = false;
+        if (c < nh) h = st + c, k = KEY[h];
+        else if (c < nh + nb) {
+          const int4 bm = A.BM[b0 + c - nh];
+          k = (unsigned long long)(unsigned)bm.y << 32 | (unsigned)bm.x, h = bm.z, tf = bm.w != 0;
+        } else h = (b1 << 5) + (c - nh - nb), k = KEY[h];
+        if (k < uk) uk = k, uj = h, utie = tf;
+        else if (k == uk) utie = true;
+      }
+      bool fast;
+      {
+        const unsigned hi = (unsigned)(uk >> 32);
+        const unsigned mh = __reduce_min_sync(FULL, hi);
+        const unsigned ml = __reduce_min_sync(FULL, hi == mh ? (unsigned)uk : 0xffffffffu);
+        const unsigned long long gk = (unsigned long long)mh << 32 | ml;
+        const unsigned hm = __ballot_sync(FULL, uj >= 0 && uk == gk);
+        const bool gt = __popc(hm) > 1 || __any_sync(FULL, utie && uk == gk);
+        const int gj = hm ? __shfl_sync(FULL, uj, __ffs(hm) - 1) : -1;
+        fast = !gt && gj >= 0;
+        if (fast) {
+          const int yh = Y[gj];
+          if (yh > ylo && (yh < yi || (yh == yi && gj == qbase))) j = gj;
+          else fast = false;
+        }
+      }
+      if (!fast) {  // range-filtered scan of the window, eight independent loads in flight
+        unsigned long long bk = ~0ull;
+        int bj = -1;
+        bool tie = false;
+#pragma unroll 1
+        for (int jb = st + lane; jb < i0 + lane; jb += 32 * kScanUnroll) {
+          int yv[kScanUnroll];
+          unsigned long long kv[kScanUnroll];
+#pragma unroll
+          for (int u = 0; u < kScanUnroll; ++u) {
+            const int jc = min(jb + 32 * u, i0 - 1);
+            yv[u] = Y[jc], kv[u] = KEY[jc];
+          }
+#pragma unroll
+          for (int u = 0; u < kScanUnroll; ++u) {
+            const int jj = jb + 32 * u, y = yv[u];
+            const bool ok = jj < i0 && y > ylo && (y < yi || (y == yi && jj == qbase));
+            const unsigned long long k = ok ? kv[u] : ~0ull;
+            tie = k < bk ? false : (ok && k == bk ? true : tie);
+            bj = k < bk ? jj : bj;
+            bk = k < bk ? k : bk;
+          }
+        }
+        const unsigned hi = (unsigned)(bk >> 32);
+        const unsigned mh = __reduce_min_sync(FULL, hi);
+        const unsigned ml = __reduce_min_sync(FULL, hi == mh ? (unsigned)bk : 0xffffffffu);
+        const unsigned long long gk = (unsigned long long)mh << 32 | ml;
+        if (gk != ~0ull) {
+          const unsigned hm = __ballot_sync(FULL, bj >= 0 && bk == gk);
+          tie_here = __popc(hm) > 1 || __any_sync(FULL, tie && bk == gk);
+          // a lane's bj is its first (lowest) holder; the lowest lane does not hold the lowest index, so take the minimum
+          j = __reduce_min_sync(FULL, (bj >= 0 && bk == gk) ? bj : INT32_MAX);
+        }
+      }
+    }
+    bool overflow = false;
+    if (j >= 0) {
+      bool exact, wok;
+      int sc;
+      if (j == i - 1) sc = F[j] + (link >> 2), exact = link & 2, wok = link & 1;  // scored by the prep kernel
+      else {
+        int width;
+        sc = F[j] + link_score_dev(xi, yi, X[j], Y[j], QS[j], pen_gap, pen_skip, exact, width);
+        wok = width <= bw;
+      }
+      if (wok && sc > max_f) max_f = sc, max_j = j;
+      if (!exact && max_dist_inner > 0 && i0 > sti && yi > 0) {
+        // near neighbourhood (:319-348): members of [sti, i0) with query position in [yi - max_dist_inner, yi - 1],
+        // visited in descending (query position, index) order
+        const int y_hi = yi - 1, y_lo = yi - max_dist_inner;
+        int cnt = 0;
+        if (i0 - sti > kMarkBits) overflow = true;
+#pragma unroll 1
+        for (int base = i0 - 1; base >= sti && !overflow; base -= 32) {
+          const int j2 = base - lane;
+          bool c = false;
+          int y = 0;
+          if (j2 >= sti) y = Y[j2], c = y >= y_lo && y <= y_hi;
+          const unsigned m = __ballot_sync(FULL, c);
+          const int pos = cnt + __popc(m & lt_mask);
+          if (c && pos < ChainEngine::kInnerCap) keys[pos] = (unsigned long long)(unsigned)y << 32 | (unsigned)j2;
+          cnt += __popc(m);
+        }
+        if (cnt > ChainEngine::kInnerCap) overflow = true;
+        if (!overflow) {
+          for (int k = lane; k < (i0 - sti + 31) / 32; k += 32) mark[k] = 0;
+          __syncwarp();
+          bool unsorted = false;
+#pragma unroll 1
+          for (int k = lane; k + 1 < cnt; k += 32) unsorted |= keys[k] < keys[k + 1];
+          if (__any_sync(FULL, unsorted)) {
+            int n2 = 32;
+            while (n2 < cnt) n2 <<= 1;
+            for (int k = cnt + lane; k < n2; k += 32) keys[k] = 0;  // smallest: pads end up behind every member
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 2; k <= n2; k <<= 1)
+#pragma unroll 1
+              for (int d = k >> 1; d > 0; d >>= 1) {
+#pragma unroll 1
+                for (int w = lane; w < n2; w += 32) {
+                  const int u = w ^ d;
+                  if (u > w) {
+                    const unsigned long long ka = keys[w], kb = keys[u];
+                    const bool desc = (w & k) == 0;
+                    if (desc ? ka < kb : ka > kb) keys[w] = kb, keys[u] = ka;
+                  }
+                }
+                __syncwarp();
+              }
+          }
+          int n_skip = 0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const int k = c0 + lane;
+            int j2 = -1, sc2 = INT32_MIN;
+            bool ok = false;
+            if (k < cnt) {
+              j2 = (int)(unsigned)keys[k];
+              bool ex2;
+              int w2;
+              sc2 = F[j2] + link_score_dev(xi, yi, X[j2], Y[j2], QS[j2], pen_gap, pen_skip, ex2, w2);
+              ok = w2 <= bw;
+              const int pj = PO[j2];
+              // "a predecessor of something already seen in this walk" (:344); one outside the near window is never visited
+              if (ok && pj >= sti) atomicOr(&mark[(pj - sti) >> 5], 1u << ((pj - sti) & 31));
+            }
+            __syncwarp();
+            // every writer of an anchor's mark sits earlier in the visiting order (a predecessor has a smaller query position)
+            const bool marked = ok && (mark[(j2 - sti) >> 5] >> ((j2 - sti) & 31) & 1u);
+            int incl = INT32_MIN;
+            unsigned um = 0, im;
+            if (__any_sync(FULL, ok && sc2 > max_f)) {
+              incl = ok ? sc2 : INT32_MIN;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl = max(incl, o);
+              }
+              int excl = __shfl_up_sync(FULL, incl, 1);
+              if (lane == 0) excl = INT32_MIN;
+              excl = max(excl, max_f);
+              const bool upd = ok && sc2 > excl;
+              um = __ballot_sync(FULL, upd), im = __ballot_sync(FULL, ok && !upd && marked);
+            } else im = __ballot_sync(FULL, marked);
+            int brk = -1;
+            if (um == 0) {
+              const int room = max_skip - n_skip;
+              if (__popc(im) > room) {
+                unsigned m2 = im;
+                for (int r = 0; r < room; ++r) m2 &= m2 - 1;
+                brk = __ffs(m2) - 1, n_skip = max_skip + 1;
+              } else n_skip += __popc(im);
+            } else {
+              unsigned evs = um | im;
+              while (evs) {
+                const int b = __ffs(evs) - 1;
+                evs &= evs - 1;
+                if (um >> b & 1) {
+                  if (n_skip > 0) --n_skip;
+                } else if (++n_skip > max_skip) {
+                  brk = b;
+                  break;
+                }
+              }
+            }
+            const int last = brk >= 0 ? brk : 31;
+            const int best = um ? max(max_f, __shfl_sync(FULL, incl, last)) : max_f;
+            if (best > max_f) {
+              const unsigned wm = __ballot_sync(FULL, ok && sc2 == best);
+              max_j = __shfl_sync(FULL, j2, __ffs(wm) - 1);
+              max_f = best;
+            }
+            if (brk >= 0) break;
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      A.TIE[i] = tie_here ? 1 : 0;
+      if (overflow) atomicMax(&A.seg_flag[sgi], (int)ChainEngine::INNER);
+      A.Pn[i] = max_j;
+      A.G[i] = max_j >= 0 ? max_f - F[max_j] : max_f;
+      if (max_j != PO[i]) {
+        atomicMin(&fr_cur[sgi], i);
+        ++n_changed;
+      }
+    }
+  }
+  if (lane == 0 && n_changed) atomicAdd(&A.changed[t], n_changed);
+}
+
+// results in the caller's terms: predecessors relative to the query's first anchor, ties folded into the segment flags
+__global__ void par_export_kernel(ParArgs A, int t_last) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
+    const int sg = A.SEG[i];
+    const int p = A.P[i];
+    A.PX[i] = p >= 0 ? p - A.segs[sg].z : -1;
+    if (A.TIE[i]) atomicMax(&A.seg_flag[sg], (int)ChainEngine::TIE);
+    // a segment whose decisions still changed in the last iteration that ran has not converged: the host fills it
+    if (A.frontier[(size_t)(t_last & 1) * A.n_segs + sg] != INT32_MAX && i == A.segs[sg].x) atomicMax(&A.seg_flag[sg], (int)ChainEngine::WINDOW);
+  }
+}
+
 }  // namespace
 
 void trace_attach_chain(PgmmCtaTraceRec *buf, unsigned long long *cnt, unsigned long long cap) { trace::attach(buf, cnt, cap); }
@@ -458,17 +824,20 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
   for (const ChainFillJob &j : jobs) n_total += (size_t)j.n, n_segs += j.segs.size();
   if (n_total == 0) return;
   if (n_total >= (size_t)INT32_MAX) PGMM_FATAL("chain fill: %zu anchors in one batch exceed the 31-bit index space", n_total);
+  static const bool serial = getenv("PGMM_K4_SERIAL") != nullptr && atoi(getenv("PGMM_K4_SERIAL")) != 0;
   ChainDevParams P;
   P.max_dist = cp.max_dist < cp.bw ? cp.bw : cp.max_dist;
   P.max_dist_inner = (cp.max_dist_inner <= 0 || cp.max_dist_inner >= P.max_dist) ? 0 : cp.max_dist_inner;
   P.bw = cp.bw, P.max_skip = cp.max_chn_skip, P.cap = cp.cap_rmq_size, P.pen_gap = cp.pen_gap, P.pen_skip = cp.pen_skip;
   P.zero = 0, P.half_pen = 0.5 * (double)cp.pen_gap;
 
-  // staging: anchors query after query; segments longest first so that the long ones start first
+  // staging: anchors query after query.  Segment list 1 (serial kernel: longest first so that the long ones start
+  // first), the kernels' parameter block, the segment starts in ascending order, segment list 2 (ascending, what SEG[]
+  // indexes: start, end, first anchor of the query)
   U128 *ha = h_a_.ensure(n_total);
-  // behind the segment list ride the kernels' parameter block and the segment starts in ascending order
   const size_t n_start4 = (n_segs + 3) / 4;
-  int4 *hs = h_segs_.ensure(n_segs + 3 + n_start4);
+  const size_t o_par = n_segs, o_starts = n_segs + 3, o_asc = n_segs + 3 + n_start4, n_hs = o_asc + n_segs;
+  int4 *hs = h_segs_.ensure(n_hs);
   static_assert(sizeof(ChainDevParams) <= 3 * sizeof(int4), "parameter block");
   struct Ref {
     int job, seg;
@@ -478,40 +847,125 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
   order.reserve(n_segs);
   std::vector<size_t> base(jobs.size());
   size_t off = 0;
+  int64_t seg_max = 1;
   for (size_t q = 0; q < jobs.size(); ++q) {
     ChainFillJob &j = jobs[q];
     base[q] = off;
     if (j.n) memcpy(ha + off, j.a, (size_t)j.n * sizeof(U128));
     off += (size_t)j.n;
     j.redo.assign(j.segs.size(), 0);
-    for (size_t k = 0; k < j.segs.size(); ++k) order.push_back(Ref{(int)q, (int)k, j.segs[k].end - j.segs[k].start});
+    for (size_t k = 0; k < j.segs.size(); ++k) {
+      order.push_back(Ref{(int)q, (int)k, j.segs[k].end - j.segs[k].start});
+      seg_max = std::max(seg_max, j.segs[k].end - j.segs[k].start);
+    }
   }
-  std::stable_sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.len > b.len; });
+  std::vector<Ref> asc = order;  // (query, segment) in ascending anchor order
+  if (serial) std::stable_sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.len > b.len; });
   for (size_t k = 0; k < n_segs; ++k) {
     const Ref &r = order[k];
     const ChainSeg &sg = jobs[r.job].segs[r.seg];
     hs[k] = make_int4((int)(base[r.job] + sg.start), (int)(base[r.job] + sg.end), (int)base[r.job], 0);
+    const Ref &ra = asc[k];
+    const ChainSeg &sa = jobs[ra.job].segs[ra.seg];
+    hs[o_asc + k] = make_int4((int)(base[ra.job] + sa.start), (int)(base[ra.job] + sa.end), (int)base[ra.job], 0);
   }
   d_a_.ensure(n_total), d_x_.ensure(n_total), d_y_.ensure(n_total), d_qs_.ensure(n_total), d_f_.ensure(3 * n_total);
-  d_segs_.ensure(n_segs + 3 + n_start4), d_flag_.ensure(n_segs), d_aux_.ensure(n_total);
-  memcpy(hs + n_segs, &P, sizeof(P));
+  d_segs_.ensure(n_hs), d_flag_.ensure(n_segs), d_aux_.ensure(n_total);
+  memcpy(hs + o_par, &P, sizeof(P));
   {
-    int *starts = (int *)(hs + n_segs + 3);
+    int *starts = (int *)(hs + o_starts);
     size_t k = 0;
     for (size_t q = 0; q < jobs.size(); ++q)
       for (const ChainSeg &sg : jobs[q].segs) starts[k++] = (int)(base[q] + sg.start);  // ascending by construction
   }
   int32_t *dF = d_f_.p, *dP = d_f_.p + n_total, *dV = d_f_.p + 2 * n_total;
   PGMM_CUDA(cudaMemcpyAsync(d_a_.p, ha, n_total * sizeof(U128), cudaMemcpyHostToDevice, st));
-  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, (n_segs + 3 + n_start4) * sizeof(int4), cudaMemcpyHostToDevice, st));
+  PGMM_CUDA(cudaMemcpyAsync(d_segs_.p, hs, n_hs * sizeof(int4), cudaMemcpyHostToDevice, st));
   PGMM_CUDA(cudaEventRecord(ev0_, st));
-  const ChainDevParams *dP_ = (const ChainDevParams *)(d_segs_.p + n_segs);
-  chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, (const int *)(d_segs_.p + n_segs + 3), (int)n_segs, dP_,
-                                                                       d_x_.p, d_y_.p, d_qs_.p, d_aux_.p);
-  // PGMM_K4_SMEM_KB: shared memory a fill warp asks for at least (a large value keeps other CTAs off its SM)
-  static const size_t fill_smem = getenv("PGMM_K4_SMEM_KB") ? std::max(kFillSmem, (size_t)atoi(getenv("PGMM_K4_SMEM_KB")) * 1024) : kFillSmem;
-  chain_fill_kernel<<<(unsigned)n_segs, 32, fill_smem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_aux_.p, d_segs_.p, dP_, dF, dP, dV, d_flag_.p);
-  PGMM_CUDA(cudaGetLastError());
+  const ChainDevParams *dP_ = (const ChainDevParams *)(d_segs_.p + o_par);
+  int launches = 0, iters = 0;
+  if (serial) {
+    chain_prep_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n_total, (const int *)(d_segs_.p + o_starts), (int)n_segs, dP_,
+                                                                         d_x_.p, d_y_.p, d_qs_.p, d_aux_.p, nullptr);
+    // PGMM_K4_SMEM_KB: shared memory a fill warp asks for at least (a large value keeps other CTAs off its SM)
+    static const size_t fill_smem = getenv("PGMM_K4_SMEM_KB") ? std::max(kFillSmem, (size_t)atoi(getenv("PGMM_K4_SMEM_KB")) * 1024) : kFillSmem;
+    chain_fill_kernel<<<(unsigned)n_segs, 32, fill_smem, st>>>(d_x_.p, d_y_.p, d_qs_.p, d_aux_.p, d_segs_.p, dP_, dF, dP, dV, d_flag_.p);
+    PGMM_CUDA(cudaGetLastError());
+    launches = 2;
+  } else {
+    // ---- K4p: parallel fixed-point iteration ----
+    const size_t n = n_total, nb = (n + 31) / 32;
+    // one slab: SEG, P, Pn, G (int n each) | KEY (u64 n) | BM (int4 nb) | JA, JB (int4 n each) | frontier (2 n_segs) |
+    // changed (kMaxIter + 2) | TIE (n bytes)
+    const size_t words = 4 * n + 2 * n + 4 * nb + 8 * n + 2 * n_segs + (size_t)kMaxIter + 2 + (n + 3) / 4 + 64;
+    int *slab = d_par_.ensure(words);
+    ParArgs A;
+    A.X = d_x_.p, A.Y = d_y_.p, A.QS = d_qs_.p, A.AUX = d_aux_.p, A.segs = d_segs_.p + o_asc;
+    size_t w = 0;
+    int *SEG = slab + w;
+    w += n;
+    A.SEG = SEG, A.P = slab + w, w += n, A.Pn = slab + w, w += n, A.G = slab + w, w += n;
+    w = (w + 3) & ~(size_t)3;
+    A.KEY = (unsigned long long *)(slab + w), w += 2 * n;
+    w = (w + 3) & ~(size_t)3;
+    A.BM = (int4 *)(slab + w), w += 4 * nb;
+    A.JA = (int4 *)(slab + w), w += 4 * n;
+    A.JB = (int4 *)(slab + w), w += 4 * n;
+    A.frontier = slab + w, w += 2 * n_segs;
+    A.changed = slab + w, w += (size_t)kMaxIter + 2;
+    A.TIE = (unsigned char *)(slab + w);
+    A.F = dF, A.V = dV, A.PX = dP, A.seg_flag = d_flag_.p;
+    A.n = (int)n, A.n_segs = (int)n_segs;
+    int rounds = 0;
+    while ((int64_t(1) << rounds) < seg_max) ++rounds;  // pointer-jumping rounds: 2^rounds >= longest possible chain
+    const unsigned g1 = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+    const unsigned gd = (unsigned)std::min<size_t>((n + kParWarps - 1) / kParWarps, 148 * 32);
+    chain_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a_.p, (int)n, (const int *)(d_segs_.p + o_starts), (int)n_segs, dP_, d_x_.p, d_y_.p,
+                                                                   d_qs_.p, d_aux_.p, SEG);
+    PGMM_CUDA(cudaMemsetAsync(d_flag_.p, 0, n_segs * sizeof(int), st));
+    PGMM_CUDA(cudaMemsetAsync(A.changed, 0, ((size_t)kMaxIter + 2) * sizeof(int), st));
+    PGMM_CUDA(cudaMemsetAsync(A.frontier, 0x7f, 2 * n_segs * sizeof(int), st));
+    {
+      const int one = 1;  // changed[0] = 1: the first decide always runs
+      h_changed_.ensure(kMaxIter + 2)[0] = one;
+      PGMM_CUDA(cudaMemcpyAsync(A.changed, h_changed_.p, sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    par_init_kernel<<<g1, 256, 0, st>>>(A, dP_);
+    launches += 2;
+    const auto propagate = [&](int t) {
+      par_jump_init_kernel<<<g1, 256, 0, st>>>(A, t);
+      for (int r = 0; r < rounds; ++r) par_jump_kernel<<<g1, 256, 0, st>>>(A, t, r & 1);
+      par_finalize_kernel<<<g1, 256, 0, st>>>(A, dP_, t, rounds & 1);
+      launches += rounds + 2;
+    };
+    propagate(0);
+    int t = 0, t_last = 0;
+    int *hc = h_changed_.p;
+    while (t < kMaxIter) {
+      const int t_to = std::min(kMaxIter, t + (t == 0 ? 8 : 8));
+      for (int k = t + 1; k <= t_to; ++k) {
+        par_decide_kernel<<<gd, kParWarps * 32, 0, st>>>(A, dP_, k);
+        ++launches;
+        propagate(k);
+      }
+      PGMM_CUDA(cudaGetLastError());
+      PGMM_CUDA(cudaMemcpyAsync(hc, A.changed, ((size_t)kMaxIter + 2) * sizeof(int), cudaMemcpyDeviceToHost, st));
+      PGMM_CUDA(cudaStreamSynchronize(st));
+      t_last = t_to;
+      bool done = false;
+      for (int k = t + 1; k <= t_to; ++k)
+        if (hc[k] == 0) {
+          t_last = k, done = true;
+          break;
+        }
+      t = t_to;
+      if (done) break;
+    }
+    iters = t_last;
+    par_export_kernel<<<g1, 256, 0, st>>>(A, t_last);
+    ++launches;
+    PGMM_CUDA(cudaGetLastError());
+  }
   PGMM_CUDA(cudaEventRecord(ev1_, st));
   int32_t *hfpv = h_fpv_.ensure(3 * n_total);
   int32_t *hflag = h_flag_.ensure(n_segs);
@@ -523,16 +977,17 @@ void ChainEngine::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, cu
     j.f = hfpv + base[q], j.p = hfpv + n_total + base[q], j.v = hfpv + 2 * n_total + base[q];
   }
   uint64_t redo_segs = 0, redo_anchors = 0;
+  const std::vector<Ref> &flag_order = serial ? order : asc;
   for (size_t k = 0; k < n_segs; ++k)
     if (hflag[k] != DONE) {
-      jobs[order[k].job].redo[order[k].seg] = (uint8_t)hflag[k];
-      ++redo_segs, redo_anchors += (uint64_t)order[k].len;
+      jobs[flag_order[k].job].redo[flag_order[k].seg] = (uint8_t)hflag[k];
+      ++redo_segs, redo_anchors += (uint64_t)flag_order[k].len;
     }
   if (stats) {
     float ms = 0;
     PGMM_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats->anchors += n_total, stats->segments += n_segs, stats->redo_segments += redo_segs, stats->redo_anchors += redo_anchors;
-    stats->launches += 2, stats->kernel_ms += ms;
+    stats->launches += launches, stats->kernel_ms += ms, stats->iterations += (uint64_t)iters, stats->batches += 1;
   }
 }
 

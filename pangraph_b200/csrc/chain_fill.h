@@ -30,6 +30,8 @@ class ChainEngine {
   DevBuf<int32_t> d_x_, d_y_, d_f_, d_flag_;
   DevBuf<uint8_t> d_qs_;
   DevBuf<int4> d_segs_, d_aux_;
+  DevBuf<int> d_par_;      // state of the parallel fixed-point fill (K4p)
+  PinBuf<int> h_changed_;
   PinBuf<U128> h_a_;
   PinBuf<int32_t> h_fpv_, h_flag_;
   PinBuf<int4> h_segs_;

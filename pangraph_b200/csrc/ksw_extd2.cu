@@ -991,7 +991,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     // anti-diagonal for everything but the small fills), shared memory follows the length of the target ----
     constexpr int kClasses = Impl::kClasses;
     static const int max_nt_tier = getenv("PGMM_MAX_NT_TIER") ? atoi(getenv("PGMM_MAX_NT_TIER")) : 4;
-    std::vector<int> cls[kClasses];
+    std::vector<int> cls[kClasses], generic;
     size_t cls_smem[kClasses] = {};
     KswJob *hj = m.h_jobs.ensure(nw);
     for (size_t k = 0; k < nw; ++k) {  // jobs of this wave are renumbered 0..nw-1 on the device
@@ -1026,8 +1026,9 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       if (sm_tier < 3) cls_smem[c] = std::max(cls_smem[c], sb);
       const uint64_t band_cells = (uint64_t)std::min<int64_t>((int64_t)jobs[i].qlen * jobs[i].tlen,
                                                               (int64_t)geo[i].n_row * std::min(geo[i].n_col16, geo[i].T));
-      res.cells += band_cells;
-      res.fam_cells[0] += band_cells, res.fam_bases[0] += (uint64_t)jobs[i].qlen + jobs[i].tlen;
+      res.cells += band_cells;  // asked for (upper bound: an extension that z-drops stops early)
+      res.fam_bases[0] += (uint64_t)jobs[i].qlen + jobs[i].tlen;
+      generic.push_back((int)k);
     }
     int *hid = m.h_ids.ensure(nw);
     size_t cls_off[kClasses], nid = 0;
@@ -1146,6 +1147,17 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       const int i = order[pos + k];
       res.out[i] = ho[k];
       res.cig_start[i] = base + ho[k].cig_pos;
+    }
+    // K5 generic: the in-band cells of the anti-diagonals that were actually evaluated (ksw2_extd2_sse.c:137-147)
+    for (int k : generic) {
+      const KswJob &j = jobs[order[pos + k]];
+      const int w = j.w < 0 ? std::max(j.qlen, j.tlen) : j.w, nd = std::min(ho[k].n_diag, j.qlen + j.tlen - 1);
+      uint64_t c = 0;
+      for (int r = 0; r < nd; ++r) {
+        const int st = std::max(std::max(0, r - j.qlen + 1), (r - w + 1) >> 1), en = std::min(std::min(j.tlen - 1, r), (r + w) >> 1);
+        if (en >= st) c += (uint64_t)(en - st + 1);
+      }
+      res.fam_cells[0] += c;
     }
     pos = end;
   }

@@ -32,6 +32,7 @@ struct Stats {
   uint64_t fam_cells[3] = {0, 0, 0}, fam_bases[3] = {0, 0, 0}, fam_launches[3] = {0, 0, 0};
   double t_chain_sort = 0, t_chain_fill = 0, t_chain_rest = 0, chain_kernel_ms = 0;
   uint64_t chain_anchors = 0, chain_segments = 0, chain_redo_segments = 0, chain_redo_anchors = 0, chain_launches = 0;
+  uint64_t chain_iterations = 0, chain_batches = 0;
 };
 Stats g_stats;
 std::mutex g_stats_mu;
@@ -232,6 +233,7 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   g_stats.chain_kernel_ms += be.stats.chain.kernel_ms, g_stats.chain_anchors += be.stats.chain.anchors;
   g_stats.chain_segments += be.stats.chain.segments, g_stats.chain_redo_segments += be.stats.chain.redo_segments;
   g_stats.chain_redo_anchors += be.stats.chain.redo_anchors, g_stats.chain_launches += (uint64_t)be.stats.chain.launches;
+  g_stats.chain_iterations += be.stats.chain.iterations, g_stats.chain_batches += be.stats.chain.batches;
   for (int i = 0; i < n; ++i) g_stats.bases_mapped += lens[i];
 }
 
@@ -377,9 +379,10 @@ void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *cons
 // stats: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells [6] dp_waves [7] bases_mapped
 //        [8] bases_indexed [9] batches [10] kernel launches (all engines) ... [33..41] chaining: sort ms, fill ms, rest ms,
 //        fill kernel ms, anchors, segments, segments redone on the host, their anchors, launches
+//        [42] fixed-point iterations of the chain fill summed over its batches [43] those batches
 void pgmm_get_stats(double *out, int n, int reset) {
   std::lock_guard<std::mutex> sl(g_stats_mu);
-  const double v[42] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+  const double v[44] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
                         (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
                         (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches + (double)g_stats.chain_launches,
                         g_stats.t_encode, g_stats.t_seed, g_stats.t_chain, g_stats.t_dp, g_stats.t_stitch, g_stats.t_final,
@@ -390,8 +393,9 @@ void pgmm_get_stats(double *out, int n, int reset) {
                         g_stats.fam_ms[2], (double)g_stats.fam_cells[2], (double)g_stats.fam_bases[2], (double)g_stats.fam_launches[2],
                         g_stats.t_chain_sort, g_stats.t_chain_fill, g_stats.t_chain_rest, g_stats.chain_kernel_ms,
                         (double)g_stats.chain_anchors, (double)g_stats.chain_segments, (double)g_stats.chain_redo_segments,
-                        (double)g_stats.chain_redo_anchors, (double)g_stats.chain_launches};
-  for (int i = 0; i < n && i < 42; ++i) out[i] = v[i];
+                        (double)g_stats.chain_redo_anchors, (double)g_stats.chain_launches,
+                        (double)g_stats.chain_iterations, (double)g_stats.chain_batches};
+  for (int i = 0; i < n && i < 44; ++i) out[i] = v[i];
   if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0, pgmm::DevicePool::misses() = 0;
   if (reset) g_stats = Stats();
 }
