@@ -70,6 +70,14 @@ __device__ __forceinline__ bool band(int r, int qlen, int tlen, int w, int &st0,
   return st <= en;
 }
 
+// GPU-side time span of a wave: slot 1 of the wave's counter block = earliest CTA start, slot 2 = latest CTA end
+// (%globaltimer, ns); slots 3 / 4 are stamped by marker kernels on the wave's main stream (PGMM_TRACE only)
+__device__ __forceinline__ void span_begin(unsigned long long *counter) {
+  if (threadIdx.x == 0) atomicMin(counter + 1, trace::now());
+}
+__device__ __forceinline__ void span_end(unsigned long long *counter) { atomicMax(counter + 2, trace::now()); }
+__global__ void stamp_kernel(unsigned long long *slot) { *slot = trace::now(); }
+
 struct EzState {
   int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end;
 };
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const K
   extern __shared__ uint32_t dyn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot_id = blockIdx.x * kFillWarps + warp;
+  span_begin(cig_counter);
   if (slot_id >= n_jobs) return;  // whole warp leaves together
   const int jid = job_ids[slot_id];
   const KswJob job = jobs[jid];
@@ -362,6 +371,7 @@ __global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const K
     const unsigned long long tr1 = trace::begin();
     finish_job(job, jid, ez, n_row, /*w=*/tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed, cig_counter, outs);
     if (warp == 0) trace::emit(1, tr0, tr1, (unsigned)n_row);
+    span_end(cig_counter);
   }
 }
 
@@ -395,6 +405,7 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
   const int jid = job_ids[blockIdx.x];
   const KswJob job = jobs[jid];
   const unsigned long long tr0 = trace::begin();
+  span_begin(cig_counter);
   const int qlen = job.qlen, tlen = job.tlen;
   int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
   if (q2 + e2 < q + e) {
@@ -595,6 +606,7 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
     finish_job(job, jid, ez, r_done + 1, tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed,
                cig_counter, outs);
     trace::emit(EXACT ? 3 : 2, tr0, tr1, (unsigned)(r_done + 1));
+    span_end(cig_counter);
   }
 }
 
@@ -611,6 +623,7 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
   const int jid = job_ids[blockIdx.x];  // index within this wave
   const KswJob job = jobs[jid];
   const unsigned long long tr0 = trace::begin();
+  span_begin(cig_counter);
   const int qlen = job.qlen, tlen = job.tlen, flag = job.flag;
   int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
   if (q2 + e2 < q + e) {  // ksw2_extd2_sse.c:73
@@ -842,6 +855,7 @@ __global__ void __launch_bounds__(NT) ksw_extd2_kernel(const KswJob *__restrict_
     finish_job(job, jid, ez, r_done + 1, w, /*abs_layout=*/false, stride, P, (const uint8_t *)TQ32, (const uint8_t *)QR32 + 4, sc,
                cig_arena, cig_packed, cig_counter, outs);
     trace::emit(4, tr0, tr1, (unsigned)(r_done + 1));
+    span_end(cig_counter);
   }
 }
 
@@ -899,6 +913,18 @@ KswGeom ksw_geometry(int qlen, int tlen, int w, int flag) {
 struct KswEngine::Impl {
   static constexpr int kClasses = 29;  // 5 CTA widths x 4 state-size tiers, K5a (20), K5b: 4 widths x {approximate, exact} (21..28)
   cudaStream_t cls_stream[kClasses] = {};
+  int n_streams = kClasses, prio_lo = 0, prio_hi = 0;  // priorities: numerically lower = more urgent
+  // PGMM_CLASS_STREAMS=k: the launch classes of an engine share k streams instead of one each.  The few long,
+  // latency-bound problems (wide CTAs, long fills) decide when a wave ends: their CTAs go first; the thousands of small
+  // fills soak up whatever is left.
+  cudaStream_t stream_of(int c) {
+    const int k = c % n_streams;
+    if (!cls_stream[k]) {
+      const bool small = (c == 20 || c < 4) && n_streams == kClasses;
+      PGMM_CUDA(cudaStreamCreateWithPriority(&cls_stream[k], cudaStreamNonBlocking, small ? prio_lo : prio_hi));
+    }
+    return cls_stream[k];
+  }
   cudaEvent_t cls_done[kClasses] = {}, fork = nullptr;
   DevBuf<KswJob> d_jobs;
   DevBuf<int> d_ids;
@@ -920,13 +946,11 @@ KswEngine::KswEngine() : impl_(new Impl) {
   PGMM_CUDA(cudaEventCreate(&impl_->ev0));
   PGMM_CUDA(cudaEventCreate(&impl_->ev1));
   PGMM_CUDA(cudaEventCreateWithFlags(&impl_->fork, cudaEventDisableTiming));
-  int prio_lo = 0, prio_hi = 0;
-  PGMM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = more urgent
+  // class streams are created on first use (stream_of): PGMM_NO_CLASS_STREAMS engines never create any
+  static const int n_cls_streams = getenv("PGMM_CLASS_STREAMS") ? std::max(1, std::min((int)Impl::kClasses, atoi(getenv("PGMM_CLASS_STREAMS")))) : (int)Impl::kClasses;
+  impl_->n_streams = n_cls_streams;
+  PGMM_CUDA(cudaDeviceGetStreamPriorityRange(&impl_->prio_lo, &impl_->prio_hi));
   for (int c = 0; c < Impl::kClasses; ++c) {
-    // the few long, latency-bound problems (wide CTAs, long fills) decide when a wave ends: their CTAs go first;
-    // the thousands of small fills soak up whatever is left
-    const bool small = c == 20 || c < 4;
-    PGMM_CUDA(cudaStreamCreateWithPriority(&impl_->cls_stream[c], cudaStreamNonBlocking, small ? prio_lo : prio_hi));
     PGMM_CUDA(cudaEventCreateWithFlags(&impl_->cls_done[c], cudaEventDisableTiming | cudaEventBlockingSync));
     PGMM_CUDA(cudaEventCreate(&impl_->cls_t0[c]));
     PGMM_CUDA(cudaEventCreate(&impl_->cls_t1[c]));
@@ -936,8 +960,10 @@ KswEngine::~KswEngine() {
   cudaEventDestroy(impl_->ev0);
   cudaEventDestroy(impl_->ev1);
   cudaEventDestroy(impl_->fork);
-  for (int c = 0; c < Impl::kClasses; ++c)
-    cudaStreamDestroy(impl_->cls_stream[c]), cudaEventDestroy(impl_->cls_done[c]), cudaEventDestroy(impl_->cls_t0[c]), cudaEventDestroy(impl_->cls_t1[c]);
+  for (int c = 0; c < Impl::kClasses; ++c) {
+    if (impl_->cls_stream[c]) cudaStreamDestroy(impl_->cls_stream[c]);
+    cudaEventDestroy(impl_->cls_done[c]), cudaEventDestroy(impl_->cls_t0[c]), cudaEventDestroy(impl_->cls_t1[c]);
+  }
   delete impl_;
 }
 
@@ -951,6 +977,10 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
   for (int f = 0; f < 3; ++f) res.fam_ms[f] = 0.f, res.fam_cells[f] = 0, res.fam_bases[f] = 0, res.fam_launches[f] = 0;
   if (n == 0) return;
   Impl &m = *impl_;
+  timespec ts_entry;
+  clock_gettime(CLOCK_MONOTONIC, &ts_entry);
+  const double w_entry = ts_entry.tv_sec * 1e3 + ts_entry.tv_nsec * 1e-6;
+  double w_prev_end = w_entry;
 
   // order by traceback size, largest first, so that waves are filled greedily and long problems start early
   std::vector<Geom> geo(n);
@@ -1036,17 +1066,27 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       cls_off[c] = nid;
       for (int k : cls[c]) hid[nid++] = k;
     }
-    m.d_jobs.ensure(nw), m.d_outs.ensure(nw), m.d_ids.ensure(nw), m.d_counter.ensure(1);
+    m.d_jobs.ensure(nw), m.d_outs.ensure(nw), m.d_ids.ensure(nw), m.d_counter.ensure(8);
     // the traceback arena grows on demand up to its budget, in steps of at least half its size: a cudaMalloc stalls every
     // stream of the device, so growth has to stop after the first few waves
     if (p_used + 256 > m.p_arena.cap) {
       const size_t want = std::max<size_t>(p_used + 256, std::min<size_t>(arena_budget_bytes + 256, std::max<size_t>(m.p_arena.cap + m.p_arena.cap / 2, size_t(256) << 20)));
+      if (getenv("PGMM_TRACE")) fprintf(stderr, "[pgmm trace] traceback arena grows from %zu to %zu MB (budget %zu MB)\n", m.p_arena.cap >> 20, want >> 20, arena_budget_bytes >> 20);
       m.p_arena.ensure_exact(want);
     }
     m.cig_arena.ensure(2 * cig_used + 4), m.cig_packed.ensure(2 * cig_used + 4), m.scratch.ensure(scr_used + 256);
     PGMM_CUDA(cudaMemcpyAsync(m.d_jobs.p, hj, nw * sizeof(KswJob), cudaMemcpyHostToDevice, stream));
     PGMM_CUDA(cudaMemcpyAsync(m.d_ids.p, hid, nw * sizeof(int), cudaMemcpyHostToDevice, stream));
-    PGMM_CUDA(cudaMemsetAsync(m.d_counter.p, 0, sizeof(unsigned long long), stream));
+    static const bool trace_spans = getenv("PGMM_TRACE") != nullptr;
+    const auto wall = [] {
+      timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    const double w_submit = wall();
+    PGMM_CUDA(cudaMemsetAsync(m.d_counter.p, 0, 8 * sizeof(unsigned long long), stream));
+    PGMM_CUDA(cudaMemsetAsync(m.d_counter.p + 1, 0xff, sizeof(unsigned long long), stream));
+    if (trace_spans) stamp_kernel<<<1, 1, 0, stream>>>(m.d_counter.p + 3);
     PGMM_CUDA(cudaEventRecord(m.ev0, stream));
     // the size classes are independent launches: fork them onto their own streams so that the few long problems of the
     // large classes overlap with the many short ones instead of queueing behind each other
@@ -1056,7 +1096,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     static const size_t wide_min_smem = getenv("PGMM_WIDE_SMEM_KB") ? std::min(kSmemMax, (size_t)atoi(getenv("PGMM_WIDE_SMEM_KB")) * 1024) : 0;
     for (int c = kClasses - 1; c >= 0; --c) {  // widest / longest first
       if (cls[c].empty()) continue;
-      cudaStream_t cs = no_fork ? stream : m.cls_stream[c];
+      cudaStream_t cs = no_fork ? stream : m.stream_of(c);
       if (!no_fork) PGMM_CUDA(cudaStreamWaitEvent(cs, m.fork, 0));
       PGMM_CUDA(cudaEventRecord(m.cls_t0[c], cs));
 #define PGMM_LAUNCH(NT, SMEM)                                                                                                     \
@@ -1120,13 +1160,23 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       else PGMM_CUDA(cudaStreamWaitEvent(stream, m.cls_done[c], 0));
     }
     PGMM_CUDA(cudaEventRecord(m.ev1, stream));
+    const double w_joined = wall();
+    if (trace_spans) stamp_kernel<<<1, 1, 0, stream>>>(m.d_counter.p + 4);
 
     // ---- results of this wave: ez + the number of CIGAR words, then exactly those words ----
     KswOut *ho = m.h_outs.ensure(nw);
-    unsigned long long *hc = m.h_counter.ensure(1);
+    unsigned long long *hc = m.h_counter.ensure(8);
     PGMM_CUDA(cudaMemcpyAsync(ho, m.d_outs.p, nw * sizeof(KswOut), cudaMemcpyDeviceToHost, stream));
-    PGMM_CUDA(cudaMemcpyAsync(hc, m.d_counter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    PGMM_CUDA(cudaMemcpyAsync(hc, m.d_counter.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     PGMM_CUDA(cudaStreamSynchronize(stream));
+    if (trace_spans) {
+      const double w_done = wall();
+      fprintf(stderr, "[pgmm trace] dp span: %zu jobs, %d launches; host: prep %.2f ms, enqueue+join %.2f ms, results %.2f ms; gpu: main stream reached the wave -> first CTA %.2f ms, "
+              "first CTA -> last CTA end %.2f ms, last CTA end -> main stream after the join %.2f ms\n", nw, res.launches, w_submit - w_prev_end, w_joined - w_submit, w_done - w_joined,
+              hc[1] == ~0ull ? 0.0 : ((double)hc[1] - (double)hc[3]) * 1e-6, hc[1] == ~0ull ? 0.0 : ((double)hc[2] - (double)hc[1]) * 1e-6,
+              hc[1] == ~0ull ? 0.0 : ((double)hc[4] - (double)hc[2]) * 1e-6);
+      w_prev_end = w_done;
+    }
     float ms = 0.f;
     PGMM_CUDA(cudaEventElapsedTime(&ms, m.ev0, m.ev1));
     res.kernel_ms += ms;

@@ -21,6 +21,7 @@
 #endif
 #include <functional>
 #include <thread>
+#include <unordered_map>
 #include <ctime>
 
 namespace pgmm {
@@ -161,8 +162,40 @@ inline Ez ez_reset() {
   return e;
 }
 
+// A DP problem is a pure function of its windows and parameters, and the same window comes up again when a hit is split
+// at a z-drop and its remainder is planned anew (the fills behind the split and the right extension are the ones the
+// original hit already asked for, speculatively).  Every query keeps the results it has seen, keyed by the job itself.
+struct DpKey {
+  uint64_t q_off, t_off;
+  int32_t qlen, tlen, w, zdrop, end_bonus, flag;
+  bool operator==(const DpKey &o) const {
+    return q_off == o.q_off && t_off == o.t_off && qlen == o.qlen && tlen == o.tlen && w == o.w && zdrop == o.zdrop &&
+           end_bonus == o.end_bonus && flag == o.flag;
+  }
+};
+struct DpKeyHash {
+  size_t operator()(const DpKey &k) const {
+    uint64_t h = k.q_off * 0x9E3779B97F4A7C15ull;
+    h ^= (k.t_off + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+    h ^= ((uint64_t)(uint32_t)k.qlen << 32 | (uint32_t)k.tlen) * 0x165667B19E3779F9ull;
+    h ^= ((uint64_t)(uint32_t)k.w << 32 | (uint32_t)k.flag) + ((uint64_t)(uint32_t)k.zdrop << 17) + (uint32_t)k.end_bonus;
+    h ^= h >> 29;
+    return (size_t)(h * 0xBF58476D1CE4E5B9ull);
+  }
+};
+struct DpCached {
+  int8_t zcode = -1;  // mm_test_zdrop's verdict on this result when it is a first-pass fill (-1 = not computed yet)
+  int job = -1;  // >= 0: submitted in the current wave under this index, result not in yet
+  KswOut ez;
+  std::shared_ptr<const KswBatchResult> keep;
+  const uint32_t *cigar = nullptr;
+};
+
 struct DpCall {   // one DP window and, once its wave has run, its result
   int job = -1;   // index in the query's job list of the current wave; -1 = not submitted
+  int wave = -1;  // the wave `job` belongs to
+  DpKey key{};    // the problem itself (valid when keyed)
+  bool keyed = false;
   Ez ez = ez_reset();
   // the CIGAR stays in the wave's result buffer (kept alive here) instead of being copied per problem
   std::shared_ptr<const KswBatchResult> keep;
@@ -210,6 +243,10 @@ struct QCtx {
   std::vector<KswJob> jobs;  // this query's share of the next wave
   size_t job_base = 0;
   bool pending = false;
+  std::unordered_map<DpKey, DpCached, DpKeyHash> dp_cache;  // every DP result of this query so far
+  std::vector<DpKey> wave_keys;                              // key of jobs[i] of the wave being assembled / in flight
+  uint64_t dp_reused = 0;
+  int wave_id = 0, done_wave = -1;  // the wave being assembled; the last one whose results are in
 };
 
 struct Mapper {
@@ -218,9 +255,13 @@ struct Mapper {
   const mm_mapopt_t &opt;
   int8_t mat[25];
   // fills at least this long get their exact second pass queued with the first one (0 = never; PGMM_SPEC_FILL_LEN)
-  int spec_fill_len = 2000;
+  int spec_fill_len = 400;
+  bool dp_reuse = true;  // PGMM_DP_REUSE=0: every planned window is computed again
+  int spec_depth = 16;   // generations of split-off remainders planned ahead (PGMM_SPEC_DEPTH, 0 = off)
   Mapper(const TargetSet &t, const QueryBatch &q, const mm_mapopt_t &o) : ts(t), qb(q), opt(o) {
     if (const char *e = getenv("PGMM_SPEC_FILL_LEN")) spec_fill_len = atoi(e);
+    if (const char *e = getenv("PGMM_DP_REUSE")) dp_reuse = atoi(e) != 0;
+    if (const char *e = getenv("PGMM_SPEC_DEPTH")) spec_depth = atoi(e);
     // ksw_gen_simple_mat(5, mat, a, b, sc_ambi), align.c:9-22
     const int a = opt.a < 0 ? -opt.a : opt.a, b = opt.b > 0 ? -opt.b : opt.b, amb = opt.sc_ambi > 0 ? -opt.sc_ambi : opt.sc_ambi;
     for (int i = 0; i < 4; ++i) {
@@ -582,7 +623,7 @@ struct Mapper {
     c.ez = ez_reset();
     c.cigar = nullptr;
     c.keep.reset();
-    c.job = -1;
+    c.job = -1, c.keyed = false;
     if (opt.max_sw_mat > 0 && (int64_t)tl * ql > opt.max_sw_mat) {
       c.ez.zdropped = 1;
       return;
@@ -593,10 +634,137 @@ struct Mapper {
     j.q_off = q.qbase + (strand ? (uint64_t)q.qlen : 0) + (uint64_t)qstart;
     j.t_off = ts.offs[rid] + (uint64_t)tstart;
     j.qlen = ql, j.tlen = tl, j.w = w, j.zdrop = zdrop, j.end_bonus = end_bonus, j.flag = flag;
+    c.wave = q.wave_id;
+    if (dp_reuse) {
+      const DpKey key{j.q_off, j.t_off, ql, tl, w, zdrop, end_bonus, flag};
+      c.key = key, c.keyed = true;
+      auto it = q.dp_cache.find(key);
+      if (it != q.dp_cache.end()) {
+        ++q.dp_reused;
+        const DpCached &e = it->second;
+        if (e.job >= 0) c.job = e.job, q.pending = true;  // asked for earlier in this very wave: share the slot
+        else c.ez = e.ez, c.keep = e.keep, c.cigar = e.cigar;
+        return;
+      }
+      DpCached e;
+      e.job = (int)q.jobs.size();
+      q.dp_cache.emplace(key, e);
+      q.wave_keys.push_back(key);
+    }
     c.job = (int)q.jobs.size();
     q.jobs.push_back(j);
     q.pending = true;
   }
+  // the results of the wave that just ran become reusable (before any hit of the query looks at them)
+  static void publish_wave(QCtx &q, const std::shared_ptr<const KswBatchResult> &res) {
+    for (size_t k = 0; k < q.wave_keys.size(); ++k) {
+      DpCached &e = q.dp_cache[q.wave_keys[k]];
+      const size_t g = q.job_base + k;
+      e.job = -1, e.ez = res->out[g], e.keep = res, e.cigar = res->cigar.data() + res->cig_start[g];
+    }
+    q.wave_keys.clear();
+  }
+  // a call is ready when nothing was submitted for it or the wave it went into has run
+  static bool ready(const QCtx &q, const DpCall &c) { return c.job < 0 || c.wave == q.done_wave; }
+  static bool region_ready(const QCtx &q, const Region &R) {
+    if (!ready(q, R.left) || !ready(q, R.right) || !ready(q, R.inv)) return false;
+    for (const Fill &f : R.fills)
+      if (!ready(q, f.pass1) || !ready(q, f.pass2)) return false;
+    return true;
+  }
+  // mm_test_zdrop on a first-pass result; the verdict is remembered with the result (it is a function of the same inputs)
+  int fill_code(QCtx &q, const Region &R, const Fill &f, DpCall &p1) const {
+    DpCached *e = nullptr;
+    if (p1.keyed) {
+      auto it = q.dp_cache.find(p1.key);
+      if (it != q.dp_cache.end()) e = &it->second;
+      if (e && e->zcode >= 0) return e->zcode;
+    }
+    if (p1.ez.zd_max < 0) zdrop_scan(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), p1.cigar, p1.ez.n_cigar, p1.ez);
+    const int code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), p1.ez);
+    if (e) e->zcode = (int8_t)code;
+    return code;
+  }
+  // the result of a call that is not pending: its own, or -- for a call planned in this very iteration -- nothing yet
+  static bool resolved(const DpCall &c) { return c.job < 0; }
+
+  // Where will this hit be split?  Everything finish_region needs for that -- the z-drop verdict of every fill and the
+  // exact pass of the first fill that drops -- may already be known from the hit the region was split off (their
+  // windows coincide), long before the region's own new windows (its left extension, usually its first fill) have
+  // run.  A fill whose result is still pending is taken not to drop.  Returns true and the split-off hit when the
+  // answer is "it will be split"; exact second passes that are missing are queued on the way (speculatively: their
+  // results only land in the query's result cache).
+  bool predict_split(QCtx &q, Region &R, mm_reg1_t &r2) const {
+    const U128 *a = q.a.data();
+    static const bool trace = getenv("PGMM_TRACE") != nullptr;
+    if (trace) {
+      int n_pend = 0, n_code = 0, n_drop = 0;
+      for (Fill &f : R.fills) {
+        if (!resolved(f.pass1)) { ++n_pend; continue; }
+        const int code = fill_code(q, R, f, f.pass1);
+        n_code += code != 0, n_drop += f.pass1.ez.zdropped != 0;
+        if (code) fprintf(stderr, "[pgmm trace]   fill i=%d len %d x %d code %d spec2 %d pass2 resolved %d zdropped %d\n", f.i, f.qe - f.qs, f.re - f.rs, code, (int)f.spec2, (int)resolved(f.pass2), f.pass2.ez.zdropped);
+      }
+      fprintf(stderr, "[pgmm trace]   predict: %zu fills, %d pending, %d fail the z-drop test, %d first passes dropped\n", R.fills.size(), n_pend, n_code, n_drop);
+    }
+    for (Fill &f : R.fills) {
+      DpCall &p1 = f.pass1;
+      if (!resolved(p1)) continue;
+      const int code = fill_code(q, R, f, p1);
+      const Ez *ez = &p1.ez;
+      DpCall tmp;
+      if (code != 0) {
+        if (f.spec2 && resolved(f.pass2)) ez = &f.pass2.ez;
+        else if (f.spec2) return false;
+        else {
+          submit(q, tmp, R.rev, f.qs, f.qe - f.qs, R.rid, f.rs, f.re - f.rs, f.bw1, code == 2 ? opt.zdrop_inv : opt.zdrop, -1, 0);
+          if (!resolved(tmp)) return false;  // queued now (or pending): known after the next wave
+          ez = &tmp.ez;
+        }
+      }
+      if (ez->zdropped) {
+        int j;
+        for (j = f.i - 1; j >= 0; --j)
+          if ((int32_t)a[R.as1 + j].x <= f.rs + ez->max_t) break;
+        if (j < 0) j = 0;
+        if (R.cnt1 - (j + 1) < opt.min_cnt) return false;
+        mm_reg1_t r = R.r;
+        memset(&r2, 0, sizeof(r2));
+        split_reg(r, r2, R.as1 + j + 1 - r.as, q.qlen, a);
+        if (code == 2) r2.split_inv = 1;
+        return r2.cnt > 0;
+      }
+    }
+    return false;
+  }
+  // Plans the remainders a waiting hit is going to leave behind, generation after generation, so that their new
+  // windows (left extensions, first fills) run in the NEXT wave instead of one wave per generation.  Nothing of this
+  // touches the real state: the plans live in throw-away regions, the anchor flags they set are put back, and what
+  // the windows compute reaches the real remainders through the result cache when they are planned for real.
+  void speculate_remainders(QCtx &q, Region &R0) const {
+    if (!dp_reuse || spec_depth <= 0 || R0.fills.empty()) return;
+    mm_reg1_t r2;
+    static const bool trace = getenv("PGMM_TRACE") != nullptr;
+    if (!predict_split(q, R0, r2)) {
+      if (trace) fprintf(stderr, "[pgmm trace] speculate: hit as=%d cnt=%d: no split predicted (%zu fills, %zu jobs queued)\n", R0.r.as, R0.r.cnt, R0.fills.size(), q.jobs.size());
+      return;
+    }
+    if (trace) fprintf(stderr, "[pgmm trace] speculate: hit as=%d cnt=%d -> remainder as=%d cnt=%d\n", R0.r.as, R0.r.cnt, r2.as, r2.cnt);
+    const int32_t lo = R0.r.as, hi = R0.r.as + R0.r.cnt;
+    std::vector<uint64_t> saved((size_t)(hi - lo));
+    for (int32_t i = lo; i < hi; ++i) saved[i - lo] = q.a[i].y;
+    for (int depth = 0; depth < spec_depth; ++depth) {
+      Region S;
+      S.r = r2;
+      plan_region(q, S);
+      mm_reg1_t r3;
+      if (S.fills.empty() || !predict_split(q, S, r3)) break;
+      if (trace) fprintf(stderr, "[pgmm trace] speculate:   depth %d: remainder as=%d cnt=%d -> as=%d cnt=%d (%zu jobs queued)\n", depth, r2.as, r2.cnt, r3.as, r3.cnt, q.jobs.size());
+      r2 = r3;
+    }
+    for (int32_t i = lo; i < hi; ++i) q.a[i].y = saved[i - lo];
+  }
+
   static void collect(const QCtx &q, DpCall &c, const std::shared_ptr<const KswBatchResult> &res) {
     if (c.job < 0) return;
     const size_t g = q.job_base + (size_t)c.job;
@@ -796,15 +964,24 @@ struct Mapper {
     bool any = false;
     for (Fill &f : R.fills)
       if (f.spec2) collect(q, f.pass2, res);  // all of them: their slots belong to this wave
+    bool behind = false;  // behind a fill that is known to drop: this hit never uses these fills, its remainders will
     for (Fill &f : R.fills) {
       collect(q, f.pass1, res);
-      if (f.pass1.ez.zd_max < 0) zdrop_scan(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.cigar, f.pass1.ez.n_cigar, f.pass1.ez);
-      f.code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), f.pass1.ez);
+      if (behind) {
+        if (!dp_reuse || spec_depth <= 0) break;
+        if (fill_code(q, R, f, f.pass1) != 0 && !f.spec2) {  // exact pass for the remainders' benefit (result cache only)
+          DpCall tmp;
+          const int code = fill_code(q, R, f, f.pass1);
+          submit(q, tmp, R.rev, f.qs, f.qe - f.qs, R.rid, f.rs, f.re - f.rs, f.bw1, code == 2 ? opt.zdrop_inv : opt.zdrop, -1, 0);
+        }
+        continue;
+      }
+      f.code = fill_code(q, R, f, f.pass1);
       if (f.code != 0 && !f.spec2) {
         submit(q, f.pass2, R.rev, f.qs, f.qe - f.qs, R.rid, f.rs, f.re - f.rs, f.bw1, f.code == 2 ? opt.zdrop_inv : opt.zdrop, -1, 0);
         any |= f.pass2.job >= 0;
       }
-      if ((f.code ? f.pass2.job < 0 && f.pass2.ez.zdropped : f.pass1.ez.zdropped)) break;  // later fills can never be used
+      if ((f.code ? f.pass2.job < 0 && f.pass2.ez.zdropped : f.pass1.ez.zdropped)) behind = true;  // later fills can never be used
     }
     R.state = Region::WAIT2;  // finishing happens in one place: right away when nothing is pending, else after the second wave
     return any;
@@ -1429,6 +1606,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
       q.job_base = jobs.size();
       jobs.insert(jobs.end(), q.jobs.begin(), q.jobs.end());
       q.jobs.clear();
+      q.done_wave = q.wave_id++;  // what was assembled so far runs now; new windows join the next wave
       any_pending |= q.pending;
       q.pending = false;
     }
@@ -1462,9 +1640,12 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     }
     parallel_for(qb.n, n_threads, [&](int qi) {
       QCtx &q = Q[qi];
+      if (!jobs.empty()) Mapper::publish_wave(q, res_sp);
       double s0 = now(), s1, tr_p1 = 0, tr_fin = 0, tr_plan = 0;
+      for (int pass = 0; pass < 64; ++pass) {
       for (size_t k = 0; k < q.regs.size(); ++k) {
         Region &R = *q.regs[k];
+        if (!Mapper::region_ready(q, R)) continue;  // waits for windows of the next wave
         switch (R.state) {
           case Region::WAIT1: {
             s0 = now();
@@ -1505,11 +1686,21 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
             break;
         }
       }
-      // newly created remainders plan their windows now; they join the next wave
+      // newly created remainders plan their windows now; what the result cache cannot answer joins the next wave, and
+      // so do the new windows of the remainders these hits are going to leave behind in turn
       s0 = now();
-      for (auto &R : q.regs)
-        if (R->state == Region::NEW) M.plan_region(q, *R);
+      bool go_on = false;
+      for (size_t k = 0; k < q.regs.size(); ++k) {
+        Region &R = *q.regs[k];
+        if (R.state != Region::NEW) continue;
+        M.plan_region(q, R);
+        if (R.state != Region::WAIT1) continue;
+        M.speculate_remainders(q, R);
+        go_on |= M.dp_reuse && Mapper::region_ready(q, R);  // everything it asked for is known already
+      }
       s1 = now(), tr_plan += s1 - s0;
+      if (!go_on) break;
+      }
       if (getenv("PGMM_TRACE") && tr_p1 + tr_fin + tr_plan > 1.0)
         fprintf(stderr, "[pgmm trace] query %d wave: test_zdrop+queue %.1f ms, finish %.1f ms, plan %.1f ms\n", qi, tr_p1, tr_fin, tr_plan);
     });

@@ -62,6 +62,19 @@ struct DeviceCtx {
   DeviceSeqSet qset;
   cudaStream_t stream = nullptr;
   DeviceCtx() {
+    // PGMM_CTX_STREAMS=k: the contexts share k streams (a device runs kernels from at most 32 hardware queues and
+    // streams beyond that alias onto them; every kernel of a context is short, so sharing a stream costs little)
+    static const int shared = getenv("PGMM_CTX_STREAMS") ? atoi(getenv("PGMM_CTX_STREAMS")) : 0;
+    if (shared > 0) {
+      static std::mutex mu;
+      static std::vector<cudaStream_t> pool;
+      static int next = 0;
+      std::lock_guard<std::mutex> g(mu);
+      if ((int)pool.size() < shared) {
+        PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        pool.push_back(stream);
+      } else stream = pool[next++ % shared];
+    } else
     PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (!DpService::enabled()) {
       const char *e = getenv("PGMM_ARENA_GB");
