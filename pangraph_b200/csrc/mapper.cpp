@@ -968,7 +968,7 @@ struct Mapper {
     for (Fill &f : R.fills) {
       collect(q, f.pass1, res);
       if (behind) {
-        if (!dp_reuse || spec_depth <= 0) break;
+        if (!dp_reuse || spec_depth <= 0) continue;  // (collected all the same: a slot left pending would never be ready)
         if (fill_code(q, R, f, f.pass1) != 0 && !f.spec2) {  // exact pass for the remainders' benefit (result cache only)
           DpCall tmp;
           const int code = fill_code(q, R, f, f.pass1);
