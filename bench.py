@@ -230,7 +230,8 @@ def ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    os.environ.setdefault("PGMM_CONTEXTS", str(max(8, args.workers)))
+    # execution contexts (seeding / chaining workspaces, ~1 GB each) are held for the first third of a round only
+    os.environ.setdefault("PGMM_CONTEXTS", str(max(8, min(args.workers, args.contexts))))
     os.environ.setdefault("PGMM_ARENA_GB", "2")
     L = abi.lib()
     abi.set_device(local)
@@ -278,6 +279,18 @@ def ours(args):
     def step_resident(idxs):
         return finish(list(pool.map(round_resident, idxs)))
 
+    # The timed region feeds the rounds of ALL its steps to the pool at once: a step's results are collected (and
+    # gathered on rank 0) as soon as its own rounds are done, while rounds of the following steps are already running --
+    # the pipeline is not drained between steps, only at the two ends of the timed region.
+    step_e2e.submit = lambda s: [pool.submit(round_e2e, p) for p in pairs_of_step(s)]
+    res_locks = {}
+
+    def round_resident_locked(idx):
+        with res_locks.setdefault(id(idx), threading.Lock()):  # a resident pair is rebuilt in place: one round at a time
+            return round_resident(idx)
+
+    step_resident.submit = lambda idxs: [pool.submit(round_resident_locked, ix) for ix in idxs]
+
     def sync():
         torch.cuda.synchronize()
         if dist is not None:
@@ -320,8 +333,9 @@ def ours(args):
         t0 = time.perf_counter()
         ev0.record()
         hits = 0
-        for it in items:
-            hits += fn(it)
+        futures = [fn.submit(it) for it in items]
+        for fs in futures:
+            hits += finish([f.result() for f in fs])
         ev1.record()
         sync()
         wall = time.perf_counter() - t0
@@ -426,10 +440,11 @@ def ours(args):
                        "l2": f"working set > L2: {n_pool} distinct genome pairs per rank ({n_pool * 2 * args.genome_len / 1e6:.0f} MB of bases), "
                              f"rounds in flight work on different pairs, > 1 GB of traceback written per round",
                        "rounds_per_step": P, "rounds_in_flight": min(P, args.workers), "distinct_pairs_per_rank": n_pool,
+                       "steps_pipelined": "rounds of consecutive steps overlap inside the timed region (no drain between steps)",
                        "busy_host_cores": {"value": round(cpu_used.get("step_resident", 0), 1), "e2e": round(cpu_used.get("step_e2e", 0), 1)},
                        "hits_per_round": hits_res / max(1, rounds_timed), "host_threads": os.cpu_count(),
                        "device_memory_gb": {"total": total_mem / 1e9, "free_before_timed": free0 / 1e9, "free_after_timed": free1 / 1e9},
-                       "device_footprint_model": device_footprint_gb(P, min(P, args.workers), args.genome_len)},
+                       "device_footprint_model": device_footprint_gb(P, min(P, args.workers, args.contexts), args.genome_len)},
             "e2e": {"value": bp_total_e2e / t_e2e / 1e9, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
             "gpu_launches": int(st_res["launches"]),
@@ -481,6 +496,7 @@ def main():
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--rounds-per-step", type=int, default=192, help="independent leaf-merge rounds of one rank per step")
     ap.add_argument("--workers", type=int, default=64, help="host threads driving rounds concurrently (one CUDA stream each)")
+    ap.add_argument("--contexts", type=int, default=24, help="execution contexts of the library (PGMM_CONTEXTS)")
     ap.add_argument("--pool", type=int, default=32, help="distinct genome pairs generated per rank (rounds cycle through them)")
     ap.add_argument("--ref-rounds-per-step", type=int, default=0, help="reference arm / cpu_baseline: full-size rounds per step (0 = 2 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

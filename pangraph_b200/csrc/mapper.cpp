@@ -1585,6 +1585,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
               q.regs.size(), q.jobs.size());
   });
   be.stats.t_chain_rest += now() - tc1;
+  be.end_chain();
   cpu_mark("backtrack + regs + plan");
 
   t1 = now(), be.stats.t_chain += t1 - t0, t0 = t1;

@@ -70,6 +70,8 @@ struct Backend {
   virtual void chain_fill(const ChainParams &cp, std::vector<ChainFillJob> &jobs) = 0;
   // q_off indexes qb.codes, t_off indexes ts.codes
   virtual void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) = 0;
+  // the chaining results (ChainFillJob::f/p/v) are no longer needed: whatever the seeding and chaining stages hold may go
+  virtual void end_chain() {}
   virtual void end_batch() {}
   DpStats stats;
 };

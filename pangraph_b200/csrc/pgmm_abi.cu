@@ -58,7 +58,6 @@ struct DeviceCtx {
   SeedEngine seeder;
   ChainEngine chainer;
   std::unique_ptr<KswEngine> ksw;  // only when the DP service is off (its 29 streams and its arena are per engine)
-  DevBuf<uint8_t> d_qcodes;
   DeviceSeqSet qset;
   cudaStream_t stream = nullptr;
   DeviceCtx() {
@@ -117,13 +116,13 @@ class CtxPool {
  private:
   CtxPool() {
     const char *e = getenv("PGMM_CONTEXTS");
-    max_ = e ? atoi(e) : 8;
+    max_ = e ? atoi(e) : 16;
     if (max_ < 1) max_ = 1;
   }
   std::mutex mu_;
   std::condition_variable cv_;
   std::vector<DeviceCtx *> idle_;
-  int n_ = 0, max_ = 8;
+  int n_ = 0, max_ = 16;
 };
 struct CtxLease {
   DeviceCtx *c;
@@ -168,42 +167,60 @@ __global__ void self_query_kernel(const uint8_t *__restrict__ tcodes, const uint
   q[i] = c, q[L + (L - 1 - i)] = c < 4 ? 3 - c : 4;
 }
 
+// The seeding and chaining stages need an execution context (their workspaces are sized for a whole round: ~100 bytes
+// per base); the DP waves -- most of a round's latency -- only need the round's query codes.  So a round holds a context
+// from begin_batch to end_chain only and a dozen contexts serve several dozen rounds in flight.
 struct CudaBackend : Backend {
   PgmmIndex &ix;
-  DeviceCtx &cx;
-  CudaBackend(PgmmIndex &i, DeviceCtx &c) : ix(i), cx(c) {}
+  std::unique_ptr<CtxLease> lease;
+  DevBuf<uint8_t> d_qcodes;  // forward + reverse-complement codes of the round's queries (what the DP kernels read)
+  CudaBackend(PgmmIndex &i) : ix(i) {}
+  DeviceCtx &cx() {
+    if (!lease) lease.reset(new CtxLease);
+    return *lease->c;
+  }
   double t_seed = 0;
   void begin_batch(const TargetSet &ts, const QueryBatch &qb) override {
     const size_t nbytes = qb.codes.size();
-    cx.d_qcodes.ensure(nbytes + 64);
+    d_qcodes.ensure(nbytes + 64);
+    DeviceCtx &c = cx();
     if (qb.from_targets) {  // nothing crosses the bus: the query buffer is derived from the resident target codes
       const DeviceSeqSet &s = ix.didx.seqs;
       if (s.total > 0)
-        self_query_kernel<<<(unsigned)((s.total + 255) / 256), 256, 0, cx.stream>>>(ix.d_tcodes.p, s.starts.p, s.vstart.p, s.n, s.total, cx.d_qcodes.p);
+        self_query_kernel<<<(unsigned)((s.total + 255) / 256), 256, 0, c.stream>>>(ix.d_tcodes.p, s.starts.p, s.vstart.p, s.n, s.total, d_qcodes.p);
       PGMM_CUDA(cudaGetLastError());
       ++g_seed_launches;
       (void)ts;
-    } else PGMM_CUDA(cudaMemcpyAsync(cx.d_qcodes.p, qb.codes.data(), nbytes, cudaMemcpyHostToDevice, cx.stream));
+    } else PGMM_CUDA(cudaMemcpyAsync(d_qcodes.p, qb.codes.data(), nbytes, cudaMemcpyHostToDevice, c.stream));
   }
   void seed_batch(const TargetSet &ts, const QueryBatch &qb, const mm_mapopt_t &opt, std::vector<QuerySeeds> &out) override {
     const double t0 = now_ms();
+    DeviceCtx &c = cx();
     std::vector<uint64_t> starts(qb.base.begin(), qb.base.end());
     std::vector<int> lens(qb.lens.begin(), qb.lens.end());
-    cx.seeder.sketch(cx.d_qcodes.p, starts, lens, ts.w, ts.k, cx.qset, cx.stream);
+    c.seeder.sketch(d_qcodes.p, starts, lens, ts.w, ts.k, c.qset, c.stream);
     std::vector<int32_t> q_rank(qb.n);
     // skip_seed only looks at names when the query has one (map.c:81): INT32_MIN marks "no name"
     for (int i = 0; i < qb.n; ++i) q_rank[i] = qb.names[i] ? rank_of(ix.sorted_names, qb.names[i]) : INT32_MIN;
-    cx.seeder.collect(ix.didx, cx.qset, q_rank, opt, out, cx.stream);
+    c.seeder.collect(ix.didx, c.qset, q_rank, opt, out, c.stream);
     t_seed += now_ms() - t0;
   }
   std::shared_ptr<std::vector<int32_t>> chain_keep;  // f / p / v of this round when they came from the chain service
   void chain_fill(const ChainParams &cp, std::vector<ChainFillJob> &jobs) override {
     if (ChainService::enabled()) ChainService::get().run(cp, jobs, chain_keep, &stats.chain);
-    else cx.chainer.run(cp, jobs, cx.stream, &stats.chain);
+    else {
+      DeviceCtx &c = cx();
+      c.chainer.run(cp, jobs, c.stream, &stats.chain);
+    }
+  }
+  void end_chain() override {
+    if (DpService::enabled()) lease.reset();  // without the service the context's own DP engine runs the waves
   }
   void run_dp(std::vector<KswJob> &jobs, const KswScoring &sc, KswBatchResult &res) override {
-    if (cx.ksw) cx.ksw->run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res, cx.stream);
-    else DpService::get().run(jobs, cx.d_qcodes.p, ix.d_tcodes.p, sc, res);
+    if (!DpService::enabled()) {
+      DeviceCtx &c = cx();
+      c.ksw->run(jobs, d_qcodes.p, ix.d_tcodes.p, sc, res, c.stream);
+    } else DpService::get().run(jobs, d_qcodes.p, ix.d_tcodes.p, sc, res);
   }
 };
 
@@ -212,7 +229,6 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   require_device();
   PgmmIndex *ix = (PgmmIndex *)mi->h;
   if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200 (no device index attached)");
-  CtxLease cx;
   const double t0 = now_ms();
   QueryBatch qb;
   std::vector<int> self_lens;
@@ -231,7 +247,7 @@ void map_with_index(const mm_idx_t *mi, int n, const int *lens, const char *cons
   }
   qb.n = n;
   qb.lens.assign(lens, lens + n);
-  CudaBackend be(*ix, *cx.c);
+  CudaBackend be(*ix);
   map_batch(be, ix->ts, qb, *opt, n_regs, regs, host_threads());
   std::lock_guard<std::mutex> sl(g_stats_mu);
   g_stats.total_ms += now_ms() - t0, g_stats.seed_ms += be.t_seed, g_stats.dp_kernel_ms += be.stats.kernel_ms;
@@ -455,7 +471,6 @@ int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *c
   require_device();
   PgmmIndex *ix = mi ? (PgmmIndex *)mi->h : nullptr;
   if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200 (no device index attached)");
-  CtxLease cx;
   QueryBatch qb;
   qb.n = n;
   qb.seqs.assign(seqs, seqs + n);
@@ -463,7 +478,7 @@ int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *c
   else qb.names.assign(n, nullptr);
   qb.lens.assign(lens, lens + n);
   encode_queries(qb, ix->ts, host_threads());
-  CudaBackend be(*ix, *cx.c);
+  CudaBackend be(*ix);
   be.begin_batch(ix->ts, qb);
   std::vector<QuerySeeds> out;
   be.seed_batch(ix->ts, qb, *opt, out);
