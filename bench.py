@@ -471,6 +471,7 @@ def ours(args):
             "phases_ms_per_round": {k: st_res[k] / rounds_timed for k in ("index_ms", "t_encode", "t_seed", "t_chain", "t_dp", "t_stitch",
                                                                        "t_final", "dp_kernel_ms", "total_ms", "t_chain_sort", "t_chain_fill",
                                                                        "t_chain_rest", "chain_kernel_ms")},
+            "host_cpu_ms_per_round": {k[4:]: st_res[k] / rounds_timed for k in st_res if k.startswith("cpu_")},
             "chain": {"anchors_per_round": st_res["chain_anchors"] / rounds_timed, "segments_per_round": st_res["chain_segments"] / rounds_timed,
                       "segments_to_host_arbiter": st_res["chain_redo_segments"] / rounds_timed,
                       "anchors_to_host_arbiter": st_res["chain_redo_anchors"] / rounds_timed,

@@ -321,7 +321,9 @@ PGMM_API int64_t pgmm_cta_trace_end(void *out, uint64_t max_n);
  * [21..32] per DP kernel family (K5 generic, K5a small fills, K5b wide fills): ms on the launch streams, cells, bases read,
  * launches [33..41] chaining: host sort ms, device fill ms (with copies), host rest ms (redo + backtrack + hit skeletons +
  * plan), fill kernel ms, anchors, segments, segments handed back to the host, their anchors, launches 
- * [42] fixed-point iterations of the chain fill summed over its batches, [43] those batches */
+ * [42] fixed-point iterations of the chain fill summed over its batches, [43] those batches
+ * [44..53] host CPU ms (thread CPU clocks) by phase: encode, seeding, anchor sort, chain fill, refill + backtrack + hits +
+ * plan, DP waves (round side), DP service workers, stitching, final, index build */
 PGMM_API void pgmm_get_stats(double *out, int n, int reset);
 
 #ifdef __cplusplus

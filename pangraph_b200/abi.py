@@ -168,7 +168,9 @@ STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_
               "k5_ms", "k5_cells", "k5_bases", "k5_launches", "k5a_ms", "k5a_cells", "k5a_bases", "k5a_launches",
               "k5b_ms", "k5b_cells", "k5b_bases", "k5b_launches",
               "t_chain_sort", "t_chain_fill", "t_chain_rest", "chain_kernel_ms", "chain_anchors", "chain_segments",
-              "chain_redo_segments", "chain_redo_anchors", "chain_launches", "chain_iterations", "chain_batches")
+              "chain_redo_segments", "chain_redo_anchors", "chain_launches", "chain_iterations", "chain_batches",
+              "cpu_encode", "cpu_seed", "cpu_sort", "cpu_chain_fill", "cpu_backtrack_plan", "cpu_dp_round_side", "cpu_dp_workers",
+              "cpu_stitch", "cpu_final", "cpu_index")
 
 
 def get_stats(reset=False):

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <thread>
 
+#include "mapper.h"
 #include "pgmm_cuda.h"
 
 namespace pgmm {
@@ -66,6 +67,7 @@ struct DpService::Impl {
         }
       }
       static const bool trace = getenv("PGMM_TRACE") != nullptr;
+      CpuScope cpu_scope(6);
       timespec ts0, ts1, ts2;
       clock_gettime(CLOCK_MONOTONIC, &ts0);
       merged_jobs.clear();

@@ -46,6 +46,17 @@ const uint8_t kNt4[256] = {
 #undef R4
 };
 
+static std::atomic<uint64_t> g_cpu_ns[kCpuPhases];
+void cpu_phase_add(int phase, uint64_t ns) { g_cpu_ns[phase].fetch_add(ns, std::memory_order_relaxed); }
+void cpu_phase_read(double *ms_out, bool reset) {
+  for (int i = 0; i < kCpuPhases; ++i) ms_out[i] = (double)(reset ? g_cpu_ns[i].exchange(0) : g_cpu_ns[i].load()) * 1e-6;
+}
+uint64_t CpuScope::now() {
+  timespec t;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t);
+  return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
+}
+
 static void parallel_chunks(uint64_t total, int n_threads, const std::function<void(uint64_t, uint64_t)> &fn) {
   const uint64_t kChunk = 1 << 20;
   const uint64_t n_chunks = (total + kChunk - 1) / kChunk;
@@ -75,6 +86,7 @@ void encode_queries(QueryBatch &qb, const TargetSet &ts, int n_threads) {
   qb.codes.resize(tot + 16);
   // forward codes and their reverse complement per query (align.c:969-975), chunked over all bases of the batch
   parallel_chunks(vstart[qb.n], n_threads, [&](uint64_t lo, uint64_t hi) {
+    CpuScope cpu_scope(0);
     int i = (int)(std::upper_bound(vstart.begin(), vstart.end(), lo) - vstart.begin()) - 1;
     for (uint64_t p = lo; p < hi;) {
       while (vstart[i + 1] <= p) ++i;
@@ -1500,12 +1512,18 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     cpu0 = c;
   };
   double t0 = now(), t1;
-  encode_queries(qb, ts, std::min(n_threads, 4));
+  {
+    CpuScope cpu_scope(0);  // (the helper threads account for themselves; this is the caller's share)
+    encode_queries(qb, ts, std::min(n_threads, 4));
+  }
   cpu_mark("encode");
   t1 = now(), be.stats.t_encode += t1 - t0, t0 = t1;
-  be.begin_batch(ts, qb);
   std::vector<QuerySeeds> seeds;
-  be.seed_batch(ts, qb, opt, seeds);
+  {
+    CpuScope cpu_scope(1);
+    be.begin_batch(ts, qb);
+    be.seed_batch(ts, qb, opt, seeds);
+  }
   t1 = now(), be.stats.t_seed += t1 - t0, t0 = t1;
   cpu_mark("seeding (host side)");
 
@@ -1518,6 +1536,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
   const bool trace = getenv("PGMM_TRACE") != nullptr;
   std::vector<ChainFillJob> cjobs(qb.n);
   parallel_for(qb.n, n_threads, [&](int i) {
+    CpuScope cpu_scope(2);
     QCtx &q = Q[i];
     q.qi = i, q.qlen = qb.lens[i], q.qname = qb.names[i], q.qbase = qb.base[i];
     q.q0[0] = qb.codes.data() + q.qbase, q.q0[1] = q.q0[0] + q.qlen;
@@ -1545,11 +1564,15 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
   const double tc0 = now();
   be.stats.t_chain_sort += tc0 - t0;
   cpu_mark("anchor sort + segments");
-  be.chain_fill(cp, cjobs);
+  {
+    CpuScope cpu_scope(3);
+    be.chain_fill(cp, cjobs);
+  }
   cpu_mark("chain fill (host side)");
   const double tc1 = now();
   be.stats.t_chain_fill += tc1 - tc0;
   parallel_for(qb.n, n_threads, [&](int i) {
+    CpuScope cpu_scope(4);
     QCtx &q = Q[i];
     ChainFillJob &cj = cjobs[i];
     if (cj.n == 0) return;
@@ -1598,6 +1621,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
   sc.q = (int8_t)opt.q, sc.e = (int8_t)opt.e, sc.q2 = (int8_t)opt.q2, sc.e2 = (int8_t)opt.e2;
   std::vector<KswJob> jobs;
   for (;;) {
+    std::unique_ptr<CpuScope> cpu_wave(new CpuScope(5));
     auto res_mut = std::make_shared<KswBatchResult>();
     KswBatchResult &res = *res_mut;
     const std::shared_ptr<const KswBatchResult> res_sp = res_mut;
@@ -1639,7 +1663,9 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     } else {
       res.out.clear(), res.cigar.clear(), res.cig_start.clear();
     }
+    cpu_wave.reset();
     parallel_for(qb.n, n_threads, [&](int qi) {
+      CpuScope cpu_scope(7);
       QCtx &q = Q[qi];
       if (!jobs.empty()) Mapper::publish_wave(q, res_sp);
       double s0 = now(), s1, tr_p1 = 0, tr_fin = 0, tr_plan = 0;
@@ -1713,6 +1739,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
 
   // ---- final filters, order, mapq, and the malloc()-owned result the boundary promises (minimap.h:353-366) ----
   parallel_for(qb.n, n_threads, [&](int qi) {
+    CpuScope cpu_scope(8);
     QCtx &q = Q[qi];
     if (q.regs.empty()) return;
     M.filter_regs(q);

@@ -76,6 +76,21 @@ struct Backend {
   DpStats stats;
 };
 
+// Host CPU time by phase (thread CPU clocks, summed over every thread that works for the path): [0] encode, [1] seeding
+// (host side), [2] anchor sort + segments, [3] chain fill (host side), [4] host refill + backtrack + hits + plan,
+// [5] DP waves: job lists, hand-over, result slices (round side), [6] DP service workers, [7] stitching + next plan,
+// [8] final filters and output, [9] index build (host side)
+constexpr int kCpuPhases = 10;
+void cpu_phase_add(int phase, uint64_t ns);
+void cpu_phase_read(double *ms_out, bool reset);
+struct CpuScope {
+  int phase;
+  uint64_t t0;
+  static uint64_t now();
+  explicit CpuScope(int p) : phase(p), t0(now()) {}
+  ~CpuScope() { cpu_phase_add(phase, now() - t0); }
+};
+
 // Maps every query of the batch; n_regs[i]/regs[i] are malloc()-owned like mm_map's result.
 void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt_t &opt, int *n_regs, mm_reg1_t **regs,
                int n_threads);

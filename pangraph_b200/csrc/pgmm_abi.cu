@@ -322,6 +322,7 @@ void pgmm_idx_build(mm_idx_t *mi, int w, int k, int bucket_bits) {
   PgmmIndex *ix = (PgmmIndex *)mi->h;
   if (!ix) PGMM_FATAL("mm_idx_t was not created by libpgmm_b200");
   CtxLease cx;
+  CpuScope cpu_scope(9);
   const double t0 = now_ms();
   if (bucket_bits < 0) bucket_bits = 14;
   if (k * 2 < bucket_bits) bucket_bits = k * 2;
@@ -409,9 +410,12 @@ void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *cons
 //        [8] bases_indexed [9] batches [10] kernel launches (all engines) ... [33..41] chaining: sort ms, fill ms, rest ms,
 //        fill kernel ms, anchors, segments, segments redone on the host, their anchors, launches
 //        [42] fixed-point iterations of the chain fill summed over its batches [43] those batches
+//        [44..53] host CPU ms by phase (mapper.h: cpu_phase_*)
 void pgmm_get_stats(double *out, int n, int reset) {
   std::lock_guard<std::mutex> sl(g_stats_mu);
-  const double v[44] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+  double cpu[kCpuPhases];
+  cpu_phase_read(cpu, reset != 0);
+  const double v[44 + kCpuPhases] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
                         (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
                         (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches + (double)g_stats.chain_launches,
                         g_stats.t_encode, g_stats.t_seed, g_stats.t_chain, g_stats.t_dp, g_stats.t_stitch, g_stats.t_final,
@@ -423,8 +427,9 @@ void pgmm_get_stats(double *out, int n, int reset) {
                         g_stats.t_chain_sort, g_stats.t_chain_fill, g_stats.t_chain_rest, g_stats.chain_kernel_ms,
                         (double)g_stats.chain_anchors, (double)g_stats.chain_segments, (double)g_stats.chain_redo_segments,
                         (double)g_stats.chain_redo_anchors, (double)g_stats.chain_launches,
-                        (double)g_stats.chain_iterations, (double)g_stats.chain_batches};
-  for (int i = 0; i < n && i < 44; ++i) out[i] = v[i];
+                        (double)g_stats.chain_iterations, (double)g_stats.chain_batches,
+                        cpu[0], cpu[1], cpu[2], cpu[3], cpu[4], cpu[5], cpu[6], cpu[7], cpu[8], cpu[9]};
+  for (int i = 0; i < n && i < 44 + kCpuPhases; ++i) out[i] = v[i];
   if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0, pgmm::DevicePool::misses() = 0;
   if (reset) g_stats = Stats();
 }
