@@ -432,6 +432,21 @@ struct SeedEngine::Impl {
   PinBuf<U128> h_anchors;  // pinned landing zones for the two large device->host copies
   PinBuf<uint64_t> h_mini;
 
+  // Small device->host results (counts, offsets) land in PINNED memory: a cudaMemcpyAsync into pageable memory is
+  // staged by the driver and the calling thread spins until the stream gets there -- with dozens of rounds in flight
+  // that was 85 ms of host CPU per round (more than half of everything the host did).
+  PinBuf<uint64_t> pinned;
+  size_t pin_used = 0;
+  void pin_reset(size_t words) { pinned.ensure(words + 64), pin_used = 0; }
+  template <class T>
+  T *pin(size_t n) {
+    const size_t w = (n * sizeof(T) + 7) / 8 + 1;
+    if (pin_used + w > pinned.cap) PGMM_FATAL("pinned scratch of the seeding stage is too small (%zu + %zu > %zu words)", pin_used, w, pinned.cap);
+    T *p = (T *)(pinned.p + pin_used);
+    pin_used += w;
+    return p;
+  }
+
   void *tmp(size_t bytes) { return temp.ensure(bytes + 256); }
 
   template <class In, class Out>
@@ -450,11 +465,11 @@ struct SeedEngine::Impl {
   uint64_t scan_flags(const uint32_t *f, uint32_t *pos, uint64_t n, cudaStream_t st) {
     if (n == 0) return 0;
     excl_sum(f, pos, n, st);
-    uint32_t last_pos = 0, last_flag = 0;
-    PGMM_CUDA(cudaMemcpyAsync(&last_pos, pos + n - 1, 4, cudaMemcpyDeviceToHost, st));
-    PGMM_CUDA(cudaMemcpyAsync(&last_flag, f + n - 1, 4, cudaMemcpyDeviceToHost, st));
+    uint32_t *last = pin<uint32_t>(2);
+    PGMM_CUDA(cudaMemcpyAsync(last, pos + n - 1, 4, cudaMemcpyDeviceToHost, st));
+    PGMM_CUDA(cudaMemcpyAsync(last + 1, f + n - 1, 4, cudaMemcpyDeviceToHost, st));
     PGMM_CUDA(cudaStreamSynchronize(st));
-    return (uint64_t)last_pos + last_flag;
+    return (uint64_t)last[0] + last[1];
   }
 };
 
@@ -465,6 +480,7 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
                         DeviceSeqSet &set, cudaStream_t st) {
   Impl &m = *impl_;
   const int n = (int)lens.size();
+  m.pin_reset(4 * ((size_t)n + 2) + 64);
   set.n = n, set.d_codes = d_codes, set.h_starts = starts, set.h_lens = lens;
   set.h_vstart.assign(n + 1, 0);
   for (int i = 0; i < n; ++i) set.h_vstart[i + 1] = set.h_vstart[i] + (uint64_t)lens[i];
@@ -473,9 +489,14 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
   set.h_mz_off.assign(n + 1, 0);
   if (set.total >= (1ull << 31)) PGMM_FATAL("a batch of %llu bases exceeds the 2^31 positions one sketch launch indexes", (unsigned long long)set.total);
   if (w <= 0 || w >= 256 || k <= 0 || k > 28) PGMM_FATAL("minimizer parameters out of range: w=%d k=%d (need 0<w<256, 0<k<=28)", w, k);
-  PGMM_CUDA(cudaMemcpyAsync(set.starts.ensure(n + 1), starts.data(), n * 8, cudaMemcpyHostToDevice, st));
-  PGMM_CUDA(cudaMemcpyAsync(set.vstart.ensure(n + 1), set.h_vstart.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  PGMM_CUDA(cudaMemcpyAsync(set.lens.ensure(n + 1), lens.data(), n * 4, cudaMemcpyHostToDevice, st));
+  {
+    uint64_t *ps = m.pin<uint64_t>(n + 1), *pv = m.pin<uint64_t>(n + 1);
+    int *pl = m.pin<int>(n + 1);
+    memcpy(ps, starts.data(), (size_t)n * 8), memcpy(pv, set.h_vstart.data(), ((size_t)n + 1) * 8), memcpy(pl, lens.data(), (size_t)n * 4);
+    PGMM_CUDA(cudaMemcpyAsync(set.starts.ensure(n + 1), ps, n * 8, cudaMemcpyHostToDevice, st));
+    PGMM_CUDA(cudaMemcpyAsync(set.vstart.ensure(n + 1), pv, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    PGMM_CUDA(cudaMemcpyAsync(set.lens.ensure(n + 1), pl, n * 4, cudaMemcpyHostToDevice, st));
+  }
   set.mz_off.ensure(n + 1);
   const uint64_t N = set.total;
   if (N == 0) {
@@ -492,9 +513,10 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
     PGMM_CUDA(cub::DeviceScan::InclusiveScan(nullptr, bytes, m.rmark.p, m.rpos.p, MaxOp(), (int64_t)N, st));
     PGMM_CUDA(cub::DeviceScan::InclusiveScan(m.tmp(bytes), bytes, m.rmark.p, m.rpos.p, MaxOp(), (int64_t)N, st));
   }
-  uint32_t n_ev = 0;
-  PGMM_CUDA(cudaMemcpyAsync(&n_ev, m.ev_incl.p + N - 1, 4, cudaMemcpyDeviceToHost, st));
+  uint32_t *p_n_ev = m.pin<uint32_t>(1);
+  PGMM_CUDA(cudaMemcpyAsync(p_n_ev, m.ev_incl.p + N - 1, 4, cudaMemcpyDeviceToHost, st));
   PGMM_CUDA(cudaStreamSynchronize(st));
+  const uint32_t n_ev = *p_n_ev;
   if (n_ev == 0) {
     PGMM_CUDA(cudaMemsetAsync(set.mz_off.p, 0, (n + 1) * 8, st));
     PGMM_CUDA(cudaStreamSynchronize(st));
@@ -511,8 +533,10 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
   ++g_seed_launches, scatter_mz_kernel<<<nblk(n_ev), TPB, 0, st>>>(v, n_ev, m.flag.p, m.fpos.p, m.EX.p, m.EP.p, set.mx.p, set.my.p);
   ++g_seed_launches, mz_offsets_kernel<<<nblk(n + 1), TPB, 0, st>>>(v, n_ev, m.ev_incl.p, m.fpos.p, (uint32_t)n_mz, set.mz_off.p);
   PGMM_CUDA(cudaGetLastError());
-  PGMM_CUDA(cudaMemcpyAsync(set.h_mz_off.data(), set.mz_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  uint64_t *p_off = m.pin<uint64_t>(n + 1);
+  PGMM_CUDA(cudaMemcpyAsync(p_off, set.mz_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
   PGMM_CUDA(cudaStreamSynchronize(st));
+  memcpy(set.h_mz_off.data(), p_off, ((size_t)n + 1) * 8);
 }
 
 void SeedEngine::build_index(DeviceIndex &idx, const std::vector<uint32_t> &lens, const std::vector<int32_t> &name_rank, cudaStream_t st) {
@@ -520,8 +544,14 @@ void SeedEngine::build_index(DeviceIndex &idx, const std::vector<uint32_t> &lens
   DeviceSeqSet &set = idx.seqs;
   const uint64_t n = set.n_mz;
   const int ns = set.n;
-  PGMM_CUDA(cudaMemcpyAsync(idx.seq_len.ensure(ns + 1), lens.data(), ns * 4, cudaMemcpyHostToDevice, st));
-  PGMM_CUDA(cudaMemcpyAsync(idx.name_rank.ensure(ns + 1), name_rank.data(), ns * 4, cudaMemcpyHostToDevice, st));
+  m.pin_reset((size_t)ns + 64);
+  {
+    uint32_t *pl = m.pin<uint32_t>(ns + 1);
+    int32_t *pr = m.pin<int32_t>(ns + 1);
+    memcpy(pl, lens.data(), (size_t)ns * 4), memcpy(pr, name_rank.data(), (size_t)ns * 4);
+    PGMM_CUDA(cudaMemcpyAsync(idx.seq_len.ensure(ns + 1), pl, ns * 4, cudaMemcpyHostToDevice, st));
+    PGMM_CUDA(cudaMemcpyAsync(idx.name_rank.ensure(ns + 1), pr, ns * 4, cudaMemcpyHostToDevice, st));
+  }
   idx.n_keys = 0;
   idx.keys.ensure(n + 1), idx.key_off.ensure(n + 2), idx.pos.ensure(n + 1), idx.occ_sorted.ensure(n + 1);
   if (n == 0) {
@@ -543,9 +573,10 @@ void SeedEngine::build_index(DeviceIndex &idx, const std::vector<uint32_t> &lens
     PGMM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, bytes, m.key_out.p, idx.keys.p, m.rle_cnt.p, m.n_runs.p, (int64_t)n, st));
     PGMM_CUDA(cub::DeviceRunLengthEncode::Encode(m.tmp(bytes), bytes, m.key_out.p, idx.keys.p, m.rle_cnt.p, m.n_runs.p, (int64_t)n, st));
   }
-  uint32_t n_keys = 0;
-  PGMM_CUDA(cudaMemcpyAsync(&n_keys, m.n_runs.p, 4, cudaMemcpyDeviceToHost, st));
+  uint32_t *p_n_keys = m.pin<uint32_t>(1);
+  PGMM_CUDA(cudaMemcpyAsync(p_n_keys, m.n_runs.p, 4, cudaMemcpyDeviceToHost, st));
   PGMM_CUDA(cudaStreamSynchronize(st));
+  const uint32_t n_keys = *p_n_keys;
   idx.n_keys = n_keys;
   PGMM_CUDA(cudaMemsetAsync(m.rle_cnt.p + n_keys, 0, 4, st));
   m.excl_sum(m.rle_cnt.p, idx.key_off.p, (uint64_t)n_keys + 1, st);
@@ -562,10 +593,11 @@ int32_t SeedEngine::cal_max_occ(const DeviceIndex &idx, float f, cudaStream_t st
   const size_t n = idx.n_keys;
   if (n == 0) return 1;  // the reference reads an empty array here; an empty index never reaches a lookup
   const uint32_t kk = (uint32_t)((1. - f) * n);
-  uint32_t v = 0;
-  PGMM_CUDA(cudaMemcpyAsync(&v, idx.occ_sorted.p + (kk < n ? kk : n - 1), 4, cudaMemcpyDeviceToHost, st));
+  thread_local PinBuf<uint32_t> pinned_word;
+  uint32_t *v = pinned_word.ensure(2);
+  PGMM_CUDA(cudaMemcpyAsync(v, idx.occ_sorted.p + (kk < n ? kk : n - 1), 4, cudaMemcpyDeviceToHost, st));
   PGMM_CUDA(cudaStreamSynchronize(st));
-  return (int32_t)(v + 1);
+  return (int32_t)(*v + 1);
 }
 
 void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const std::vector<int32_t> &q_name_rank, const mm_mapopt_t &opt,
@@ -575,7 +607,12 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
   out.assign(nq, QuerySeeds());
   uint64_t n = qs.n_mz;
   if (n == 0 || idx.n_keys == 0) return;
-  PGMM_CUDA(cudaMemcpyAsync(m.q_rank.ensure(nq + 1), q_name_rank.data(), nq * 4, cudaMemcpyHostToDevice, st));
+  m.pin_reset(5 * ((size_t)nq + 2) + 64);
+  {
+    int32_t *pr = m.pin<int32_t>(nq + 1);
+    memcpy(pr, q_name_rank.data(), (size_t)nq * 4);
+    PGMM_CUDA(cudaMemcpyAsync(m.q_rank.ensure(nq + 1), pr, nq * 4, cudaMemcpyHostToDevice, st));
+  }
   const uint64_t *fx = qs.mx.p, *fy = qs.my.p, *f_off = qs.mz_off.p;
 
   // ---- query-side occurrence filter (seed.c:5-28); only queries with more than mid_occ minimizers are affected ----
@@ -602,9 +639,10 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     PGMM_CUDA(cub::DeviceRadixSort::SortPairs(m.tmp(bytes), bytes, qid2, sq, sx, sx2, (int64_t)n, 0, qbits, st));
     ++g_seed_launches, mzflt_heads_kernel<<<nblk(n), TPB, 0, st>>>(n, sx2, sq, head);
     m.incl_sum(head, run_incl, n, st);
-    uint32_t n_runs = 0;
-    PGMM_CUDA(cudaMemcpyAsync(&n_runs, run_incl + n - 1, 4, cudaMemcpyDeviceToHost, st));
+    uint32_t *p_n_runs = m.pin<uint32_t>(1);
+    PGMM_CUDA(cudaMemcpyAsync(p_n_runs, run_incl + n - 1, 4, cudaMemcpyDeviceToHost, st));
     PGMM_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_runs = *p_n_runs;
     uint32_t *run_start = m.u32[10].ensure((uint64_t)n_runs + 2);
     ++g_seed_launches, mzflt_runstart_kernel<<<nblk(n), TPB, 0, st>>>(n, head, run_incl, run_start, n_runs);
     ++g_seed_launches, fill_u32_kernel<<<nblk(n), TPB, 0, st>>>(n, keep, 1u);
@@ -649,10 +687,11 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     ++g_seed_launches, compact_flt_kernel<<<nblk(n_seed), TPB, 0, st>>>(n_seed, seeds, flt, fpos, flts);
     ++g_seed_launches, rep_len_kernel<<<nblk(n_flt), TPB, 0, st>>>(n_flt, flts, rep_len);
   }
-  std::vector<int32_t> h_rep(nq + 1, 0);
-  PGMM_CUDA(cudaMemcpyAsync(h_rep.data(), rep_len, nq * 4, cudaMemcpyDeviceToHost, st));
+  int32_t *h_rep = m.pin<int32_t>(nq + 1);
+  PGMM_CUDA(cudaMemcpyAsync(h_rep, rep_len, nq * 4, cudaMemcpyDeviceToHost, st));
 
-  std::vector<uint64_t> h_u_off(nq + 1, 0), h_q_slot(nq + 1, 0), h_a_off(nq + 1, 0);
+  uint64_t *h_u_off = m.pin<uint64_t>(nq + 1), *h_a_off = m.pin<uint64_t>(nq + 1);
+  memset(h_u_off, 0, ((size_t)nq + 1) * 8), memset(h_a_off, 0, ((size_t)nq + 1) * 8);
   uint64_t *h_mini = nullptr;
   U128 *h_anchors = nullptr;
   if (n_used > 0) {
@@ -664,12 +703,13 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
     ++g_seed_launches, remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, sd_off, upos, n_seed, n_used, u_off);
     PGMM_CUDA(cudaMemsetAsync(u_n + n_used, 0, 4, st));
     m.excl_sum(u_n, a_off, n_used + 1, st);
-    uint64_t n_slots = 0;
-    PGMM_CUDA(cudaMemcpyAsync(&n_slots, a_off + n_used, 8, cudaMemcpyDeviceToHost, st));
-    PGMM_CUDA(cudaMemcpyAsync(h_u_off.data(), u_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    uint64_t *p_n_slots = m.pin<uint64_t>(1);
+    PGMM_CUDA(cudaMemcpyAsync(p_n_slots, a_off + n_used, 8, cudaMemcpyDeviceToHost, st));
+    PGMM_CUDA(cudaMemcpyAsync(h_u_off, u_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     h_mini = m.h_mini.ensure(n_used);
     PGMM_CUDA(cudaMemcpyAsync(h_mini, mini_pos, n_used * 8, cudaMemcpyDeviceToHost, st));
     PGMM_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_slots = *p_n_slots;
     if (n_slots >= (1ull << 32)) PGMM_FATAL("%llu anchors in one batch exceed the 2^32 slots of the expansion pass", (unsigned long long)n_slots);
     if (n_slots > 0) {
       uint64_t *ax = m.u64[0].ensure(n_slots), *ay = m.u64[1].ensure(n_slots), *q_slot = m.u64[9].ensure(nq + 2);
@@ -681,7 +721,7 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
       const uint64_t n_anchor = m.scan_flags(akeep, apos, n_slots, st);
       uint64_t *qa_off = m.u64[2].ensure(nq + 2);
       ++g_seed_launches, remap_offsets_kernel<<<nblk(nq + 1), TPB, 0, st>>>(nq, q_slot, apos, n_slots, n_anchor, qa_off);
-      PGMM_CUDA(cudaMemcpyAsync(h_a_off.data(), qa_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+      PGMM_CUDA(cudaMemcpyAsync(h_a_off, qa_off, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
       if (n_anchor > 0) {
         U128 *anchors = m.anchors.ensure(n_anchor);
         ++g_seed_launches, compact_anchor_kernel<<<nblk(n_slots), TPB, 0, st>>>(n_slots, akeep, apos, ax, ay, anchors);
