@@ -45,7 +45,11 @@ struct DpService::Impl {
     std::deque<Request *> &pending = lane[L];
     require_device();
     cudaStream_t stream;
-    PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    {
+      int prio_lo = 0, prio_hi = 0;  // copies and markers of a wave: urgent, tiny
+      PGMM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      PGMM_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+    }
     KswEngine eng;
     eng.arena_budget_bytes = arena_bytes[L];
     std::vector<Request *> batch;

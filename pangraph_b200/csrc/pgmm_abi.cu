@@ -64,17 +64,25 @@ struct DeviceCtx {
     // PGMM_CTX_STREAMS=k: the contexts share k streams (a device runs kernels from at most 32 hardware queues and
     // streams beyond that alias onto them; every kernel of a context is short, so sharing a stream costs little)
     static const int shared = getenv("PGMM_CTX_STREAMS") ? atoi(getenv("PGMM_CTX_STREAMS")) : 0;
+    // The kernels of the seeding and chaining stages are tiny and sit on a round's critical path (a chain fill is ~190
+    // dependent launches of a few microseconds); the thousands of small-fill CTAs a DP wave queues are not.  When an SM
+    // slot frees up the block scheduler serves the highest stream priority first, so these streams get the highest
+    // (PGMM_CTX_PRIORITY=0: default priority, i.e. first come first served behind a wave's CTA backlog).
+    int prio_lo = 0, prio_hi = 0;
+    PGMM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    static const bool high = getenv("PGMM_CTX_PRIORITY") == nullptr || atoi(getenv("PGMM_CTX_PRIORITY")) != 0;
+    const int prio = high ? prio_hi : prio_lo;
     if (shared > 0) {
       static std::mutex mu;
       static std::vector<cudaStream_t> pool;
       static int next = 0;
       std::lock_guard<std::mutex> g(mu);
       if ((int)pool.size() < shared) {
-        PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        PGMM_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio));
         pool.push_back(stream);
       } else stream = pool[next++ % shared];
     } else
-    PGMM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    PGMM_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio));
     if (!DpService::enabled()) {
       const char *e = getenv("PGMM_ARENA_GB");
       const double gb = e ? atof(e) : 8.0;
