@@ -196,6 +196,88 @@ __device__ __noinline__ void finish_job(const KswJob &job, int jid, EzState ez, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The cell-pair step shared by K5a and K5b: two neighbouring target positions per 32-bit register, 16 bits each.
+//
+// Representation (chosen so that one anti-diagonal step of a pair costs ~30 integer instructions, all of them either
+// DPX three-operand instructions -- VIADDMNMX.U16x2 = max(a + b, c) per lane -- or plain 32-bit IADD3 / LOP3 / IMAD):
+//   * every value is scaled by 8 and stored in offset binary: half = 8*value + 0x4000.  All halves are positive and
+//     differences of two stay positive after the constant is restored, so a packed SUBTRACT is one 32-bit IADD3 with no
+//     borrow between the halves (there is no 16x2 subtract instruction; the negation costs two more);
+//   * the three spare low bits carry the traceback direction through the maximum: the score carries tag 7, x+v (dir 1)
+//     6, y+u (2) 5, x2+v (3) 4, y2+u (4) 3, so among equal scores the unsigned max keeps the earlier candidate exactly
+//     like the reference's strict compares (ksw2_extd2_sse.c:240-249), and dir = ~max & 7.  x, y, x2, y2 keep their tag
+//     in the state, u, v and z are tag-free;
+//   * the continuation flags a > 0 ... (:262-269) come out of carry bits: for a half h = 8a + 0x4000 + tag,
+//     bit 15 of h + 0x3ff8, bit 14 of h - 8, bit 13 of h - 0x2008, bit 12 of h - 0x3008 are set iff a >= 1
+//     (|a| <= 128 under the reference's (q+e)+(q2+e2) <= 127 precondition), one add and one mask-or per flag.
+// The same arithmetic as a numpy model, checked against the scalar recurrence: tests/test_lane_model.py.
+// Cells outside the matrix: below / right of it they are cells of the matrix extended with base 'A' (legitimate DP
+// values, same bounds); above the first row they hold unbounded garbage, but such a cell is never the LOW half of a pair
+// whose high half is real, and carries only travel upwards.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kLB = 0x4000u;  // offset of a half
+__host__ __device__ __forceinline__ uint32_t enc1(int v) { return (uint32_t)(8 * v + (int)kLB) & 0xffffu; }
+__host__ __device__ __forceinline__ uint32_t rep2(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
+__device__ __forceinline__ int dec_lo(uint32_t w) { return ((int)(w & 0xffffu) - (int)kLB) >> 3; }
+__device__ __forceinline__ int dec_hi(uint32_t w) { return ((int)(w >> 16) - (int)kLB) >> 3; }
+
+struct LaneConsts {  // computed on the host, passed as a kernel parameter: the loop reads them as constant-bank operands
+  uint32_t MCH7, SCN7, DM8, CQ, CQ2, NQE, NQE2, FLX, FLY, FLX2, FLY2;
+  uint32_t X0, X20;          // x[-1], x2[-1] of the first column (low half, with tag)
+  uint32_t Y0, Y20, V0;      // first-row y, y2 (with tag) and the initial v as single halves
+  uint32_t UF0, UF1, UF2, UF3;  // u of the first row / v of the first column: r == 0, r < long_thres, r == long_thres, beyond
+  int32_t q, e, q2, e2, long_thres;  // gap costs ordered like the reference orders them (:50-52)
+  __host__ __device__ void init(const KswScoring &sc) {
+    q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
+    if (q2 + e2 < q + e) {
+      int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t;
+    }
+    const int long_thres0 = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+    long_thres = (q2 + e2 + long_thres0 * e2 > q + e + long_thres0 * e) ? long_thres0 + 1 : long_thres0;
+    const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+    UF0 = enc1(-q - e), UF1 = enc1(-e), UF2 = enc1(long_diff), UF3 = enc1(-e2);
+    const int scN = sc.sc_ambi == 0 ? -e2 : -(sc.sc_ambi < 0 ? -sc.sc_ambi : sc.sc_ambi);
+    MCH7 = rep2(8 * sc.sc_mch + 0x8000 + 7), SCN7 = rep2(8 * scN + 0x8000 + 7), DM8 = (uint32_t)(8 * (sc.sc_mch - sc.sc_mis));
+    CQ = rep2(8 * q + (int)kLB), CQ2 = rep2(8 * q2 + (int)kLB);
+    NQE = rep2(-8 * (q + e)), NQE2 = rep2(-8 * (q2 + e2));
+    FLX = rep2((int)kLB + 6 - 8 * (q + e)), FLY = rep2((int)kLB + 5 - 8 * (q + e));
+    FLX2 = rep2((int)kLB + 4 - 8 * (q2 + e2)), FLY2 = rep2((int)kLB + 3 - 8 * (q2 + e2));
+    X0 = enc1(-q - e) + 6, X20 = enc1(-q2 - e2) + 4, Y0 = enc1(-q - e) + 5, Y20 = enc1(-q2 - e2) + 3, V0 = enc1(-q - e);
+  }
+  __device__ __forceinline__ uint32_t ufirst(int r) const { return r == 0 ? UF0 : r < long_thres ? UF1 : r == long_thres ? UF2 : UF3; }
+};
+
+// One anti-diagonal step of a pair.  In: x, v, x2 of the cells to the left (previous anti-diagonal), u, y, y2 of the
+// pair itself, the two target and the two query codes.  Out: the new state and the two traceback bytes (low byte =
+// low cell).  HAS_N is uniform per problem: sequences without ambiguous bases skip the third score.
+__device__ __forceinline__ uint32_t pair_step(const LaneConsts &c, bool has_n, uint32_t XT1, uint32_t VT1, uint32_t X2T1, uint32_t Uo,
+                                              uint32_t Yo, uint32_t Y2o, uint32_t tq, uint32_t qq, uint32_t &Un, uint32_t &Vn,
+                                              uint32_t &Xn, uint32_t &Yn, uint32_t &X2n, uint32_t &Y2n) {
+  const uint32_t ne = __vminu2(tq ^ qq, 0x00010001u);
+  uint32_t Z = c.MCH7 - ne * c.DM8;  // halves stay positive: exact per half
+  if (has_n) {
+    const uint32_t isn = __vminu2((tq | qq) & 0x00040004u, 0x00010001u) * 0xffffu;
+    Z = (Z & ~isn) | (c.SCN7 & isn);
+  }
+  uint32_t M = __viaddmax_u16x2(XT1, VT1, Z);
+  M = __viaddmax_u16x2(Yo, Uo, M);
+  M = __viaddmax_u16x2(X2T1, VT1, M);
+  M = __viaddmax_u16x2(Y2o, Uo, M);
+  const uint32_t Z8 = __vminu2(M, c.MCH7) & 0xfff8fff8u;  // z, offset 0x8000
+  Un = Z8 - VT1, Vn = Z8 - Uo;                            // offset back to 0x4000
+  const uint32_t A = XT1 - Un + c.CQ, B = Yo - Vn + c.CQ, A2 = X2T1 - Un + c.CQ2, B2 = Y2o - Vn + c.CQ2;
+  uint32_t acc = __vadd2(A, 0xcff8cff8u) & 0x10001000u;          // - 0x3008
+  acc |= __vadd2(B, 0xdff8dff8u) & 0x20002000u;                  // - 0x2008
+  acc |= __vadd2(A2, 0xfff8fff8u) & 0x40004000u;                 // - 8
+  acc |= (B2 + 0x3ff83ff8u) & 0x80008000u;                      // + 0x3ff8: no carry out of a half
+  // max(a, 0) - (q + e): signed lanes here (the addend is negative, all three operands are far from the 16-bit limits)
+  Xn = __viaddmax_s16x2(A, c.NQE, c.FLX), Yn = __viaddmax_s16x2(B, c.NQE, c.FLY);
+  X2n = __viaddmax_s16x2(A2, c.NQE2, c.FLX2), Y2n = __viaddmax_s16x2(B2, c.NQE2, c.FLY2);
+  const uint32_t D = (acc >> 9) | (~M & 0x00070007u);
+  return __byte_perm(D, 0u, 0x4420);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K5a: first-pass gap fills (flag == KSW_APPROX_MAX, band never binding, target window <= 256 bases) -- about 85 % of
 // all DP cells of a round (~28 000 windows of ~205 x 205 per 5-Mbp pair).  Specialised because, when the band cannot
 // bind, padded cells can never reach a real cell (oracle/pgmm_oracle.c::orc_ksw_extd2_unbanded states and tests this):
@@ -211,14 +293,11 @@ constexpr int kFillWarps = 4;     // problems per CTA
 constexpr int kFillMaxT = 256;    // target window limit (4 slots x 32 lanes x 2 cells)
 constexpr int kFillMaxQ = 1024;   // query window limit (two 16-bit copies of the reversed query in shared memory)
 
-__device__ __forceinline__ uint32_t pk2(int v) { return (uint32_t)(uint16_t)(int16_t)v * 0x00010001u; }
-__device__ __forceinline__ int lo16(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
-__device__ __forceinline__ int hi16(uint32_t w) { return (int)(int16_t)(w >> 16); }
-__device__ __forceinline__ uint32_t neg2(uint32_t w) { return __vadd2(~w, 0x00010001u); }
 
-__global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
+__global__ void __launch_bounds__(kFillWarps * 32, 6) ksw_fill_small_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
                                                                          int n_jobs, const uint8_t *__restrict__ qcodes,
-                                                                         const uint8_t *__restrict__ tcodes, KswScoring sc, int q_cap,
+                                                                         const uint8_t *__restrict__ tcodes, KswScoring sc,
+                                                                         const __grid_constant__ LaneConsts lc, int q_cap,
                                                                          uint8_t *__restrict__ p_arena, uint32_t *__restrict__ cig_arena,
                                                                          KswOut *__restrict__ outs, uint32_t *__restrict__ cig_packed,
                                                                          unsigned long long *__restrict__ cig_counter) {
@@ -231,10 +310,6 @@ __global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const K
   const KswJob job = jobs[jid];
   const unsigned long long tr0 = trace::begin();
   const int qlen = job.qlen, tlen = job.tlen;
-  int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
-  if (q2 + e2 < q + e) {
-    int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t;
-  }
   // per-warp shared memory: target bytes [kFillMaxT+16], reversed query bytes [4 + q_cap + 28], and the reversed query
   // as 16-bit codes twice (second copy shifted by one element) so that the two query bases of a pair are always one
   // aligned 32-bit load; both copies have 2*kFillMaxT zero elements in front and behind
@@ -249,115 +324,88 @@ __global__ void __launch_bounds__(kFillWarps * 32) ksw_fill_small_kernel(const K
   for (int i = lane; i < (q_cap + 32) / 4; i += 32) ((uint32_t *)QRraw)[i] = 0;
   for (int i = lane; i < qh_len; i += 32) ((uint32_t *)QH0)[i] = 0;  // both copies (2*qh_len halfwords)
   __syncwarp();
+  uint32_t any_n = 0;
   {
     const uint8_t *tb = tcodes + job.t_off, *qb = qcodes + job.q_off;
-    for (int i = lane; i < tlen; i += 32) TQ8[i] = tb[i];
+    for (int i = lane; i < tlen; i += 32) {
+      const uint8_t c = tb[i];
+      TQ8[i] = c, any_n |= c;
+    }
     for (int i = lane; i < qlen; i += 32) {
       const uint8_t c = qb[qlen - 1 - i];  // reversed query: element i pairs with target t on anti-diagonal r when i = qlen-1-r+t
-      QR8[i] = c;
+      QR8[i] = c, any_n |= c;
       QH0[2 * kFillMaxT + i] = c;
       QH1[2 * kFillMaxT + i - 1] = c;  // QH1[k] = QH0[k+1]
     }
   }
+  const bool has_n = __any_sync(0xffffffffu, (any_n & 4u) != 0);  // ambiguous bases anywhere in the two windows
   __syncwarp();
 
-  const int long_thres0 = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
-  const int long_thres = (q2 + e2 + long_thres0 * e2 > q + e + long_thres0 * e) ? long_thres0 + 1 : long_thres0;
-  const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
-  const int scN = sc.sc_ambi == 0 ? -e2 : -(sc.sc_ambi < 0 ? -sc.sc_ambi : sc.sc_ambi);
-  const uint32_t MCH = pk2(sc.sc_mch), MIS = pk2(sc.sc_mis), SCN = pk2(scN), ONE = 0x00010001u;
-  const uint32_t DMCH = (uint32_t)(sc.sc_mch - sc.sc_mis);  // multiplies a 0/1-per-lane word: no carry between lanes
-  const uint32_t QP = pk2(q), Q2P = pk2(q2), NQE = pk2(-q - e), NQE2 = pk2(-q2 - e2);
-  const int Tp = (tlen + 15) / 16 * 16, n_row = qlen + tlen - 1, qe = q + e;
+  const int Tp = (tlen + 15) / 16 * 16, n_row = qlen + tlen - 1;
   uint8_t *P = p_arena + job.p_off;
 
   uint32_t U[4], Y[4], Y2[4], V[4], X[4], X2[4], TQ[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    U[k] = Y[k] = V[k] = X[k] = NQE, Y2[k] = X2[k] = NQE2;
+    U[k] = V[k] = lc.V0 * 0x00010001u, X[k] = lc.X0 * 0x00010001u, Y[k] = lc.Y0 * 0x00010001u;
+    X2[k] = lc.X20 * 0x00010001u, Y2[k] = lc.Y20 * 0x00010001u;
     const int t = 2 * (32 * k + lane);
     TQ[k] = (uint32_t)TQ8[t] | (uint32_t)TQ8[t + 1] << 16;
   }
-  int32_t H0 = 0, last = 0;
+  int32_t H0 = 0;
+  uint32_t vsum = 0;
+  const int k_end = (tlen - 1) >> 6, sh_end = ((tlen - 1) & 1) * 16;  // slot and half of the last target position
+  // per-lane addresses, advanced incrementally: the query word of (slot 0, this lane) in either copy (shared-space
+  // addresses: no generic-address arithmetic in the loop) and this lane's two traceback bytes of the current row
+  const uint32_t qa0 = (uint32_t)__cvta_generic_to_shared(QH0) + 4u * lane, qa1 = (uint32_t)__cvta_generic_to_shared(QH1) + 4u * lane;
+  uint8_t *prow_l = P + 2 * lane;
+  const bool last_lane = lane == 31;
 
-  for (int r = 0; r < n_row; ++r) {
+  for (int r = 0; r < n_row; ++r, prow_l += Tp) {
     const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
-    const int ufirst = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+    const uint32_t UF = lc.ufirst(r);
     const int p_lo = st0 >> 1, p_hi = en0 >> 1;  // active pairs
     const int qbase = 2 * kFillMaxT + (qlen - 1 - r);  // halfword index of the query base of target position 0
-    const uint16_t *QH = (qbase & 1) ? QH1 : QH0;
-    const int qword = (qbase & 1) ? (qbase - 1) >> 1 : qbase >> 1;  // 32-bit index of (t=0, t=1) in the chosen copy
-    uint8_t *prow = P + (size_t)r * Tp;
-    int d0 = 0, d1 = 0;  // v[last], u[last+1] of this anti-diagonal (for the tracked score)
-    const int l0p = last >> 1, l1p = (last + 1) >> 1;
+    // the copy in which (t=0, t=1) is an aligned 32-bit word: copy 1 is copy 0 shifted by one element
+    const uint32_t qaddr = ((qbase & 1) ? qa1 : qa0) + 4u * (uint32_t)(qbase >> 1);
+    const int fr_k = en0 == r ? r >> 6 : -1, fr_lane = (r >> 1) & 31;  // slot and lane of the first-row cell, if any
 #pragma unroll
     for (int k = 3; k >= 0; --k) {
       if (32 * k > p_hi || 32 * k + 31 < p_lo) continue;  // warp-uniform
-      const int p = 32 * k + lane;
-      // previous anti-diagonal's x, v, x2 of the cell to the left: high half of the previous pair
-      uint32_t px = __shfl_up_sync(0xffffffffu, X[k], 1), pv = __shfl_up_sync(0xffffffffu, V[k], 1), px2 = __shfl_up_sync(0xffffffffu, X2[k], 1);
+      // previous anti-diagonal's x, v, x2 of the cell to the left: high half of the previous pair.  Lane 31 offers the
+      // last pair of the previous slot (read by lane 0); in slot 0, lane 0 reads the first-column values (:156-159).
+      uint32_t sx = X[k], sv = V[k], sx2 = X2[k];
       if (k > 0) {
-        const uint32_t wx = __shfl_sync(0xffffffffu, X[k - 1], 31), wv = __shfl_sync(0xffffffffu, V[k - 1], 31), wx2 = __shfl_sync(0xffffffffu, X2[k - 1], 31);
-        if (lane == 0) px = wx, pv = wv, px2 = wx2;
-      }
-      uint32_t XT1 = __funnelshift_l(px, X[k], 16), VT1 = __funnelshift_l(pv, V[k], 16), X2T1 = __funnelshift_l(px2, X2[k], 16);
-      if (p == 0) {  // first column (ksw2_extd2_sse.c:156-159)
-        XT1 = (XT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q - e);
-        X2T1 = (X2T1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q2 - e2);
-        VT1 = (VT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst;
-      }
+        if (last_lane) sx = X[k - 1], sv = V[k - 1], sx2 = X2[k - 1];
+      } else if (last_lane) sx = lc.X0 << 16, sv = UF << 16, sx2 = lc.X20 << 16;
+      const uint32_t px = __shfl_sync(0xffffffffu, sx, (lane + 31) & 31), pv = __shfl_sync(0xffffffffu, sv, (lane + 31) & 31),
+                     px2 = __shfl_sync(0xffffffffu, sx2, (lane + 31) & 31);
+      const uint32_t XT1 = __funnelshift_l(px, X[k], 16), VT1 = __funnelshift_l(pv, V[k], 16), X2T1 = __funnelshift_l(px2, X2[k], 16);
       uint32_t Uo = U[k], Yo = Y[k], Y2o = Y2[k];
-      if (en0 == r && (r >> 1) == p) {  // first row (:160-163)
-        if (r & 1) Uo = (Uo & 0x0000ffffu) | (uint32_t)(uint16_t)(int16_t)ufirst << 16, Yo = (Yo & 0x0000ffffu) | (NQE & 0xffff0000u), Y2o = (Y2o & 0x0000ffffu) | (NQE2 & 0xffff0000u);
-        else Uo = (Uo & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst, Yo = (Yo & 0xffff0000u) | (NQE & 0xffffu), Y2o = (Y2o & 0xffff0000u) | (NQE2 & 0xffffu);
+      if (fr_k == k) {  // first row (:160-163): warp-uniform test, one lane acts
+        if (fr_lane == lane) {
+          if (r & 1) Uo = (Uo & 0x0000ffffu) | UF << 16, Yo = (Yo & 0x0000ffffu) | lc.Y0 << 16, Y2o = (Y2o & 0x0000ffffu) | lc.Y20 << 16;
+          else Uo = (Uo & 0xffff0000u) | UF, Yo = (Yo & 0xffff0000u) | lc.Y0, Y2o = (Y2o & 0xffff0000u) | lc.Y20;
+        }
       }
-      // substitution scores of the two cells
-      const uint32_t qq = ((const uint32_t *)QH)[qword + p];
-      const uint32_t ne = __vminu2(TQ[k] ^ qq, ONE);
-      uint32_t Z = __vadd2(MIS, (ne ^ ONE) * DMCH);
-      const uint32_t isn = __vminu2((TQ[k] | qq) & 0x00040004u, ONE) * 0xffffu;
-      Z = (Z & ~isn) | (SCN & isn);
-      // the recurrence (left gap alignment, :228-275), two cells at a time
-      uint32_t A = __vadd2(XT1, VT1), B = __vadd2(Yo, Uo), A2 = __vadd2(X2T1, VT1), B2 = __vadd2(Y2o, Uo);
-      bool ph, pl;
-      uint32_t dl = 0, dh = 0;
-      Z = __vibmax_s16x2(Z, A, &ph, &pl);  dl = pl ? dl : 1u; dh = ph ? dh : 1u;
-      Z = __vibmax_s16x2(Z, B, &ph, &pl);  dl = pl ? dl : 2u; dh = ph ? dh : 2u;
-      Z = __vibmax_s16x2(Z, A2, &ph, &pl); dl = pl ? dl : 3u; dh = ph ? dh : 3u;
-      Z = __vibmax_s16x2(Z, B2, &ph, &pl); dl = pl ? dl : 4u; dh = ph ? dh : 4u;
-      Z = __vmins2(Z, MCH);
-      const uint32_t NZ = neg2(Z);
-      const uint32_t Un = __vadd2(Z, neg2(VT1)), Vn = __vadd2(Z, neg2(Uo));
-      const uint32_t T1 = __vadd2(NZ, QP), T2 = __vadd2(NZ, Q2P);
-      A = __vadd2(A, T1), B = __vadd2(B, T1), A2 = __vadd2(A2, T2), B2 = __vadd2(B2, T2);
-      // continuation flags: a > 0 <=> a >= 1.  (With a literal first operand nvcc 12.9 swaps the operands of
-      // __vibmax_s16x2 without flipping the predicates, so the variable goes first and the clamp is a separate max.)
-      (void)__vibmax_s16x2(A, ONE, &ph, &pl);  dl |= pl ? 0x08u : 0u; dh |= ph ? 0x08u : 0u;
-      (void)__vibmax_s16x2(B, ONE, &ph, &pl);  dl |= pl ? 0x10u : 0u; dh |= ph ? 0x10u : 0u;
-      (void)__vibmax_s16x2(A2, ONE, &ph, &pl); dl |= pl ? 0x20u : 0u; dh |= ph ? 0x20u : 0u;
-      (void)__vibmax_s16x2(B2, ONE, &ph, &pl); dl |= pl ? 0x40u : 0u; dh |= ph ? 0x40u : 0u;
-      A = __vmaxs2(A, 0u), B = __vmaxs2(B, 0u), A2 = __vmaxs2(A2, 0u), B2 = __vmaxs2(B2, 0u);
-      U[k] = Un, V[k] = Vn;
-      X[k] = __vadd2(A, NQE), Y[k] = __vadd2(B, NQE), X2[k] = __vadd2(A2, NQE2), Y2[k] = __vadd2(B2, NQE2);
-      if (p <= p_hi) *(uint16_t *)(prow + 2 * p) = (uint16_t)(dl | dh << 8);  // cells past the target end share the padded row
-      // values the tracked score needs (:367-379)
-      if ((l0p >> 5) == k) {
-        const uint32_t w = __shfl_sync(0xffffffffu, Vn, l0p & 31);
-        d0 = (last & 1) ? hi16(w) : lo16(w);
-      }
-      if ((l1p >> 5) == k) {
-        const uint32_t w = __shfl_sync(0xffffffffu, Un, l1p & 31);
-        d1 = ((last + 1) & 1) ? hi16(w) : lo16(w);
-      }
+      uint32_t qq;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qq) : "r"(qaddr + 128u * k));
+      const uint32_t d16 = pair_step(lc, has_n, XT1, VT1, X2T1, Uo, Yo, Y2o, TQ[k], qq, U[k], V[k], X[k], Y[k], X2[k], Y2[k]);
+      if (32 * k + lane <= p_hi) *(uint16_t *)(prow_l + 64 * k) = (uint16_t)d16;  // cells past the target end share the padded row
     }
-    if (r > 0) {
-      const bool in0 = last >= st0 && last <= en0, in1 = last + 1 >= st0 && last + 1 <= en0;
-      if (in0 && in1) {
-        if (d0 > d1) H0 += d0;
-        else H0 += d1, ++last;
-      } else if (in0) H0 += d0;
-      else ++last, H0 += d1;
-    } else H0 = d0 - qe, last = 0;
+    // The score (:367-379).  The reference walks a data-dependent staircase from (0,0) and adds v[last] or u[last+1] on
+    // every anti-diagonal; u and v are exact differences of one score matrix, so the sum does not depend on the path
+    // (tests/test_lane_model.py checks the identity): here the lane that owns the last target position adds up its v
+    // on the anti-diagonals that reach it, which needs no communication; the boundary H(tlen-1, -1) is added at the end.
+    if (en0 == tlen - 1) {
+      const uint32_t w = k_end == 0 ? V[0] : k_end == 1 ? V[1] : k_end == 2 ? V[2] : V[3];
+      vsum += (w >> sh_end) & 0xffffu;
+    }
+  }
+  {
+    const int gap1 = lc.q + lc.e * tlen, gap2 = lc.q2 + lc.e2 * tlen;
+    const uint32_t tot = __shfl_sync(0xffffffffu, vsum, ((tlen - 1) >> 1) & 31);  // qlen halves of 8*v + 0x4000 each
+    H0 = ((int32_t)(tot - (uint32_t)qlen * kLB) >> 3) - (gap1 < gap2 ? gap1 : gap2);
   }
 
   __threadfence_block();  // every lane's traceback bytes must be visible to the lane that walks them
@@ -395,7 +443,8 @@ struct WideMail {      // per parity
 template <int NW, int KP, bool EXACT>
 __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
                                                                 const uint8_t *__restrict__ qcodes, const uint8_t *__restrict__ tcodes,
-                                                                KswScoring sc, uint8_t *__restrict__ p_arena,
+                                                                KswScoring sc, const __grid_constant__ LaneConsts lc,
+                                                                uint8_t *__restrict__ p_arena,
                                                                 uint32_t *__restrict__ cig_arena, KswOut *__restrict__ outs,
                                                                 uint32_t *__restrict__ cig_packed, unsigned long long *__restrict__ cig_counter) {
   constexpr int NT = NW * 32;
@@ -407,11 +456,7 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
   const unsigned long long tr0 = trace::begin();
   span_begin(cig_counter);
   const int qlen = job.qlen, tlen = job.tlen;
-  int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
-  if (q2 + e2 < q + e) {
-    int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t;
-  }
-  const int Tp = (tlen + 15) / 16 * 16, n_row = qlen + tlen - 1, qe = q + e;
+  const int Tp = (tlen + 15) / 16 * 16, n_row = qlen + tlen - 1, qe = lc.q + lc.e, e2 = lc.e2;
   // shared memory: target bytes [Tp + 16], reversed query bytes [4 + qlen + pad], reversed query as 16-bit codes with
   // Tp + 16 zero elements in front and behind
   uint8_t *TQ8 = (uint8_t *)dyn_smem;
@@ -423,31 +468,29 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
   for (int i = tid; i < qr_bytes / 4; i += NT) ((uint32_t *)QRraw)[i] = 0;
   for (int i = tid; i < (qh_len + 1) / 2; i += NT) ((uint32_t *)QH)[i] = 0;
   __syncthreads();
+  uint32_t any_n = 0;
   {
     const uint8_t *tb = tcodes + job.t_off, *qb = qcodes + job.q_off;
-    for (int i = tid; i < tlen; i += NT) TQ8[i] = tb[i];
+    for (int i = tid; i < tlen; i += NT) {
+      const uint8_t c = tb[i];
+      TQ8[i] = c, any_n |= c;
+    }
     for (int i = tid; i < qlen; i += NT) {
       const uint8_t c = qb[qlen - 1 - i];
-      QR8[i] = c;
+      QR8[i] = c, any_n |= c;
       QH[qh_pad + i] = c;
     }
   }
-  __syncthreads();
+  const bool has_n = __syncthreads_or((any_n & 4u) != 0) != 0;  // ambiguous bases anywhere in the two windows
 
-  const int long_thres0 = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
-  const int long_thres = (q2 + e2 + long_thres0 * e2 > q + e + long_thres0 * e) ? long_thres0 + 1 : long_thres0;
-  const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
-  const int scN = sc.sc_ambi == 0 ? -e2 : -(sc.sc_ambi < 0 ? -sc.sc_ambi : sc.sc_ambi);
-  const uint32_t MCH = pk2(sc.sc_mch), MIS = pk2(sc.sc_mis), SCN = pk2(scN), ONE = 0x00010001u;
-  const uint32_t DMCH = (uint32_t)(sc.sc_mch - sc.sc_mis);
-  const uint32_t QP = pk2(q), Q2P = pk2(q2), NQE = pk2(-q - e), NQE2 = pk2(-q2 - e2);
   uint8_t *P = p_arena + job.p_off;
 
   uint32_t U[KP], Y[KP], Y2[KP], V[KP], X[KP], X2[KP], TQ[KP];
   int32_t HL[KP], HH[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    U[k] = Y[k] = V[k] = X[k] = NQE, Y2[k] = X2[k] = NQE2;
+    U[k] = V[k] = lc.V0 * 0x00010001u, X[k] = lc.X0 * 0x00010001u, Y[k] = lc.Y0 * 0x00010001u;
+    X2[k] = lc.X20 * 0x00010001u, Y2[k] = lc.Y20 * 0x00010001u;
     HL[k] = HH[k] = KSW_NEG_INF;
     const int t = 2 * (NT * k + tid);
     TQ[k] = t + 1 < Tp + 16 ? ((uint32_t)TQ8[t] | (uint32_t)TQ8[t + 1] << 16) : 0u;
@@ -456,7 +499,9 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
   ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
   ez.max = 0, ez.score = ez.mqe = ez.mte = KSW_NEG_INF;
   ez.zdropped = 0, ez.reach_end = 0;
-  int32_t H0 = 0, last = 0;
+  // first pass: the score is the sum of v along the last target column (see K5a); its owner adds them up
+  uint32_t vsum = 0;
+  const int p_end = (tlen - 1) >> 1, sh_end = ((tlen - 1) & 1) * 16;
   int r_done = 0;
 
   for (int r = 0; r < n_row; ++r) {
@@ -464,7 +509,7 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
     const int par = r & 1;
     WideMail &in = mail[par ^ 1], &out = mail[par];
     const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
-    const int ufirst = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+    const uint32_t UF = lc.ufirst(r);
     const int p_lo = st0 >> 1, p_hi = en0 >> 1;
     const int qbase = qh_pad + (qlen - 1 - r);  // halfword index of the query base that meets target position 0
     uint8_t *prow = P + (size_t)r * Tp;
@@ -479,54 +524,30 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
       if (lane == 0) {  // previous warp's last pair, or the last pair of the previous slot, as of the previous anti-diagonal
         if (warp > 0) px = in.x[warp - 1][k], pv = in.v[warp - 1][k], px2 = in.x2[warp - 1][k], ph_old = EXACT ? in.hhi[warp - 1][k] : 0;
         else if (k > 0) px = in.x[NW - 1][k - 1], pv = in.v[NW - 1][k - 1], px2 = in.x2[NW - 1][k - 1], ph_old = EXACT ? in.hhi[NW - 1][k - 1] : 0;
+        else px = lc.X0 << 16, pv = UF << 16, px2 = lc.X20 << 16;  // first column (:156-159)
       }
-      uint32_t XT1 = __funnelshift_l(px, X[k], 16), VT1 = __funnelshift_l(pv, V[k], 16), X2T1 = __funnelshift_l(px2, X2[k], 16);
-      if (p == 0) {
-        XT1 = (XT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q - e);
-        X2T1 = (X2T1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)(-q2 - e2);
-        VT1 = (VT1 & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst;
-      }
+      const uint32_t XT1 = __funnelshift_l(px, X[k], 16), VT1 = __funnelshift_l(pv, V[k], 16), X2T1 = __funnelshift_l(px2, X2[k], 16);
       uint32_t Uo = U[k], Yo = Y[k], Y2o = Y2[k];
-      if (en0 == r && (r >> 1) == p) {
-        if (r & 1) Uo = (Uo & 0x0000ffffu) | (uint32_t)(uint16_t)(int16_t)ufirst << 16, Yo = (Yo & 0x0000ffffu) | (NQE & 0xffff0000u), Y2o = (Y2o & 0x0000ffffu) | (NQE2 & 0xffff0000u);
-        else Uo = (Uo & 0xffff0000u) | (uint32_t)(uint16_t)(int16_t)ufirst, Yo = (Yo & 0xffff0000u) | (NQE & 0xffffu), Y2o = (Y2o & 0xffff0000u) | (NQE2 & 0xffffu);
+      if (en0 == r && (r >> 1) == p) {  // first row (:160-163)
+        if (r & 1) Uo = (Uo & 0x0000ffffu) | UF << 16, Yo = (Yo & 0x0000ffffu) | lc.Y0 << 16, Y2o = (Y2o & 0x0000ffffu) | lc.Y20 << 16;
+        else Uo = (Uo & 0xffff0000u) | UF, Yo = (Yo & 0xffff0000u) | lc.Y0, Y2o = (Y2o & 0xffff0000u) | lc.Y20;
       }
       const int qi = qbase + 2 * p;
       const uint32_t qq = qi + 1 < qh_len ? ((uint32_t)QH[qi] | (uint32_t)QH[qi + 1] << 16) : 0u;
-      const uint32_t ne = __vminu2(TQ[k] ^ qq, ONE);
-      uint32_t Z = __vadd2(MIS, (ne ^ ONE) * DMCH);
-      const uint32_t isn = __vminu2((TQ[k] | qq) & 0x00040004u, ONE) * 0xffffu;
-      Z = (Z & ~isn) | (SCN & isn);
-      uint32_t A = __vadd2(XT1, VT1), B = __vadd2(Yo, Uo), A2 = __vadd2(X2T1, VT1), B2 = __vadd2(Y2o, Uo);
-      bool ph, pl;
-      uint32_t dl = 0, dh = 0;
-      Z = __vibmax_s16x2(Z, A, &ph, &pl);  dl = pl ? dl : 1u; dh = ph ? dh : 1u;
-      Z = __vibmax_s16x2(Z, B, &ph, &pl);  dl = pl ? dl : 2u; dh = ph ? dh : 2u;
-      Z = __vibmax_s16x2(Z, A2, &ph, &pl); dl = pl ? dl : 3u; dh = ph ? dh : 3u;
-      Z = __vibmax_s16x2(Z, B2, &ph, &pl); dl = pl ? dl : 4u; dh = ph ? dh : 4u;
-      Z = __vmins2(Z, MCH);
-      const uint32_t NZ = neg2(Z);
-      const uint32_t Un = __vadd2(Z, neg2(VT1)), Vn = __vadd2(Z, neg2(Uo));
-      const uint32_t T1 = __vadd2(NZ, QP), T2 = __vadd2(NZ, Q2P);
-      A = __vadd2(A, T1), B = __vadd2(B, T1), A2 = __vadd2(A2, T2), B2 = __vadd2(B2, T2);
-      (void)__vibmax_s16x2(A, ONE, &ph, &pl);  dl |= pl ? 0x08u : 0u; dh |= ph ? 0x08u : 0u;
-      (void)__vibmax_s16x2(B, ONE, &ph, &pl);  dl |= pl ? 0x10u : 0u; dh |= ph ? 0x10u : 0u;
-      (void)__vibmax_s16x2(A2, ONE, &ph, &pl); dl |= pl ? 0x20u : 0u; dh |= ph ? 0x20u : 0u;
-      (void)__vibmax_s16x2(B2, ONE, &ph, &pl); dl |= pl ? 0x40u : 0u; dh |= ph ? 0x40u : 0u;
-      A = __vmaxs2(A, 0u), B = __vmaxs2(B, 0u), A2 = __vmaxs2(A2, 0u), B2 = __vmaxs2(B2, 0u);
+      uint32_t Un, Vn;
+      const uint32_t d16 = pair_step(lc, has_n, XT1, VT1, X2T1, Uo, Yo, Y2o, TQ[k], qq, Un, Vn, X[k], Y[k], X2[k], Y2[k]);
       U[k] = Un, V[k] = Vn;
-      X[k] = __vadd2(A, NQE), Y[k] = __vadd2(B, NQE), X2[k] = __vadd2(A2, NQE2), Y2[k] = __vadd2(B2, NQE2);
-      if (p <= p_hi) *(uint16_t *)(prow + 2 * p) = (uint16_t)(dl | dh << 8);
+      if (p <= p_hi) *(uint16_t *)(prow + 2 * p) = (uint16_t)d16;
       const int t_lo = 2 * p, t_hi = 2 * p + 1;
       if (EXACT) {  // H[t] += v[t] for st0 <= t < en0; H[en0] = H[en0-1] (previous anti-diagonal) + u[en0]   (:333-357)
         const int32_t hl_old = HL[k];
         if (r == 0) {
-          if (p == 0) HL[k] = lo16(Vn) - qe;
+          if (p == 0) HL[k] = dec_lo(Vn) - qe;
         } else {
-          if (t_lo >= st0 && t_lo < en0) HL[k] += lo16(Vn);
-          else if (t_lo == en0) HL[k] = en0 > 0 ? ph_old + lo16(Un) : HL[k] + lo16(Vn);
-          if (t_hi >= st0 && t_hi < en0) HH[k] += hi16(Vn);
-          else if (t_hi == en0) HH[k] = hl_old + hi16(Un);
+          if (t_lo >= st0 && t_lo < en0) HL[k] += dec_lo(Vn);
+          else if (t_lo == en0) HL[k] = en0 > 0 ? ph_old + dec_lo(Un) : HL[k] + dec_lo(Vn);
+          if (t_hi >= st0 && t_hi < en0) HH[k] += dec_hi(Vn);
+          else if (t_hi == en0) HH[k] = hl_old + dec_hi(Un);
         }
 #pragma unroll
         for (int hsel = 0; hsel < 2; ++hsel) {
@@ -541,12 +562,7 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
             if (t == st0) out.hst0 = h;
           }
         }
-      } else {
-        if (t_lo == last) out.d0 = lo16(Vn);
-        if (t_hi == last) out.d0 = hi16(Vn);
-        if (t_lo == last + 1) out.d1 = lo16(Un);
-        if (t_hi == last + 1) out.d1 = hi16(Un);
-      }
+      } else if (p == p_end && en0 == tlen - 1) vsum += (Vn >> sh_end) & 0xffffu;
       if (lane == 31) {
         out.x[warp][k] = X[k], out.v[warp][k] = V[k], out.x2[warp][k] = X2[k];
         if (EXACT) out.hhi[warp][k] = HH[k];
@@ -586,22 +602,18 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
       }
       if (!brk && r == n_row - 1 && en0 == tlen - 1) ez.score = hen;
       if (brk) break;
-    } else {
-      const int d0 = out.d0, d1 = out.d1;
-      if (r > 0) {
-        const bool in0 = last >= st0 && last <= en0, in1 = last + 1 >= st0 && last + 1 <= en0;
-        if (in0 && in1) {
-          if (d0 > d1) H0 += d0;
-          else H0 += d1, ++last;
-        } else if (in0) H0 += d0;
-        else ++last, H0 += d1;
-      } else H0 = d0 - qe, last = 0;
-      if (r == n_row - 1) ez.score = H0;
+    }
+  }
+  if (!EXACT) {
+    if ((tid % NT) == (p_end % NT)) {  // qlen halves of 8*v + 0x4000 each, plus the boundary H(tlen-1, -1)
+      const int gap1 = lc.q + lc.e * tlen, gap2 = lc.q2 + lc.e2 * tlen;
+      mail[0].d0 = ((int32_t)(vsum - (uint32_t)qlen * kLB) >> 3) - (gap1 < gap2 ? gap1 : gap2);
     }
   }
   __threadfence_block();
   __syncthreads();
   if (tid == 0) {
+    if (!EXACT) ez.score = mail[0].d0;
     const unsigned long long tr1 = trace::begin();
     finish_job(job, jid, ez, r_done + 1, tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed,
                cig_counter, outs);
@@ -1002,6 +1014,8 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
 
   // problems whose state is larger than this keep it in the global slab (L2-resident) instead of shared memory
   static const size_t state_limit = getenv("PGMM_STATE_SMEM_KB") ? std::min(kSmemMax, (size_t)atoi(getenv("PGMM_STATE_SMEM_KB")) * 1024) : kSmemMax;
+  LaneConsts lane_consts;
+  lane_consts.init(sc);
   size_t pos = 0;
   while (pos < order.size()) {
     // ---- carve one wave ----
@@ -1112,7 +1126,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
         }
         const int nj = (int)cls[20].size();
         ksw_fill_small_kernel<<<(nj + kFillWarps - 1) / kFillWarps, kFillWarps * 32, per_warp * kFillWarps, cs>>>(
-            m.d_jobs.p, m.d_ids.p + cls_off[20], nj, d_q, d_t, sc, q_cap, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p);
+            m.d_jobs.p, m.d_ids.p + cls_off[20], nj, d_q, d_t, sc, lane_consts, q_cap, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p);
         PGMM_CUDA(cudaGetLastError());
       } else if (c > 20) {
 #define PGMM_WIDE(NW, KP, EX)                                                                                                   \
@@ -1123,7 +1137,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
       attr_set = true;                                                                                                          \
     }                                                                                                                           \
     ksw_fill_wide_kernel<NW, KP, EX><<<(unsigned)cls[c].size(), NW * 32, std::max(cls_smem[c], wide_min_smem), cs>>>(                                    \
-        m.d_jobs.p, m.d_ids.p + cls_off[c], d_q, d_t, sc, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p); \
+        m.d_jobs.p, m.d_ids.p + cls_off[c], d_q, d_t, sc, lane_consts, m.p_arena.p, m.cig_arena.p, m.d_outs.p, m.cig_packed.p, m.d_counter.p); \
     PGMM_CUDA(cudaGetLastError());                                                                                              \
   } while (0)
         switch (c - 21) {
