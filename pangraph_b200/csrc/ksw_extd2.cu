@@ -93,17 +93,18 @@ __device__ __forceinline__ void cta_bar() {
 __device__ __noinline__ void finish_job(const KswJob &job, int jid, EzState ez, int n_diag, int w, bool abs_layout, int stride,
                                         const uint8_t *__restrict__ P, const uint8_t *TQ8, const uint8_t *QR8, const KswScoring &sc,
                                         uint32_t *__restrict__ cig_arena, uint32_t *__restrict__ cig_packed,
-                                        unsigned long long *__restrict__ cig_counter, KswOut *__restrict__ outs) {
+                                        unsigned long long *__restrict__ cig_counter, KswOut *__restrict__ outs, int n_walked = -1) {
   const int qlen = job.qlen, tlen = job.tlen, flag = job.flag;
   {
     int i = -1, j = -1, n = 0, state = 0;
-    bool go = true;
+    bool go = n_walked < 0;  // a warp-cooperative walk (walk_warp) has already left its n_walked runs in the arena
+    if (!go) n = n_walked;
     if (!ez.zdropped && !(flag & KSW_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
     else if (!ez.zdropped && (flag & KSW_EXTZ_ONLY) && ez.mqe + job.end_bonus > ez.max) ez.reach_end = 1, i = ez.mqe_t, j = qlen - 1;
     else if (ez.max_t >= 0 && ez.max_q >= 0) i = ez.max_t, j = ez.max_q;
     else go = false;
     uint32_t *cig = cig_arena + job.cig_off;
-    if (go) {
+    if (go && n_walked < 0) {
       uint32_t last = 0;  // run being built: len<<4|op, flushed when the op changes
       while (i >= 0 && j >= 0) {
         const int r = i + j;
@@ -193,6 +194,52 @@ __device__ __noinline__ void finish_job(const KswJob &job, int jid, EzState ez, 
     o.n_diag = n_diag;
     outs[jid] = o;
   }
+}
+
+// The traceback walk of finish_job for a problem whose rows hold all target positions (K5a / K5b layout), run by a whole
+// warp: from a cell reached in state 0 the 32 lanes read the next 32 cells of the DIAGONAL at once and the walk takes all
+// leading ones whose direction is 0 in one step (at 1 % divergence that is almost the whole path: ~n/32 + #gaps dependent
+// loads instead of n).  Cells inside a gap are walked one at a time (every lane reads the same byte).  Runs are written by
+// lane 0, back to front like the serial walk; returns their number.  Same rules as ksw2.h:127-159.
+__device__ __forceinline__ int walk_warp(int i, int j, int stride, const uint8_t *__restrict__ P, uint32_t *__restrict__ cig, int lane) {
+  int n = 0, state = 0;
+  uint32_t last = 0;
+  const auto push = [&](uint32_t op, uint32_t len) {
+    if (last != 0 && (last & 0xf) == op) last += len << 4;
+    else {
+      if (last != 0 && lane == 0) cig[n] = last;
+      n += last != 0;
+      last = len << 4 | op;
+    }
+  };
+  while (i >= 0 && j >= 0) {
+    if (state == 0) {
+      const bool valid = i - lane >= 0 && j - lane >= 0;
+      const int tmp = valid ? __ldcg(P + (size_t)(i + j - 2 * lane) * stride + (i - lane)) : 7;
+      const unsigned stop = __ballot_sync(0xffffffffu, (tmp & 7) != 0);
+      const int run = stop ? __ffs(stop) - 1 : 32;  // leading diagonal cells
+      if (run > 0) push(0, (uint32_t)run), i -= run, j -= run;
+      if (run == 32 || i < 0 || j < 0) continue;
+      state = __shfl_sync(0xffffffffu, tmp, run) & 7;  // the cell that leaves the diagonal: state was 0, so it takes its direction
+    } else {
+      const int tmp = __ldcg(P + (size_t)(i + j) * stride + i);
+      if (!((tmp >> (state + 2)) & 1)) state = 0;
+      if (state == 0) state = tmp & 7;
+      if (state == 0) {  // back on the diagonal: this cell is a match, continue with the wide reads
+        push(0, 1), --i, --j;
+        continue;
+      }
+    }
+    if (state == 1 || state == 3) push(2, 1), --i;
+    else push(1, 1), --j;
+  }
+  if (i >= 0) push(2, (uint32_t)(i + 1));  // leading deletion
+  if (j >= 0) push(1, (uint32_t)(j + 1));  // leading insertion
+  if (last != 0) {
+    if (lane == 0) cig[n] = last;
+    ++n;
+  }
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -294,7 +341,7 @@ constexpr int kFillMaxT = 256;    // target window limit (4 slots x 32 lanes x 2
 constexpr int kFillMaxQ = 1024;   // query window limit (two 16-bit copies of the reversed query in shared memory)
 
 
-__global__ void __launch_bounds__(kFillWarps * 32, 6) ksw_fill_small_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
+__global__ void __launch_bounds__(kFillWarps * 32, 7) ksw_fill_small_kernel(const KswJob *__restrict__ jobs, const int *__restrict__ job_ids,
                                                                          int n_jobs, const uint8_t *__restrict__ qcodes,
                                                                          const uint8_t *__restrict__ tcodes, KswScoring sc,
                                                                          const __grid_constant__ LaneConsts lc, int q_cap,
@@ -408,7 +455,10 @@ __global__ void __launch_bounds__(kFillWarps * 32, 6) ksw_fill_small_kernel(cons
     H0 = ((int32_t)(tot - (uint32_t)qlen * kLB) >> 3) - (gap1 < gap2 ? gap1 : gap2);
   }
 
-  __threadfence_block();  // every lane's traceback bytes must be visible to the lane that walks them
+  __threadfence_block();  // every lane's traceback bytes must be visible to the lanes that walk them
+  __syncwarp();
+  const unsigned long long tr1 = trace::begin();
+  const int n_runs = walk_warp(tlen - 1, qlen - 1, Tp, P, cig_arena + job.cig_off, lane);  // first-pass fill: from the last cell
   __syncwarp();
   if (lane == 0) {
     EzState ez;
@@ -416,8 +466,7 @@ __global__ void __launch_bounds__(kFillWarps * 32, 6) ksw_fill_small_kernel(cons
     ez.max = 0, ez.mqe = ez.mte = KSW_NEG_INF;
     ez.zdropped = 0, ez.reach_end = 0;
     ez.score = H0;  // the last anti-diagonal is the single cell (tlen-1, qlen-1)
-    const unsigned long long tr1 = trace::begin();
-    finish_job(job, jid, ez, n_row, /*w=*/tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed, cig_counter, outs);
+    finish_job(job, jid, ez, n_row, /*w=*/tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed, cig_counter, outs, n_runs);
     if (warp == 0) trace::emit(1, tr0, tr1, (unsigned)n_row);
     span_end(cig_counter);
   }
@@ -612,13 +661,21 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
   }
   __threadfence_block();
   __syncthreads();
-  if (tid == 0) {
-    if (!EXACT) ez.score = mail[0].d0;
+  if (warp == 0) {
     const unsigned long long tr1 = trace::begin();
-    finish_job(job, jid, ez, r_done + 1, tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed,
-               cig_counter, outs);
-    trace::emit(EXACT ? 3 : 2, tr0, tr1, (unsigned)(r_done + 1));
-    span_end(cig_counter);
+    // where the traceback starts (ksw2_extd2_sse.c:388-399 for the two flag sets of a fill: no KSW_EZ_EXTZ_ONLY)
+    int wi = -1, wj = -1;
+    if (!ez.zdropped) wi = tlen - 1, wj = qlen - 1;
+    else if (ez.max_t >= 0 && ez.max_q >= 0) wi = ez.max_t, wj = ez.max_q;
+    const int n_runs = wi >= 0 ? walk_warp(wi, wj, Tp, P, cig_arena + job.cig_off, lane) : 0;
+    __syncwarp();
+    if (tid == 0) {
+      if (!EXACT) ez.score = mail[0].d0;
+      finish_job(job, jid, ez, r_done + 1, tlen > qlen ? tlen : qlen, /*abs_layout=*/true, Tp, P, TQ8, QR8, sc, cig_arena, cig_packed,
+                 cig_counter, outs, n_runs);
+      trace::emit(EXACT ? 3 : 2, tr0, tr1, (unsigned)(r_done + 1));
+      span_end(cig_counter);
+    }
   }
 }
 
