@@ -367,6 +367,16 @@ def ours(args):
     clocks = sampler.stop() if sampler else None
     free1, total_mem = torch.cuda.mem_get_info()
 
+    # ---- solo pass (not part of any timed region): a few rounds one at a time, nothing else on the GPU, so that the
+    # CUDA-event duration of a launch is the kernel's own time (under load the launches of up to 64 rounds share the SMs
+    # and wait in hardware queues: their event times say how long a wave takes, not how fast the kernel is) ----
+    sync()
+    for j in range(args.solo_rounds):
+        n_regs, regs = round_resident(resident[j % len(resident)])
+        free_regs(abi, n_regs, regs)
+    sync()
+    st_solo = abi.get_stats(reset=True)
+
     bp_rank = args.steps * sum(bp_pair[p] for p in pairs_of_step(0))
     bp_rank_e2e = sum(bp_pair[p] for s in range(args.steps) for p in pairs_of_step(args.warmup + s))
     bp_all = torch.tensor([bp_rank, bp_rank_e2e], dtype=torch.float64, device="cuda")
@@ -403,25 +413,31 @@ def ours(args):
                 "ksw_fill_wide_kernel (K5b, long fills across inversions / big indels)": "k5b"}
         tp = os.path.join(ROOT, "profiles", "dp_traffic.json")
         traffic_tbl = json.load(open(tp)) if os.path.exists(tp) else {}
+        def family(st, key):
+            ms, cells, bases, ln = (st[f"{key}_{x}"] for x in ("ms", "cells", "bases", "launches"))
+            sec = ms / 1e3
+            return {"ms_total": ms, "launches": int(ln), "ms_per_launch": ms / max(1, ln), "cells": cells,
+                    "cells_per_launch": cells / max(1, ln),
+                    "gcups": cells / sec / 1e9 if ms > 0 else 0.0,
+                    "achieved_int_gops": 50.0 * cells / sec / 1e9 if ms > 0 else 0.0,
+                    "int_frac": 50.0 * cells / sec / 1e9 / int_peak if ms > 0 else 0.0,
+                    "gb_per_s": (cells + bases) / sec / 1e9 if ms > 0 else 0.0,
+                    "hbm_frac": (cells + bases) / sec / 1e9 / peak if ms > 0 else 0.0}
+
         dp_kernels = {}
         for name, key in fams.items():
-            ms, cells, bases, ln = (st_res[f"{key}_{x}"] for x in ("ms", "cells", "bases", "launches"))
-            sec = ms / 1e3
-            dp_kernels[name] = {"ms_total": ms, "launches": int(ln), "ms_per_launch": ms / max(1, ln), "cells": cells,
-                                "cells_per_launch": cells / max(1, ln),
-                                "gcups": cells / sec / 1e9 if ms > 0 else 0.0,
-                                "achieved_int_gops": 50.0 * cells / sec / 1e9 if ms > 0 else 0.0,
-                                "int_frac": 50.0 * cells / sec / 1e9 / int_peak if ms > 0 else 0.0,
-                                "gb_per_s": (cells + bases) / sec / 1e9 if ms > 0 else 0.0,
-                                "hbm_frac": (cells + bases) / sec / 1e9 / peak if ms > 0 else 0.0,
-                                "traffic_bytes_per_launch_ncu": traffic_tbl.get(key)}
+            dp_kernels[name] = family(st_res, key)  # under load: launches of all rounds in flight share the GPU
+            dp_kernels[name]["traffic_bytes_per_launch_ncu"] = traffic_tbl.get(key)
+            dp_kernels[name]["solo"] = family(st_solo, key)  # one round at a time: the kernel's own duration
         # K4 (chain score fill): latency-bound dependent chain; reported as anchors/us.  Algorithmic bytes per anchor = 25
         # read by the fill (x, y, q_span and the 16-byte window record of the prep kernel) + 12 written (f, p, v)
         k4_ms, k4_anchors, k4_launches = st_res["chain_kernel_ms"], st_res["chain_anchors"], max(1.0, st_res["chain_launches"])
         k4 = {"ms_total": k4_ms, "launches": int(k4_launches), "ms_per_launch": k4_ms / k4_launches, "anchors": k4_anchors,
-              "bound": "latency (dependent chain per anchor segment)",
+              "bound": "latency (K4p: ~20 short launches per fixed-point iteration, pointer jumping over the predecessor forest)",
               "anchors_per_us": k4_anchors / (k4_ms * 1e3) if k4_ms > 0 else 0.0,
-              "gb_per_s": 37.0 * k4_anchors / (k4_ms / 1e3) / 1e9 if k4_ms > 0 else 0.0}
+              "gb_per_s": 37.0 * k4_anchors / (k4_ms / 1e3) / 1e9 if k4_ms > 0 else 0.0,
+              "solo": {"ms_per_round": st_solo["chain_kernel_ms"] / max(1, args.solo_rounds), "launches_per_round": st_solo["chain_launches"] / max(1, args.solo_rounds),
+                       "anchors_per_us": st_solo["chain_anchors"] / (st_solo["chain_kernel_ms"] * 1e3) if st_solo["chain_kernel_ms"] > 0 else 0.0}}
         tot_ms = (sum(v["ms_total"] for v in dp_kernels.values()) + k4_ms) or 1.0
         tot_cells = sum(v["cells"] for v in dp_kernels.values()) or 1.0
         for v in list(dp_kernels.values()) + [k4]:
@@ -429,7 +445,10 @@ def ours(args):
         for v in dp_kernels.values():
             v["share_of_cells"] = v["cells"] / tot_cells
         dom = max(dp_kernels, key=lambda k: dp_kernels[k]["cells"])  # the kernel that does most of the DP cells
-        d = dp_kernels[dom]
+        d_load = dp_kernels[dom]
+        d = dict(d_load["solo"]) if d_load["solo"]["ms_total"] > 0 else dict(d_load)
+        d["share_of_cells"], d["share_of_kernel_time"] = d_load["share_of_cells"], d_load["share_of_kernel_time"]
+        d["traffic_bytes_per_launch_ncu"] = d_load["traffic_bytes_per_launch_ncu"]
         rounds_timed = args.steps * P
         line = {
             "metric": METRIC, "value": bp_total / t_res / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -454,16 +473,20 @@ def ours(args):
             # for is given next to it and is small by construction (1 traceback byte per ~50 lane-ops).
             "roofline": {"bound": "int-issue", "kernel": dom, "achieved": d["achieved_int_gops"], "peak": int_peak,
                          "unit": "G int32-lane-ops/s", "frac": d["int_frac"],
-                         "definition": "achieved = 50 lane-ops x cells of the family / its summed per-launch CUDA-event time; "
-                                       f"peak = {n_sm} SMs x 128 lanes x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
+                         "definition": "achieved = 50 lane-ops x cells of the family / its summed per-launch CUDA-event time, launches timed "
+                                       f"with CUDA events on their own stream in a solo pass of {args.solo_rounds} rounds after the timed regions (one round at "
+                                       f"a time, so a launch has the GPU to itself like in the ncu launch list); peak = {n_sm} SMs x 128 lanes x "
+                                       f"{sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
                          "gcups": d["gcups"], "launches": d["launches"], "ms_per_launch": d["ms_per_launch"],
                          "cells_per_launch": d["cells_per_launch"], "share_of_cells": d["share_of_cells"],
                          "share_of_kernel_time": d["share_of_kernel_time"],
                          "hbm": {"achieved": d["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": d["hbm_frac"], "peak_source": peak_src,
                                  "algorithmic_bytes": "1 traceback byte per in-band cell + the bases each problem reads"},
                          "traffic": d["traffic_bytes_per_launch_ncu"],
-                         "note": "launches of concurrent rounds share the GPU, so a launch's event time under load is longer than alone; "
-                                 "per-launch solo figures: profiles/"},
+                         "under_load": {"gcups": d_load["gcups"], "ms_per_launch": d_load["ms_per_launch"], "launches": d_load["launches"],
+                                        "cells_per_launch": d_load["cells_per_launch"], "int_frac": d_load["int_frac"],
+                                        "note": "event times of launches inside the timed region: up to 64 rounds' launches share the SMs and "
+                                                "wait in hardware queues, so this measures wave latency, not kernel speed"}},
             "kernels": dp_kernels,
             "chain_fill_kernel (K4)": k4,
             "cpu_baseline": cpu_baseline,
@@ -500,6 +523,7 @@ def main():
     ap.add_argument("--contexts", type=int, default=24, help="execution contexts of the library (PGMM_CONTEXTS)")
     ap.add_argument("--pool", type=int, default=32, help="distinct genome pairs generated per rank (rounds cycle through them)")
     ap.add_argument("--ref-rounds-per-step", type=int, default=0, help="reference arm / cpu_baseline: full-size rounds per step (0 = 2 per host thread)")
+    ap.add_argument("--solo-rounds", type=int, default=4, help="rounds run one at a time after the timed regions to time each kernel family alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against oracle/_ref (profiling runs only)")
     ap.add_argument("--parity-all-ranks", action="store_true")
