@@ -314,6 +314,30 @@ PGMM_API int64_t pgmm_chain_rmq(uint64_t *xy, int64_t n, int max_dist, int max_d
 PGMM_API int pgmm_cta_trace_begin(uint64_t capacity);
 PGMM_API int64_t pgmm_cta_trace_end(void *out, uint64_t max_n);
 
+/* ===================== Part 4: map_variations ===================== */
+
+/* The Edit the reference's map_variations returns (packages/pangraph/src/align/map_variations.rs:39-80,
+ * packages/pangraph/src/pangraph/edits.rs: Sub {pos, alt}, Del {pos, len}, Ins {pos, seq}).  Arrays are malloc blocks owned by the
+ * record; pgmm_edits_free releases them.  status: 0 ok; -1 where the reference returns Err (a character outside
+ * "TAWCYMHGKRDSBVN", an empty query); -2 / -3 where the reference panics (backtrace dead end / outside the band);
+ * -4 band wider than 24 000 columns (the kernel's row state; reported, never guessed). */
+typedef struct pgmm_edit_s {
+  int32_t status, hit_boundary, attempts, band_width, score;
+  int32_t n_sub, n_del, n_ins;
+  int32_t *sub_pos; char *sub_chr;          /* substitutions, ascending position */
+  int32_t *del_pos, *del_len;               /* inner deletions ascending, then the leading, then the trailing one */
+  int32_t *ins_pos, *ins_len; char *ins_seq;/* insertions ascending; pos = position after the insertion; bases concatenated */
+} pgmm_edit_t;
+
+/* n problems at once: qry[i] against ref[i] inside the band (mean_shift[i], band_width[i] + extra_band_width), retried with a
+ * doubled band up to max_alignment_attempts times while the traceback touches the band boundary (align.rs:52-63).
+ * Defaults of the reference: extra_band_width 5, max_alignment_attempts 4 (commands/build/build_args.rs:76-85).
+ * *out = malloc array of n records.  stats (optional, 4 doubles): kernel ms, band cells, problem attempts, launches. */
+PGMM_API int pgmm_map_variations_batch(int n, const char *const *refs, const int32_t *ref_lens, const char *const *qrys,
+                                       const int32_t *qry_lens, const int32_t *mean_shift, const int32_t *band_width,
+                                       int extra_band_width, int max_alignment_attempts, pgmm_edit_t **out, double *stats);
+PGMM_API void pgmm_edits_free(pgmm_edit_t *edits, int n);
+
 /* counters since the last reset: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells
  * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] kernel launches [11..16] wall ms of the phases of
  * pgmm_map_batch (encode, seeding, sort+chain+plan, DP waves, stitching between waves, final filters)

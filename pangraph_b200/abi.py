@@ -443,3 +443,50 @@ def find_filtered_matches(blocks, args):
     if rc != 0:
         raise RuntimeError(f"find_filtered_matches -> {rc}")
     return _take_alns(out, cnt)
+
+
+# ---------------- map_variations (include/pgmm_b200.h part 4) ----------------
+
+class pgmm_edit_t(C.Structure):
+    _fields_ = [("status", C.c_int32), ("hit_boundary", C.c_int32), ("attempts", C.c_int32), ("band_width", C.c_int32),
+                ("score", C.c_int32), ("n_sub", C.c_int32), ("n_del", C.c_int32), ("n_ins", C.c_int32),
+                ("sub_pos", C.POINTER(C.c_int32)), ("sub_chr", C.POINTER(C.c_char)), ("del_pos", C.POINTER(C.c_int32)),
+                ("del_len", C.POINTER(C.c_int32)), ("ins_pos", C.POINTER(C.c_int32)), ("ins_len", C.POINTER(C.c_int32)),
+                ("ins_seq", C.POINTER(C.c_char))]
+
+
+def map_variations_batch(refs, qrys, mean_shifts, band_widths, extra_band_width=5, max_alignment_attempts=4, with_stats=False):
+    """map_variations (packages/pangraph/src/align/map_variations.rs:39-80) for a batch of (ref, qry) pairs.
+    -> per problem dict(subs=[(pos, chr)], dels=[(pos, len)], inss=[(pos, seq)], hit_boundary, attempts, score) or the negative
+    status where the reference returns Err / panics."""
+    L = lib()
+    n = len(refs)
+    refs = [s if isinstance(s, bytes) else s.encode() for s in refs]
+    qrys = [s if isinstance(s, bytes) else s.encode() for s in qrys]
+    ra, qa = (C.c_char_p * n)(*refs), (C.c_char_p * n)(*qrys)
+    rl, ql = (C.c_int32 * n)(*[len(s) for s in refs]), (C.c_int32 * n)(*[len(s) for s in qrys])
+    ms, bw = (C.c_int32 * n)(*mean_shifts), (C.c_int32 * n)(*band_widths)
+    out = C.POINTER(pgmm_edit_t)()
+    st = (C.c_double * 4)()
+    L.pgmm_map_variations_batch.restype = C.c_int
+    rc = L.pgmm_map_variations_batch(n, ra, rl, qa, ql, ms, bw, extra_band_width, max_alignment_attempts, C.byref(out), st)
+    if rc != 0:
+        raise RuntimeError(f"pgmm_map_variations_batch -> {rc}")
+    res = []
+    for i in range(n):
+        e = out[i]
+        if e.status != 0:
+            res.append(int(e.status))
+            continue
+        ins, off = [], 0
+        for k in range(e.n_ins):
+            ins.append((int(e.ins_pos[k]), C.string_at(C.addressof(e.ins_seq.contents) + off, e.ins_len[k]).decode()))
+            off += e.ins_len[k]
+        res.append(dict(subs=[(int(e.sub_pos[k]), e.sub_chr[k].decode()) for k in range(e.n_sub)],
+                        dels=[(int(e.del_pos[k]), int(e.del_len[k])) for k in range(e.n_del)], inss=ins,
+                        hit_boundary=bool(e.hit_boundary), attempts=int(e.attempts), score=int(e.score)))
+    L.pgmm_edits_free.argtypes = [C.POINTER(pgmm_edit_t), C.c_int]
+    L.pgmm_edits_free(out, n)
+    if with_stats:
+        return res, dict(kernel_ms=st[0], cells=st[1], problems=st[2], launches=st[3])
+    return res

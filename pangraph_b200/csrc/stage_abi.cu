@@ -3,6 +3,7 @@
 #include "../../include/pgmm_b200.h"
 #include "chain_fill.h"
 #include "ksw_extd2.h"
+#include "nextalign.h"
 #include "pgmm_cuda.h"
 
 #include <algorithm>
@@ -123,4 +124,46 @@ extern "C" int64_t pgmm_cta_trace_end(void *out, uint64_t max_n) {
   cudaFree(g_trace_buf), cudaFree(g_trace_cnt);
   g_trace_buf = nullptr, g_trace_cnt = nullptr;
   return (int64_t)n;
+}
+
+// ---- map_variations (Part 4) ----
+template <class T>
+static T *dup_array(const T *src, size_t n) {
+  T *p = (T *)malloc(std::max<size_t>(1, n) * sizeof(T));
+  if (n) memcpy(p, src, n * sizeof(T));
+  return p;
+}
+
+extern "C" int pgmm_map_variations_batch(int n, const char *const *refs, const int32_t *ref_lens, const char *const *qrys,
+                                         const int32_t *qry_lens, const int32_t *mean_shift, const int32_t *band_width,
+                                         int extra_band_width, int max_alignment_attempts, pgmm_edit_t **out, double *stats) {
+  require_device();
+  std::vector<na::Problem> probs((size_t)std::max(0, n));
+  for (int i = 0; i < n; ++i) probs[i] = na::Problem{refs[i], qrys[i], ref_lens[i], qry_lens[i], mean_shift[i], band_width[i]};
+  std::vector<na::Edit> edits;
+  na::Stats st;
+  na::run_batch(probs, extra_band_width, max_alignment_attempts, edits, &st);
+  pgmm_edit_t *res = (pgmm_edit_t *)calloc((size_t)std::max(1, n), sizeof(pgmm_edit_t));
+  for (int i = 0; i < n; ++i) {
+    const na::Edit &e = edits[i];
+    pgmm_edit_t &r = res[i];
+    r.status = e.status, r.hit_boundary = e.hit_boundary, r.attempts = e.attempts, r.band_width = e.band_width, r.score = e.score;
+    r.n_sub = (int32_t)e.sub_pos.size(), r.n_del = (int32_t)e.del_pos.size(), r.n_ins = (int32_t)e.ins_pos.size();
+    r.sub_pos = dup_array(e.sub_pos.data(), e.sub_pos.size()), r.sub_chr = dup_array(e.sub_chr.data(), e.sub_chr.size());
+    r.del_pos = dup_array(e.del_pos.data(), e.del_pos.size()), r.del_len = dup_array(e.del_len.data(), e.del_len.size());
+    r.ins_pos = dup_array(e.ins_pos.data(), e.ins_pos.size()), r.ins_len = dup_array(e.ins_len.data(), e.ins_len.size());
+    r.ins_seq = dup_array(e.ins_seq.data(), e.ins_seq.size());
+  }
+  *out = res;
+  if (stats) stats[0] = st.kernel_ms, stats[1] = (double)st.cells, stats[2] = (double)st.problems, stats[3] = (double)st.launches;
+  return 0;
+}
+
+extern "C" void pgmm_edits_free(pgmm_edit_t *edits, int n) {
+  if (!edits) return;
+  for (int i = 0; i < n; ++i) {
+    free(edits[i].sub_pos), free(edits[i].sub_chr), free(edits[i].del_pos), free(edits[i].del_len);
+    free(edits[i].ins_pos), free(edits[i].ins_len), free(edits[i].ins_seq);
+  }
+  free(edits);
 }
