@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(32) nextalign_kernel(const Job *__restrict__ j
     const int q0 = g.b(ri) + lane * m;  // query column of this lane's first band column
     const int beg = row_ok ? g.begin(ri) : 0, en = row_ok ? g.end(ri) : 0;
     const int rc = (row_ok && ri > 0) ? R[ri - 1] : 0;
+    const RowGeom rw = (row_ok && ri > 0) ? row_geom(g, ri) : RowGeom{0, 0, 0, 0};
     for (int c = 0; c < m; ++c) {
       const int K = lane * m + c, qpos = q0 + c;
       if (row_ok && K < W && qpos >= beg && qpos < en) {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(32) nextalign_kernel(const Job *__restrict__ j
           CellIn in;
           in.diagS = S[K], in.leftS = curS, in.ref_gaps = rg, in.upS = S[K + 1], in.qry_gaps = QG[K + 1];
           in.qc = qpos > 0 ? Q[qpos - 1] : 0, in.rc = rc;
-          o = cell(g, p, ri, qpos, in);
+          o = cell(g, p, rw, ri, qpos, in);
         }
         S[K] = o.S, QG[K] = o.qry_gaps, rg = o.ref_gaps, curS = o.S;
         B[(int64_t)ri * W + K] = (uint8_t)o.path;
@@ -103,9 +104,10 @@ __global__ void __launch_bounds__(32) nextalign_kernel(const Job *__restrict__ j
           else upS = row0_score(p, g.qlen), qg = kNoAlign;      // row 0 spans the whole matrix (forced begin)
           for (int ri = max(i1, 0) + 1; ri <= g.rlen; ++ri) {
             CellIn in;
-            in.diagS = 0, in.leftS = 0, in.ref_gaps = kNoAlign, in.upS = upS, in.qry_gaps = qg;
+            in.diagS = row0_score(p, g.qlen - 1);  // only read by (1, qlen) under the forced full row 0
+            in.leftS = 0, in.ref_gaps = kNoAlign, in.upS = upS, in.qry_gaps = qg;
             in.qc = g.qlen > 0 ? Q[g.qlen - 1] : 0, in.rc = R[ri - 1];
-            const CellOut o = cell(g, p, ri, g.qlen, in);
+            const CellOut o = cell(g, p, row_geom(g, ri), ri, g.qlen, in);
             E[ri] = (uint8_t)o.path, upS = o.S, qg = o.qry_gaps;
           }
           final_score = upS, have = true;
@@ -115,12 +117,13 @@ __global__ void __launch_bounds__(32) nextalign_kernel(const Job *__restrict__ j
           int32_t leftS, rgc;
           if (K_last >= 0 && K_last < W) leftS = ownS, rgc = ownRG;
           else leftS = col0_score(p, g.rlen), rgc = kNoAlign;   // the stripe was clamped to the single cell (rlen, 0)
+          const RowGeom rw_last = row_geom(g, g.rlen);
           for (int qpos = t0; qpos <= g.qlen; ++qpos) {
             CellIn in;
             in.diagS = col0_score(p, g.rlen - 1);  // only read for qpos == 1 below a stripe clamped to column 0
             in.leftS = leftS, in.ref_gaps = rgc, in.upS = 0, in.qry_gaps = kNoAlign;
             in.qc = Q[qpos - 1], in.rc = R[g.rlen - 1];
-            const CellOut o = cell(g, p, g.rlen, qpos, in);
+            const CellOut o = cell(g, p, rw_last, g.rlen, qpos, in);
             T[qpos] = (uint8_t)o.path, leftS = o.S, rgc = o.ref_gaps;
           }
           final_score = leftS, have = true;

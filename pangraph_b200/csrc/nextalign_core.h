@@ -63,8 +63,18 @@ struct CellOut {
   int path;
 };
 
+// The stripe limits a cell of row ri looks at: computed once per row, not per cell.
+struct RowGeom {
+  int beg, beg1, end1, end2;  // begin(ri), begin(ri-1), end(ri-1), end(ri-2) (unused for ri == 1)
+};
+NA_HD RowGeom row_geom(const Geom &g, int ri) {
+  RowGeom r;
+  r.beg = g.begin(ri), r.beg1 = g.begin(ri - 1), r.end1 = g.end(ri - 1), r.end2 = ri >= 2 ? g.end(ri - 2) : 0;
+  return r;
+}
+
 // One cell with ri >= 1 (score_matrix.rs:92-195).  `in.ref_gaps` is the running value of the row (NO_ALIGN at its start).
-NA_HD CellOut cell(const Geom &g, const Params &p, int ri, int qpos, const CellIn &in) {
+NA_HD CellOut cell(const Geom &g, const Params &p, const RowGeom &rw, int ri, int qpos, const CellIn &in) {
   CellOut o;
   int tmp_path = 0, origin = 0;
   int32_t score = kNoAlign, tmp_score;
@@ -74,7 +84,7 @@ NA_HD CellOut cell(const Geom &g, const Params &p, int ri, int qpos, const CellI
     if (p.left_free) score = 0;
     else score = -p.gopen - (ri - 1) * p.ext;  // scores[(ri-1, 0)] - ext unrolled: row 1 opens, every further row extends
   } else {
-    const int beg = g.begin(ri), beg1 = g.begin(ri - 1), end1 = g.end(ri - 1);
+    const int beg = rw.beg, beg1 = rw.beg1, end1 = rw.end1;
     if (qpos > beg1 && qpos - 1 < end1) {
       if (in.qc == 14 || in.rc == 14) score = in.diagS + p.match - 1;
       else if (nuc_match(in.qc, in.rc)) score = in.diagS + p.match;
@@ -95,7 +105,7 @@ NA_HD CellOut cell(const Geom &g, const Params &p, int ri, int qpos, const CellI
       if (qpos != g.qlen || !p.right_free) q_gap_extend = in.qry_gaps - p.ext, q_gap_open = in.upS - p.gopen;
       else q_gap_extend = in.qry_gaps, q_gap_open = in.upS;
       // (ri == 1: qry_gaps is still NO_ALIGN, the extension can never win, stripes[ri - 2] is not looked at)
-      if (q_gap_extend >= q_gap_open && ri >= 2 && qpos < g.end(ri - 2)) tmp_score = q_gap_extend, tmp_path += kQryGapExtend;
+      if (q_gap_extend >= q_gap_open && ri >= 2 && qpos < rw.end2) tmp_score = q_gap_extend, tmp_path += kQryGapExtend;
       else tmp_score = q_gap_open;
       o.qry_gaps = tmp_score;
       if (score - p.left_align < tmp_score) score = tmp_score, origin = kQryGapMatrix;

@@ -42,7 +42,7 @@ AttemptOut attempt(const uint8_t *R, int rlen, const uint8_t *Q, int qlen, int m
             CellIn in;
             in.diagS = S[K], in.leftS = curS[lane], in.ref_gaps = rg[lane], in.upS = S[K + 1], in.qry_gaps = QG[K + 1];
             in.qc = qpos > 0 ? Q[qpos - 1] : 0, in.rc = R[ri - 1];
-            o = cell(g, p, ri, qpos, in);
+            o = cell(g, p, row_geom(g, ri), ri, qpos, in);
           }
           S[K] = o.S, QG[K] = o.qry_gaps, rg[lane] = o.ref_gaps, curS[lane] = o.S;
           B[(size_t)ri * W + K] = (uint8_t)o.path;
@@ -71,7 +71,7 @@ AttemptOut attempt(const uint8_t *R, int rlen, const uint8_t *Q, int qlen, int m
           CellIn in;
           in.diagS = row0_score(p, qlen - 1), in.leftS = 0, in.ref_gaps = kNoAlign, in.upS = upS, in.qry_gaps = qg;
           in.qc = qlen > 0 ? Q[qlen - 1] : 0, in.rc = R[ri - 1];
-          const CellOut o = cell(g, p, ri, qlen, in);
+          const CellOut o = cell(g, p, row_geom(g, ri), ri, qlen, in);
           E[ri] = (uint8_t)o.path, upS = o.S, qg = o.qry_gaps;
         }
         final_score = upS, have = true;
@@ -80,11 +80,12 @@ AttemptOut attempt(const uint8_t *R, int rlen, const uint8_t *Q, int qlen, int m
         int32_t leftS, rgc;
         if (K_last >= 0 && K_last < W) leftS = ownS, rgc = ownRG;
         else leftS = col0_score(p, rlen), rgc = kNoAlign;
+        const RowGeom rw_last = row_geom(g, rlen);
         for (int qpos = t0; qpos <= qlen; ++qpos) {
           CellIn in;
           in.diagS = col0_score(p, rlen - 1), in.leftS = leftS, in.ref_gaps = rgc, in.upS = 0, in.qry_gaps = kNoAlign;
           in.qc = Q[qpos - 1], in.rc = R[rlen - 1];
-          const CellOut o = cell(g, p, rlen, qpos, in);
+          const CellOut o = cell(g, p, rw_last, rlen, qpos, in);
           T[qpos] = (uint8_t)o.path, leftS = o.S, rgc = o.ref_gaps;
         }
         final_score = leftS, have = true;
