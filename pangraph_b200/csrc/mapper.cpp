@@ -206,8 +206,7 @@ struct DpCached {
 struct DpCall {   // one DP window and, once its wave has run, its result
   int job = -1;   // index in the query's job list of the current wave; -1 = not submitted
   int wave = -1;  // the wave `job` belongs to
-  DpKey key{};    // the problem itself (valid when keyed)
-  bool keyed = false;
+  struct DpCached *entry = nullptr;  // the query's result-cache entry of this problem (node addresses are stable), if it has one
   Ez ez = ez_reset();
   // the CIGAR stays in the wave's result buffer (kept alive here) instead of being copied per problem
   std::shared_ptr<const KswBatchResult> keep;
@@ -256,7 +255,7 @@ struct QCtx {
   size_t job_base = 0;
   bool pending = false;
   std::unordered_map<DpKey, DpCached, DpKeyHash> dp_cache;  // every DP result of this query so far
-  std::vector<DpKey> wave_keys;                              // key of jobs[i] of the wave being assembled / in flight
+  std::vector<DpCached *> wave_entries;                      // cache entry of jobs[i] of the wave being assembled / in flight
   uint64_t dp_reused = 0;
   int wave_id = 0, done_wave = -1;  // the wave being assembled; the last one whose results are in
 };
@@ -503,7 +502,29 @@ struct Mapper {
       const uint32_t op = c & 0xf, len = c >> 4;
       if (op == MM_CIGAR_MATCH) {
         int n_ambi = 0, n_diff = 0;
-        for (uint32_t l = 0; l < len; ++l) {
+        uint32_t l = 0;
+        // eight equal unambiguous bases at a time: the score only climbs through them (s >= 0 on entry, every step adds
+        // the match score), so the clamp never acts and the running maximum ends at the last one -- the same doubles as
+        // base by base (all of them integers plus a few float-precision gap terms, far below 2^53)
+        if (mat[0] > 0)
+          for (; l + 8 <= len; l += 8) {
+            uint64_t wq, wt;
+            memcpy(&wq, qseq + qoff + l, 8), memcpy(&wt, tseq + toff + l, 8);
+            if (wq != wt || (wq & 0x0404040404040404ull)) {  // a mismatch or an ambiguous base: this block goes base by base
+              for (uint32_t j = l; j < l + 8; ++j) {
+                const int cq = qseq[qoff + j], ct = tseq[toff + j];
+                if (ct > 3 || cq > 3) ++n_ambi;
+                else if (ct != cq) ++n_diff;
+                s += mat[ct * 5 + cq];
+                if (s < 0) s = 0;
+                else max = max > s ? max : s;
+              }
+              continue;
+            }
+            s += 8.0 * mat[0];
+            max = max > s ? max : s;
+          }
+        for (; l < len; ++l) {
           const int cq = qseq[qoff + l], ct = tseq[toff + l];
           if (ct > 3 || cq > 3) ++n_ambi;
           else if (ct != cq) ++n_diff;
@@ -635,7 +656,7 @@ struct Mapper {
     c.ez = ez_reset();
     c.cigar = nullptr;
     c.keep.reset();
-    c.job = -1, c.keyed = false;
+    c.job = -1, c.entry = nullptr;
     if (opt.max_sw_mat > 0 && (int64_t)tl * ql > opt.max_sw_mat) {
       c.ez.zdropped = 1;
       return;
@@ -649,19 +670,18 @@ struct Mapper {
     c.wave = q.wave_id;
     if (dp_reuse) {
       const DpKey key{j.q_off, j.t_off, ql, tl, w, zdrop, end_bonus, flag};
-      c.key = key, c.keyed = true;
-      auto it = q.dp_cache.find(key);
-      if (it != q.dp_cache.end()) {
+      if (q.dp_cache.bucket_count() < 4096) q.dp_cache.reserve(32768);  // one hash operation per window, no rehash on the way
+      const auto ins = q.dp_cache.try_emplace(key);
+      DpCached &e = ins.first->second;
+      c.entry = &e;
+      if (!ins.second) {
         ++q.dp_reused;
-        const DpCached &e = it->second;
         if (e.job >= 0) c.job = e.job, q.pending = true;  // asked for earlier in this very wave: share the slot
         else c.ez = e.ez, c.keep = e.keep, c.cigar = e.cigar;
         return;
       }
-      DpCached e;
       e.job = (int)q.jobs.size();
-      q.dp_cache.emplace(key, e);
-      q.wave_keys.push_back(key);
+      q.wave_entries.push_back(&e);
     }
     c.job = (int)q.jobs.size();
     q.jobs.push_back(j);
@@ -669,12 +689,12 @@ struct Mapper {
   }
   // the results of the wave that just ran become reusable (before any hit of the query looks at them)
   static void publish_wave(QCtx &q, const std::shared_ptr<const KswBatchResult> &res) {
-    for (size_t k = 0; k < q.wave_keys.size(); ++k) {
-      DpCached &e = q.dp_cache[q.wave_keys[k]];
+    for (size_t k = 0; k < q.wave_entries.size(); ++k) {
+      DpCached &e = *q.wave_entries[k];
       const size_t g = q.job_base + k;
       e.job = -1, e.ez = res->out[g], e.keep = res, e.cigar = res->cigar.data() + res->cig_start[g];
     }
-    q.wave_keys.clear();
+    q.wave_entries.clear();
   }
   // a call is ready when nothing was submitted for it or the wave it went into has run
   static bool ready(const QCtx &q, const DpCall &c) { return c.job < 0 || c.wave == q.done_wave; }
@@ -686,12 +706,8 @@ struct Mapper {
   }
   // mm_test_zdrop on a first-pass result; the verdict is remembered with the result (it is a function of the same inputs)
   int fill_code(QCtx &q, const Region &R, const Fill &f, DpCall &p1) const {
-    DpCached *e = nullptr;
-    if (p1.keyed) {
-      auto it = q.dp_cache.find(p1.key);
-      if (it != q.dp_cache.end()) e = &it->second;
-      if (e && e->zcode >= 0) return e->zcode;
-    }
+    DpCached *e = p1.entry;
+    if (e && e->zcode >= 0) return e->zcode;
     if (p1.ez.zd_max < 0) zdrop_scan(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), p1.cigar, p1.ez.n_cigar, p1.ez);
     const int code = test_zdrop(q.q0[R.rev] + f.qs, tseq(R.rid, f.rs), p1.ez);
     if (e) e->zcode = (int8_t)code;
