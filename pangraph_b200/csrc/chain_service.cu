@@ -15,6 +15,13 @@
 
 namespace pgmm {
 
+// requests are merged when they chain with the same parameters (field by field: padding bytes carry no meaning)
+static bool same_params(const ChainParams &a, const ChainParams &b) {
+  return a.max_dist == b.max_dist && a.max_dist_inner == b.max_dist_inner && a.bw == b.bw && a.max_chn_skip == b.max_chn_skip &&
+         a.cap_rmq_size == b.cap_rmq_size && a.min_cnt == b.min_cnt && a.min_sc == b.min_sc && a.pen_gap == b.pen_gap &&
+         a.pen_skip == b.pen_skip;
+}
+
 namespace {
 struct Request {
   ChainParams cp;
@@ -51,7 +58,7 @@ struct ChainService::Impl {
         for (auto it = pending.begin(); it != pending.end();) {
           size_t na = 0;
           for (const ChainFillJob &j : *(*it)->jobs) na += (size_t)j.n;
-          if (memcmp(&(*it)->cp, &cp, sizeof(cp)) == 0 && (batch.empty() || n + na <= max_anchors)) {
+          if (same_params((*it)->cp, cp) && (batch.empty() || n + na <= max_anchors)) {
             n += na;
             batch.push_back(*it);
             it = pending.erase(it);
@@ -133,7 +140,6 @@ bool ChainService::enabled() {
 
 void ChainService::run(const ChainParams &cp, std::vector<ChainFillJob> &jobs, std::shared_ptr<std::vector<int32_t>> &keep, ChainFillStats *stats) {
   Request r;
-  memset(&r.cp, 0, sizeof(r.cp));  // padding bytes take part in the memcmp that groups requests
   r.cp = cp, r.jobs = &jobs;
   size_t na = 0;
   for (const ChainFillJob &j : jobs) na += (size_t)j.n;

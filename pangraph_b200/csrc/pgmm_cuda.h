@@ -151,6 +151,10 @@ struct DevBuf {
   }
   T *ensure(size_t n) {
     if (n > cap) {
+      // The old block goes back to the process-wide pool, where another context may pick it up at once: work that this
+      // context has queued on it (e.g. the previous of two back-to-back CUB passes sharing one scratch buffer) must be
+      // done first.  Growth stops after the first few rounds (25 % headroom), so the device-wide wait is rare.
+      if (p) cudaDeviceSynchronize();
       release();
       cls = DevicePool::size_class((n + n / 4 + 64) * sizeof(T));  // 25 % headroom: rounds differ slightly in size
       p = (T *)DevicePool::get().alloc(cls);
