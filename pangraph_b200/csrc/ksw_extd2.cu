@@ -1091,7 +1091,7 @@ void KswEngine::run(std::vector<KswJob> &jobs, const uint8_t *d_q, const uint8_t
     // ---- launch classes: threads per CTA follow the width of the wavefront (one word of 4 cells per thread and
     // anti-diagonal for everything but the small fills), shared memory follows the length of the target ----
     constexpr int kClasses = Impl::kClasses;
-    static const int max_nt_tier = getenv("PGMM_MAX_NT_TIER") ? atoi(getenv("PGMM_MAX_NT_TIER")) : 4;
+    static const int max_nt_tier = getenv("PGMM_MAX_NT_TIER") ? atoi(getenv("PGMM_MAX_NT_TIER")) : 3;  // 256 threads: a 512-thread CTA (113 registers) owns its SM and leaves 70 % of its issue slots idle (profiles/r02_sweep_nt.txt)
     std::vector<int> cls[kClasses], generic;
     size_t cls_smem[kClasses] = {};
     KswJob *hj = m.h_jobs.ensure(nw);
