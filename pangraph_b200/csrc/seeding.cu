@@ -171,6 +171,175 @@ __global__ void mz_offsets_kernel(SeqView v, uint32_t n_ev, const uint32_t *__re
   mz_off[s] = E0 < n_ev ? fpos[E0] : n_flag_total;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1 fused (odd k, the case of every pangraph preset: -k 19): sketch of one tile of one sequence in ONE kernel.
+// For odd k no k-mer equals its reverse complement, so every position is a ring event and event index = position: the
+// event stream of the general path above collapses onto the sequence itself and a tile plus halo holds everything a
+// decision needs.  A CTA stages the tile's bases with 128-bit loads, every thread rolls the two k-mers over its stretch of
+// positions (one shift / mask per base instead of a k-base walk back per position), hashes, and leaves key and run length
+// in shared memory; the second phase takes the select_kernel decisions (same rules, sketch.c:116-142) from shared memory;
+// the third compacts the tile's minimizers in order (block scan) to the front of the tile's own slice of a position-sized
+// buffer and publishes their number.  A scan over the tile counts and one gather kernel put the tiles end to end.
+// Three launches and one host synchronisation instead of twelve and four.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTile = 4096, kTileThreads = 256, kTileItems = kTile / kTileThreads;
+
+struct SketchTile {
+  uint32_t seq, t0;  // sequence and first position of the tile inside it
+};
+
+__global__ void __launch_bounds__(kTileThreads) sketch_tile_kernel(SeqView v, const SketchTile *__restrict__ tiles, int w, int k,
+                                                                    uint64_t *__restrict__ TX, uint64_t *__restrict__ TY,
+                                                                    uint32_t *__restrict__ counts) {
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  const SketchTile tl = tiles[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int64_t L = (int64_t)(v.vstart[tl.seq + 1] - v.vstart[tl.seq]);
+  const uint8_t *seq = v.codes + v.starts[tl.seq];
+  const int64_t t0 = tl.t0, t1 = min(L, t0 + (int64_t)kTile);
+  // events (= positions) whose key is needed: the tile, w before it (windows) and w after it (later events flag tile positions)
+  const int64_t e_lo = max((int64_t)0, t0 - w), e_hi = min(L, t1 + w);
+  const int n_ev = (int)(e_hi - e_lo);
+  // bases needed: back to where the run length of the first event is decided (w + k + 1 positions)
+  const int64_t c_lo = max((int64_t)0, e_lo - (w + k + 1));
+  const int n_codes = (int)(e_hi - c_lo);
+  // shared memory (every part starts on a 16-byte boundary): keys [kTile + 2w], run length | strand << 15 [kTile + 2w],
+  // flags [kTile + 2w], bases [kTile + 3w + k + 48]
+  const int cap_ev = kTile + 2 * w;
+  uint64_t *X = (uint64_t *)sk_smem;
+  uint16_t *EL = (uint16_t *)(sk_smem + (size_t)cap_ev * 8);
+  uint8_t *F = sk_smem + (size_t)cap_ev * 8 + ((size_t)cap_ev * 2 + 15) / 16 * 16;
+  uint8_t *CDraw = F + ((size_t)cap_ev + 15) / 16 * 16;
+
+  // ---- stage the bases with 128-bit loads: from the 16-byte boundary at or before the first base needed (the code
+  // buffers are cudaMalloc blocks, so that boundary lies inside them); CD[i] is the base at position c_lo + i ----
+  const uint8_t *src = seq + c_lo;
+  const int pre = (int)((uintptr_t)src & 15);
+  const uint8_t *CD = CDraw + pre;
+  {
+    const int n16 = (pre + n_codes) / 16;
+    const uint4 *src16 = (const uint4 *)(src - pre);
+    for (int i = tid; i < n16; i += kTileThreads) ((uint4 *)CDraw)[i] = __ldg(src16 + i);
+    for (int i = 16 * n16 + tid; i < pre + n_codes; i += kTileThreads) CDraw[i] = src[i - pre];
+    for (int i = tid; i < cap_ev; i += kTileThreads) F[i] = 0;
+  }
+  __syncthreads();
+
+  // ---- phase 1: key and run length of every event in [e_lo, e_hi) ----
+  {
+    const int per = (n_ev + kTileThreads - 1) / kTileThreads;
+    const int a0 = tid * per, a1 = min(n_ev, a0 + per);
+    if (a0 < a1) {
+      const uint64_t mask = (1ull << 2 * k) - 1;
+      const int shift1 = 2 * (k - 1), cap_l = w + k + 1;
+      // run length of unambiguous bases ending right before the first event of this stretch (exact up to w + k + 1)
+      int64_t pos = e_lo + a0;  // position of the first event
+      int l = 0;
+      for (int64_t j = pos - 1; j >= c_lo && l < cap_l; --j) {
+        if (CD[j - c_lo] > 3) break;
+        ++l;
+      }
+      // the two k-mers over the k - 1 bases before the stretch (only used when they are all unambiguous)
+      uint64_t k0 = 0, k1 = 0;
+      for (int64_t j = max(c_lo, pos - (k - 1)); j < pos; ++j) {
+        const int c = CD[j - c_lo] & 3;
+        k0 = (k0 << 2 | (uint64_t)c) & mask;
+        k1 = k1 >> 2 | (uint64_t)(3 ^ c) << shift1;
+      }
+      for (int a = a0; a < a1; ++a, ++pos) {
+        const int c = CD[pos - c_lo];
+        uint64_t x = U64MAX;
+        int z = 0;
+        if (c < 4) {
+          l = l < cap_l ? l + 1 : l;
+          k0 = (k0 << 2 | (uint64_t)c) & mask;
+          k1 = k1 >> 2 | (uint64_t)(3 ^ c) << shift1;
+          if (l >= k) {
+            z = k0 < k1 ? 0 : 1;
+            x = hash64(z ? k1 : k0, mask) << 8 | (uint64_t)k;
+          }
+        } else l = 0;
+        X[a] = x, EL[a] = (uint16_t)(l | z << 15);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: what the reference's scan appends at each event (select_kernel's rules on shared memory) ----
+  {
+    const int64_t d_lo = t0, d_hi = e_hi;  // deciding events: the tile's own and the w after it
+    const int n_dec = (int)(d_hi - d_lo);
+    for (int q = tid; q < n_dec; q += kTileThreads) {
+      const int64_t ee = d_lo + q;          // position of the event
+      const int a = (int)(ee - e_lo);        // its slot
+      const int lo_prev = (int)(max((int64_t)0, ee - w) - e_lo), lo_new = (int)(max((int64_t)0, ee - w + 1) - e_lo);
+      const int jm = (int)(ee - w - e_lo);  // slot of the event that leaves the window at this step (negative: none yet)
+      // newest-of-the-smallest over [ee-w, ee-1] (before this step) and over [ee-w+1, ee] (after it)
+      int pm = -1, nm = -1;
+      uint64_t xpm = U64MAX, xnm = U64MAX;
+      for (int j = lo_prev; j < a; ++j) {
+        const uint64_t x = X[j];
+        if (xpm >= x) xpm = x, pm = j;
+        if (j > jm && xnm >= x) xnm = x, nm = j;
+      }
+      const uint64_t xe = X[a];
+      if (xnm >= xe) xnm = xe, nm = a;
+      const int le = EL[a] & 0x7fff;
+      if (le == w + k - 1 && xpm != U64MAX)
+        for (int j = lo_new; j < a; ++j)
+          if (X[j] == xpm && j != pm) F[j] = 1;
+      if (xe <= xpm) {
+        if (le >= w + k && xpm != U64MAX) F[pm] = 1;
+      } else if (pm == jm) {
+        if (le >= w + k - 1 && xpm != U64MAX) F[pm] = 1;
+        if (le >= w + k - 1 && xnm != U64MAX)
+          for (int j = lo_new; j <= a; ++j)
+            if (X[j] == xnm && j != nm) F[j] = 1;
+      }
+      if (ee == L - 1 && xnm != U64MAX) F[nm] = 1;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: the tile's flagged positions, in order, to the front of the tile's slice ----
+  {
+    typedef cub::BlockScan<int, kTileThreads> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    const int base = (int)(t0 - e_lo);  // slot of the tile's first position
+    const int n_own = (int)(t1 - t0);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kTileItems; ++i) {
+      const int j = tid * kTileItems + i;
+      cnt += j < n_own && F[base + j];
+    }
+    int off, total;
+    Scan(scan_tmp).ExclusiveSum(cnt, off, total);
+    const uint64_t g0 = v.vstart[tl.seq] + (uint64_t)t0;  // the tile's slice of the position-sized buffers
+#pragma unroll
+    for (int i = 0; i < kTileItems; ++i) {
+      const int j = tid * kTileItems + i;
+      if (j < n_own && F[base + j]) {
+        TX[g0 + off] = X[base + j];
+        TY[g0 + off] = (uint64_t)tl.seq << 32 | (uint64_t)(uint32_t)(t0 + j) << 1 | (uint64_t)(EL[base + j] >> 15);
+        ++off;
+      }
+    }
+    if (tid == 0) counts[blockIdx.x] = (uint32_t)total;
+  }
+}
+
+// tile t's minimizers move from the front of its slice to their final place
+__global__ void sketch_gather_kernel(SeqView v, const SketchTile *__restrict__ tiles, const uint32_t *__restrict__ counts,
+                                     const uint32_t *__restrict__ prefix, const uint64_t *__restrict__ TX, const uint64_t *__restrict__ TY,
+                                     uint64_t *__restrict__ mx, uint64_t *__restrict__ my) {
+  const SketchTile tl = tiles[blockIdx.x];
+  const uint64_t g0 = v.vstart[tl.seq] + (uint64_t)tl.t0;
+  const uint32_t n = counts[blockIdx.x], o = prefix[blockIdx.x];
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mx[o + i] = TX[g0 + i], my[o + i] = TY[g0 + i];
+}
+
 struct MaxOp {
   __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
 };
@@ -419,6 +588,7 @@ struct SeedEngine::Impl {
   DevBuf<uint64_t> hv, EX, EP, vstart, starts;
   DevBuf<int32_t> rmark, rpos, EL;
   DevBuf<uint32_t> ev_incl, flag, fpos;
+  DevBuf<SketchTile> tiles;
   // index workspace
   DevBuf<uint64_t> key_in, key_out, val_out, rle_keys;
   DevBuf<uint32_t> rle_cnt, cnt_sorted, n_runs;
@@ -480,7 +650,9 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
                         DeviceSeqSet &set, cudaStream_t st) {
   Impl &m = *impl_;
   const int n = (int)lens.size();
-  m.pin_reset(4 * ((size_t)n + 2) + 64);
+  size_t n_tiles_max = 0;  // tiles of the fused path (their table and their prefix sums pass through the pinned scratch)
+  for (int i = 0; i < n; ++i) n_tiles_max += ((size_t)lens[i] + kTile - 1) / kTile;
+  m.pin_reset(5 * ((size_t)n + 2) + 2 * n_tiles_max + 64);
   set.n = n, set.d_codes = d_codes, set.h_starts = starts, set.h_lens = lens;
   set.h_vstart.assign(n + 1, 0);
   for (int i = 0; i < n; ++i) set.h_vstart[i + 1] = set.h_vstart[i] + (uint64_t)lens[i];
@@ -505,6 +677,44 @@ void SeedEngine::sketch(const uint8_t *d_codes, const std::vector<uint64_t> &sta
     return;
   }
   SeqView v{d_codes, set.starts.p, set.vstart.p, n, N};
+  static const bool no_fused = getenv("PGMM_SKETCH_GENERAL") != nullptr && atoi(getenv("PGMM_SKETCH_GENERAL")) != 0;
+  if ((k & 1) && !no_fused) {
+    // ---- fused path (odd k): tiles of kTile positions, never across a sequence boundary ----
+    std::vector<uint32_t> first_tile((size_t)n + 1);
+    size_t n_tiles = 0;
+    for (int i = 0; i < n; ++i) first_tile[i] = (uint32_t)n_tiles, n_tiles += ((size_t)lens[i] + kTile - 1) / kTile;
+    first_tile[n] = (uint32_t)n_tiles;
+    SketchTile *ht = m.pin<SketchTile>(n_tiles + 1);
+    for (int i = 0; i < n; ++i)
+      for (uint32_t t = first_tile[i], o = 0; t < first_tile[i + 1]; ++t, o += kTile) ht[t] = SketchTile{(uint32_t)i, o};
+    m.tiles.ensure(n_tiles + 1), m.flag.ensure(n_tiles + 2), m.fpos.ensure(n_tiles + 2);
+    m.EX.ensure(N), m.EP.ensure(N);
+    PGMM_CUDA(cudaMemcpyAsync(m.tiles.p, ht, n_tiles * sizeof(SketchTile), cudaMemcpyHostToDevice, st));
+    const int cap_ev = kTile + 2 * w;
+    const size_t smem = (size_t)cap_ev * 8 + ((size_t)cap_ev * 2 + 15) / 16 * 16 + ((size_t)cap_ev + 15) / 16 * 16 + (size_t)kTile + 3 * w + k + 48;
+    static const bool attr = [] {
+      PGMM_CUDA(cudaFuncSetAttribute(sketch_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      return true;
+    }();
+    (void)attr;
+    ++g_seed_launches, sketch_tile_kernel<<<(unsigned)n_tiles, kTileThreads, smem, st>>>(v, m.tiles.p, w, k, m.EX.p, m.EP.p, m.flag.p);
+    PGMM_CUDA(cudaGetLastError());
+    PGMM_CUDA(cudaMemsetAsync(m.flag.p + n_tiles, 0, 4, st));  // one more element: its exclusive sum is the total
+    m.excl_sum(m.flag.p, m.fpos.p, n_tiles + 1, st);
+    uint32_t *hp = m.pin<uint32_t>(n_tiles + 2);
+    PGMM_CUDA(cudaMemcpyAsync(hp, m.fpos.p, (n_tiles + 1) * 4, cudaMemcpyDeviceToHost, st));
+    PGMM_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_mz = hp[n_tiles];
+    set.n_mz = n_mz;
+    set.mx.ensure(n_mz + 1), set.my.ensure(n_mz + 1);
+    ++g_seed_launches, sketch_gather_kernel<<<(unsigned)n_tiles, 128, 0, st>>>(v, m.tiles.p, m.flag.p, m.fpos.p, m.EX.p, m.EP.p, set.mx.p, set.my.p);
+    PGMM_CUDA(cudaGetLastError());
+    for (int i = 0; i <= n; ++i) set.h_mz_off[i] = hp[first_tile[i]];
+    uint64_t *p_off = m.pin<uint64_t>(n + 1);
+    memcpy(p_off, set.h_mz_off.data(), ((size_t)n + 1) * 8);
+    PGMM_CUDA(cudaMemcpyAsync(set.mz_off.p, p_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    return;
+  }
   m.ev.ensure(N), m.hv.ensure(N), m.rmark.ensure(N), m.rpos.ensure(N), m.ev_incl.ensure(N);
   ++g_seed_launches, kmer_kernel<<<nblk(N), TPB, 0, st>>>(v, k, m.ev.p, m.hv.p, m.rmark.p);
   m.incl_sum(m.ev.p, m.ev_incl.p, N, st);

@@ -50,3 +50,28 @@ def test_sketch_genome_scale(ref):
             assert len(got[i][0]) == len(want)
             assert np.array_equal(got[i][0], np.array([x for x, _ in want], dtype=np.uint64))
             assert np.array_equal(got[i][1], np.array([y for _, y in want], dtype=np.uint64))
+
+
+@pytest.mark.parametrize("w,k", [(19, 19), (1, 3), (100, 27), (255, 5), (7, 21)])
+def test_sketch_fused_path_across_tiles(ref, w, k):
+    """Odd k takes the fused tile kernel (4096 positions per tile): lengths around multiples of the tile, ambiguous bases
+    and repeats placed around the tile boundaries, several sequences per launch."""
+    from oracle import refmm2
+    from pangraph_b200 import abi
+    rng = np.random.default_rng(7 * w + k)
+    seqs = [rand_seq(rng, n) for n in (4095, 4096, 4097, 8191, 8192, 8193, 4096 + w, 4096 + w + k, 4096 - w, 3 * 4096 + 17)]
+    s = bytearray(rand_seq(rng, 5 * 4096 + 100))
+    for b in (4096, 8192, 12288, 16384):  # Ns just before / on / after the boundaries, at window and k-mer distance
+        for d in (-w - k, -w, -k, -1, 0, 1, k - 1, w, w + k - 1):
+            if 0 <= b + d < len(s):
+                s[b + d] = ord("N")
+    seqs.append(bytes(s))
+    unit = rand_seq(rng, 31)
+    seqs.append(unit * 300)                      # tandem repeat: equal keys inside every window, across the boundaries
+    seqs.append(b"A" * 9000)                     # one key everywhere
+    seqs.append(rand_seq(rng, 30000, n_frac=0.002))
+    got = abi.sketch(seqs, w, k)
+    for i, sq in enumerate(seqs):
+        want = refmm2.ref_sketch(ref, sq, w, k, rid=i)
+        g = list(zip((int(v) for v in got[i][0]), (int(v) for v in got[i][1])))
+        assert g == want, (i, len(sq), len(g), len(want), [x for x in zip(g, want) if x[0] != x[1]][:2])
