@@ -351,15 +351,6 @@ __global__ void split_key_kernel(uint64_t n, const uint64_t *__restrict__ mx, ui
 }
 
 // position of `key` in the sorted distinct keys, or -1
-__device__ __forceinline__ int64_t find_key(const uint64_t *keys, uint64_t n, uint64_t key) {
-  uint64_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint64_t mid = (lo + hi) >> 1;
-    if (keys[mid] < key) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo < n && keys[lo] == key ? (int64_t)lo : -1;
-}
 
 // ---------------- query-side occurrence filter (seed.c:5-28) ----------------
 __global__ void mzflt_prepare_kernel(uint64_t n, const uint64_t *__restrict__ my, uint32_t *__restrict__ qid, uint32_t *__restrict__ idx) {
@@ -410,15 +401,41 @@ __global__ void remap_offsets_kernel(int n, const uint64_t *__restrict__ old_off
   new_off[s] = o < n_old ? kpos[o] : n_new;
 }
 
+// ---------------- the hash table of the index (index.c:81-98: mm_idx_get is a khash lookup) ----------------
+__device__ __forceinline__ uint64_t ht_slot(uint64_t key, uint64_t mask) {
+  key *= 0x9E3779B97F4A7C15ull;  // minimizer hashes are already mixed (sketch.c:28-38); one multiply spreads their low bits
+  return (key ^ key >> 29) & mask;
+}
+__global__ void ht_insert_kernel(uint64_t n_keys, const uint64_t *__restrict__ keys, unsigned long long *__restrict__ ht_key,
+                                 uint32_t *__restrict__ ht_rank, uint64_t mask) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keys) return;
+  const unsigned long long key = keys[i];
+  for (uint64_t s = ht_slot(key, mask);; s = (s + 1) & mask)
+    if (atomicCAS(ht_key + s, ~0ull, key) == ~0ull) {  // keys are distinct: the first empty slot is ours
+      ht_rank[s] = (uint32_t)i;
+      return;
+    }
+}
+// rank of `key` among the index's distinct keys, -1 if absent
+__device__ __forceinline__ int64_t ht_find(const uint64_t *__restrict__ ht_key, const uint32_t *__restrict__ ht_rank, uint64_t mask, uint64_t key) {
+  for (uint64_t s = ht_slot(key, mask);; s = (s + 1) & mask) {
+    const uint64_t k = ht_key[s];
+    if (k == key) return (int64_t)ht_rank[s];
+    if (k == ~0ull) return -1;
+  }
+}
+
 // ---------------- seed lookup (seed.c:30-52, index.c:81-98) ----------------
 __global__ void lookup_kernel(uint64_t n, const uint64_t *__restrict__ fx, const uint64_t *__restrict__ fy, const uint64_t *__restrict__ f_off,
-                              const uint64_t *__restrict__ keys, uint64_t n_keys, const uint32_t *__restrict__ key_off,
+                              const uint64_t *__restrict__ ht_key, const uint32_t *__restrict__ ht_rank, uint64_t ht_mask,
+                              const uint32_t *__restrict__ key_off,
                               uint32_t *__restrict__ s_n, uint32_t *__restrict__ s_off, uint32_t *__restrict__ s_tandem,
                               uint32_t *__restrict__ s_has) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t h = fx[i] >> 8;
-  const int64_t kx = find_key(keys, n_keys, h);
+  const int64_t kx = ht_find(ht_key, ht_rank, ht_mask, h);  // the hash probe
   uint32_t t = 0, off = 0;
   if (kx >= 0) off = key_off[kx], t = key_off[kx + 1] - off;
   const uint32_t q = (uint32_t)(fy[i] >> 32);
@@ -788,6 +805,15 @@ void SeedEngine::build_index(DeviceIndex &idx, const std::vector<uint32_t> &lens
   PGMM_CUDA(cudaStreamSynchronize(st));
   const uint32_t n_keys = *p_n_keys;
   idx.n_keys = n_keys;
+  {  // the probe table: the smallest power of two >= 2 n_keys slots
+    uint64_t slots = 16;
+    while (slots < 2ull * n_keys) slots <<= 1;
+    idx.ht_mask = slots - 1;
+    idx.ht_key.ensure(slots), idx.ht_rank.ensure(slots);
+    PGMM_CUDA(cudaMemsetAsync(idx.ht_key.p, 0xff, slots * 8, st));
+    if (n_keys) ++g_seed_launches, ht_insert_kernel<<<nblk(n_keys), TPB, 0, st>>>(n_keys, idx.keys.p, (unsigned long long *)idx.ht_key.p, idx.ht_rank.p, idx.ht_mask);
+    PGMM_CUDA(cudaGetLastError());
+  }
   PGMM_CUDA(cudaMemsetAsync(m.rle_cnt.p + n_keys, 0, 4, st));
   m.excl_sum(m.rle_cnt.p, idx.key_off.p, (uint64_t)n_keys + 1, st);
   {
@@ -871,7 +897,7 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
   // ---- index probe and seed list (seed.c:30-52) ----
   uint32_t *s_n = m.u32[0].ensure(n), *s_off = m.u32[1].ensure(n), *s_tandem = m.u32[2].ensure(n), *s_has = m.u32[3].ensure(n);
   uint32_t *spos = m.u32[4].ensure(n);
-  ++g_seed_launches, lookup_kernel<<<nblk(n), TPB, 0, st>>>(n, fx, fy, f_off, idx.keys.p, idx.n_keys, idx.key_off.p, s_n, s_off, s_tandem, s_has);
+  ++g_seed_launches, lookup_kernel<<<nblk(n), TPB, 0, st>>>(n, fx, fy, f_off, idx.ht_key.p, idx.ht_rank.p, idx.ht_mask, idx.key_off.p, s_n, s_off, s_tandem, s_has);
   PGMM_CUDA(cudaGetLastError());
   const uint64_t n_seed = m.scan_flags(s_has, spos, n, st);
   if (n_seed == 0) return;

@@ -42,6 +42,11 @@ struct DeviceIndex {
   DevBuf<uint32_t> seq_len;     // [n]
   DevBuf<int32_t> name_rank;    // [n] rank of each target name in strcmp order (MM_F_NO_DUAL / MM_F_NO_DIAG)
   DevBuf<uint32_t> occ_sorted;  // [n_keys] occurrence counts ascending (for mid_occ)
+  // the probe structure (the reference's khash, index.c:81-98): open addressing, linear probing, load factor <= 1/2;
+  // a slot holds the key's rank in `keys` (its position list is pos[key_off[rank] .. key_off[rank+1]))
+  DevBuf<uint64_t> ht_key;      // [ht_mask + 1], ~0 = empty
+  DevBuf<uint32_t> ht_rank;     // [ht_mask + 1]
+  uint64_t ht_mask = 0;
 };
 
 class SeedEngine {
