@@ -290,7 +290,8 @@ PGMM_API int pgmm_ksw_extd2_batch(int n, const int32_t *qlen, const int32_t *tle
 PGMM_API int pgmm_sketch(int n, const char *const *seqs, const int *lens, int w, int k, uint64_t *out_x, uint64_t *out_y,
                          uint64_t cap, uint64_t *out_off);
 
-/* K1+K3 alone: what collect_seed_hits (map.c:168-204) builds for each query BEFORE its sort: anchors (x,y pairs),
+/* K1+K3 alone: what collect_seed_hits (map.c:168-204) builds for each query: anchors (x,y pairs) in collection order -- or
+ * already ordered by target position when no two of them share one (then that order is the reference's sort result) --,
  * the query positions of the seeds used (seed.c:125) and the repeat length (seed.c:113-128).
  * out_n[3*i..3*i+2] = {n_anchors, n_mini_pos, rep_len}. Returns 0, -1 if a capacity is too small. */
 PGMM_API int pgmm_collect_seeds(const mm_idx_t *mi, int n, const int *lens, const char *const *seqs, const char *const *names,

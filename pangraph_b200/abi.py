@@ -170,7 +170,7 @@ STAT_NAMES = ("total_ms", "seed_ms", "dp_kernel_ms", "index_ms", "dp_jobs", "dp_
               "t_chain_sort", "t_chain_fill", "t_chain_rest", "chain_kernel_ms", "chain_anchors", "chain_segments",
               "chain_redo_segments", "chain_redo_anchors", "chain_launches", "chain_iterations", "chain_batches",
               "cpu_encode", "cpu_seed", "cpu_sort", "cpu_chain_fill", "cpu_backtrack_plan", "cpu_dp_round_side", "cpu_dp_workers",
-              "cpu_stitch", "cpu_final", "cpu_index")
+              "cpu_stitch", "cpu_final", "cpu_index", "anchor_sort_device", "anchor_sort_host")
 
 
 def get_stats(reset=False):

@@ -1564,7 +1564,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     q.a.swap(seeds[i].a);
     q.mini_pos.swap(seeds[i].mini_pos);
     q.rep_len = seeds[i].rep_len;
-    flag_sort_128x(q.a.data(), q.a.data() + q.a.size());  // map.c:202
+    if (!seeds[i].sorted) flag_sort_128x(q.a.data(), q.a.data() + q.a.size());  // map.c:202 (unless the device proved the order unique)
     ChainFillJob &cj = cjobs[i];
     cj.a = q.a.data(), cj.n = (int64_t)q.a.size();
     chain_find_segments(cp, cj.a, cj.n, cj.segs);

@@ -41,6 +41,10 @@ struct QuerySeeds {
   std::vector<U128> a;             // anchors in collection order (seed-major, hits ascending)
   std::vector<uint64_t> mini_pos;  // q_span<<32 | q_pos of the seeds that were used (seed.c:125)
   int rep_len = 0;                 // bases covered by filtered, repetitive seeds (seed.c:113-128)
+  // true: `a` arrives sorted by target position and holds no two anchors with the same one, so it IS what the reference's
+  // radix_sort_128x (map.c:202) leaves -- the order of equal keys under that unstable sort is the only thing a stable device
+  // sort cannot reproduce, and there are none.  false: collection order, the exact replay on the host sorts it.
+  bool sorted = false;
 };
 
 struct DpStats {

@@ -419,11 +419,12 @@ void pgmm_map_batch(const mm_idx_t *mi, int n, const int *lens, const char *cons
 //        fill kernel ms, anchors, segments, segments redone on the host, their anchors, launches
 //        [42] fixed-point iterations of the chain fill summed over its batches [43] those batches
 //        [44..53] host CPU ms by phase (mapper.h: cpu_phase_*)
+//        [54] queries whose anchors came back from the device sorted (no equal target positions), [55] queries sorted by the host replay
 void pgmm_get_stats(double *out, int n, int reset) {
   std::lock_guard<std::mutex> sl(g_stats_mu);
   double cpu[kCpuPhases];
   cpu_phase_read(cpu, reset != 0);
-  const double v[44 + kCpuPhases] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
+  const double v[46 + kCpuPhases] = {g_stats.total_ms, g_stats.seed_ms, g_stats.dp_kernel_ms, g_stats.index_ms, (double)g_stats.dp_jobs,
                         (double)g_stats.dp_cells, (double)g_stats.dp_waves, (double)g_stats.bases_mapped,
                         (double)g_stats.bases_indexed, (double)g_stats.batches, (double)g_stats.launches + (double)pgmm::g_seed_launches + (double)g_stats.chain_launches,
                         g_stats.t_encode, g_stats.t_seed, g_stats.t_chain, g_stats.t_dp, g_stats.t_stitch, g_stats.t_final,
@@ -436,9 +437,11 @@ void pgmm_get_stats(double *out, int n, int reset) {
                         (double)g_stats.chain_anchors, (double)g_stats.chain_segments, (double)g_stats.chain_redo_segments,
                         (double)g_stats.chain_redo_anchors, (double)g_stats.chain_launches,
                         (double)g_stats.chain_iterations, (double)g_stats.chain_batches,
-                        cpu[0], cpu[1], cpu[2], cpu[3], cpu[4], cpu[5], cpu[6], cpu[7], cpu[8], cpu[9]};
-  for (int i = 0; i < n && i < 44 + kCpuPhases; ++i) out[i] = v[i];
+                        cpu[0], cpu[1], cpu[2], cpu[3], cpu[4], cpu[5], cpu[6], cpu[7], cpu[8], cpu[9],
+                        (double)pgmm::g_anchor_sorted_device.load(), (double)pgmm::g_anchor_sorted_host.load()};
+  for (int i = 0; i < n && i < 46 + kCpuPhases; ++i) out[i] = v[i];
   if (reset) pgmm::g_seed_launches = 0, pgmm::h2d_bytes() = 0, pgmm::d2h_bytes() = 0, pgmm::DevicePool::misses() = 0;
+  if (reset) pgmm::g_anchor_sorted_device = 0, pgmm::g_anchor_sorted_host = 0;
   if (reset) g_stats = Stats();
 }
 

@@ -13,6 +13,7 @@
 //    looks at the last k unambiguous bases, walking over ambiguous ones.
 #include "seeding.h"
 
+#include <atomic>
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -21,6 +22,7 @@
 namespace pgmm {
 
 uint64_t g_seed_launches = 0;
+std::atomic<uint64_t> g_anchor_sorted_device{0}, g_anchor_sorted_host{0};  // queries whose anchor order came from the device / from the host replay
 
 namespace {
 
@@ -340,6 +342,33 @@ __global__ void sketch_gather_kernel(SeqView v, const SketchTile *__restrict__ t
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mx[o + i] = TX[g0 + i], my[o + i] = TY[g0 + i];
 }
 
+// ---------------- anchor order on the device ----------------
+// x of every anchor, its query as a second key, and after the two stable sorts: does any query hold two anchors with the same x?
+__global__ void anchor_keys_kernel(uint64_t n, const U128 *__restrict__ a, const uint64_t *__restrict__ qa_off, int nq,
+                                   uint64_t *__restrict__ kx, uint32_t *__restrict__ kq, uint32_t *__restrict__ perm) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = nq;  // qa_off[lo] <= i < qa_off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (qa_off[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  kx[i] = a[i].x, kq[i] = (uint32_t)lo, perm[i] = (uint32_t)i;
+}
+__global__ void gather_u32_kernel(uint64_t n, const uint32_t *__restrict__ src, const uint32_t *__restrict__ perm, uint32_t *__restrict__ dst) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+__global__ void anchor_gather_kernel(uint64_t n, const U128 *__restrict__ a, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ kq,
+                                     U128 *__restrict__ out, uint32_t *__restrict__ tie) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const U128 v = a[perm[i]];
+  out[i] = v;
+  if (i > 0 && kq[i - 1] == kq[i] && a[perm[i - 1]].x == v.x) tie[kq[i]] = 1;
+}
+
 struct MaxOp {
   __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
 };
@@ -613,7 +642,7 @@ struct SeedEngine::Impl {
   DevBuf<uint32_t> u32[16];
   DevBuf<uint64_t> u64[10];
   DevBuf<Seed> seeds, useds, flts;
-  DevBuf<U128> anchors;
+  DevBuf<U128> anchors, anchors_sorted;
   DevBuf<int32_t> rep_len, q_rank;
   DevBuf<int> qlens;
   PinBuf<U128> h_anchors;  // pinned landing zones for the two large device->host copies
@@ -929,7 +958,9 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
   uint64_t *h_u_off = m.pin<uint64_t>(nq + 1), *h_a_off = m.pin<uint64_t>(nq + 1);
   memset(h_u_off, 0, ((size_t)nq + 1) * 8), memset(h_a_off, 0, ((size_t)nq + 1) * 8);
   uint64_t *h_mini = nullptr;
-  U128 *h_anchors = nullptr;
+  U128 *h_anchors = nullptr, *a_sorted = nullptr;
+  const U128 *a_orig = nullptr;
+  uint32_t *a_tie = nullptr, *h_tie = nullptr;
   if (n_used > 0) {
     // ---- used seeds, their query positions (mini_pos) and the anchor slots they expand to ----
     Seed *useds = m.useds.ensure(n_used);
@@ -962,16 +993,59 @@ void SeedEngine::collect(const DeviceIndex &idx, const DeviceSeqSet &qs, const s
         U128 *anchors = m.anchors.ensure(n_anchor);
         ++g_seed_launches, compact_anchor_kernel<<<nblk(n_slots), TPB, 0, st>>>(n_slots, akeep, apos, ax, ay, anchors);
         h_anchors = m.h_anchors.ensure(n_anchor);
-        PGMM_CUDA(cudaMemcpyAsync(h_anchors, anchors, n_anchor * sizeof(U128), cudaMemcpyDeviceToHost, st));
+        // Worth it for small batches only: two random 19-mers of a 5-Mbp genome coincide often enough (a few dozen pairs) that a
+        // large query practically always holds a tie somewhere, and a tie anywhere sends the whole query to the host replay.
+        static const uint64_t dev_sort_max = getenv("PGMM_DEVICE_ANCHOR_SORT_MAX") ? (uint64_t)atoll(getenv("PGMM_DEVICE_ANCHOR_SORT_MAX")) : 65536;
+        if (n_anchor <= dev_sort_max) {
+          // The reference sorts every query's anchors by target position with an UNSTABLE in-place radix sort (map.c:202):
+          // the order it leaves among equal positions is observable, everything else is not.  So: stable sort on the device
+          // (by position, then by query), look for equal neighbours; a query without any gets its anchors back sorted and
+          // the host skips its replay of the reference's sort, a query with ties gets them in collection order as before.
+          uint64_t *kx = m.u64[3].ensure(n_anchor), *kx2 = m.u64[4].ensure(n_anchor);
+          uint32_t *kq = m.u32[12].ensure(n_anchor), *kq2 = m.u32[13].ensure(n_anchor), *pm = m.u32[14].ensure(n_anchor), *pm2 = m.u32[15].ensure(n_anchor);
+          a_tie = m.u32[8].ensure(nq + 1);
+          a_sorted = m.anchors_sorted.ensure(n_anchor);
+          PGMM_CUDA(cudaMemsetAsync(a_tie, 0, ((size_t)nq + 1) * 4, st));
+          ++g_seed_launches, anchor_keys_kernel<<<nblk(n_anchor), TPB, 0, st>>>(n_anchor, anchors, qa_off, nq, kx, kq, pm);
+          size_t bytes = 0;
+          PGMM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kx, kx2, pm, pm2, (int64_t)n_anchor, 0, 64, st));
+          PGMM_CUDA(cub::DeviceRadixSort::SortPairs(m.tmp(bytes), bytes, kx, kx2, pm, pm2, (int64_t)n_anchor, 0, 64, st));
+          if (nq > 1) {  // anchors of all queries went through one sort: bring every query's back together (stable, by query)
+            int qbits = 1;
+            while ((1 << qbits) < nq) ++qbits;
+            ++g_seed_launches, gather_u32_kernel<<<nblk(n_anchor), TPB, 0, st>>>(n_anchor, kq, pm2, kq2);  // query of each sorted anchor
+            PGMM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kq2, kq, pm2, pm, (int64_t)n_anchor, 0, qbits, st));
+            PGMM_CUDA(cub::DeviceRadixSort::SortPairs(m.tmp(bytes), bytes, kq2, kq, pm2, pm, (int64_t)n_anchor, 0, qbits, st));
+            // (kq: queries ascending = the segments of qa_off; pm: the permutation)
+          } else {
+            PGMM_CUDA(cudaMemsetAsync(kq, 0, n_anchor * 4, st));
+            uint32_t *t = pm; pm = pm2, pm2 = t;
+          }
+          ++g_seed_launches, anchor_gather_kernel<<<nblk(n_anchor), TPB, 0, st>>>(n_anchor, anchors, pm, kq, a_sorted, a_tie);
+          PGMM_CUDA(cudaGetLastError());
+          h_tie = m.pin<uint32_t>(nq + 1);
+          PGMM_CUDA(cudaMemcpyAsync(h_tie, a_tie, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+          PGMM_CUDA(cudaMemcpyAsync(h_anchors, a_sorted, n_anchor * sizeof(U128), cudaMemcpyDeviceToHost, st));
+          a_orig = anchors;
+        } else PGMM_CUDA(cudaMemcpyAsync(h_anchors, anchors, n_anchor * sizeof(U128), cudaMemcpyDeviceToHost, st));
       }
     }
   }
   PGMM_CUDA(cudaStreamSynchronize(st));
+  bool refetch = false;
+  for (int q = 0; q < nq && h_tie; ++q)
+    if (h_tie[q] && h_a_off[q + 1] > h_a_off[q]) {  // equal positions in this query: the host needs the collection order
+      PGMM_CUDA(cudaMemcpyAsync(h_anchors + h_a_off[q], a_orig + h_a_off[q], (h_a_off[q + 1] - h_a_off[q]) * sizeof(U128), cudaMemcpyDeviceToHost, st));
+      refetch = true;
+    }
+  if (refetch) PGMM_CUDA(cudaStreamSynchronize(st));
   for (int q = 0; q < nq; ++q) {
     QuerySeeds &o = out[q];
     o.rep_len = h_rep[q];
     if (h_mini) o.mini_pos.assign(h_mini + h_u_off[q], h_mini + h_u_off[q + 1]);
     if (h_anchors) o.a.assign(h_anchors + h_a_off[q], h_anchors + h_a_off[q + 1]);
+    o.sorted = h_tie != nullptr && h_tie[q] == 0;
+    if (!o.a.empty()) ++(o.sorted ? g_anchor_sorted_device : g_anchor_sorted_host);
   }
 }
 

@@ -3,6 +3,7 @@
 // (index.c:213-265,408-456), mm_idx_cal_max_occ (index.c:186-207), mm_seed_mz_flt / mm_collect_matches /
 // mm_seed_select (seed.c) and collect_seed_hits without its final sort (map.c:168-204).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -15,6 +16,7 @@
 namespace pgmm {
 
 extern uint64_t g_seed_launches;  // kernels launched by the sketch / index / seeding stages (ours + CUB)
+extern std::atomic<uint64_t> g_anchor_sorted_device, g_anchor_sorted_host;  // queries by where their anchor order came from
 
 // A set of sequences whose coded bases (0..4) sit in one device buffer, plus their minimizers.
 struct DeviceSeqSet {

@@ -41,7 +41,7 @@ def test_bench_pair_full_size(ref):
     sys.path.insert(0, ROOT)
     import bench
     (seqs, names), = bench.make_pairs(1, 0, 5_000_000)
-    n, _ = compare(seqs, names)
+    n, st = compare(seqs, names)
     assert n >= 20
     n2, _ = compare(seqs, names, resident=True)
     assert n2 == n
@@ -54,6 +54,7 @@ def test_ecoli_pair(ref):
     n, st = compare(seqs, ["0", "1"])
     assert n == 2002
     assert st["chain_redo_segments"] > 0 and st["chain_redo_anchors"] > 0
+    assert st["anchor_sort_host"] >= 1  # repeats: equal target positions, the host replays the reference's unstable sort
 
 
 def test_klebsiella_pair(ref):
@@ -95,10 +96,15 @@ def test_many_rounds_in_flight(ref):
         return out
 
     jobs = [(r, rep % 2 == 1) for rep in range(4) for r in range(12)]
+    abi.get_stats(reset=True)
     with ThreadPoolExecutor(12) as ex:
         got = list(ex.map(run, jobs))
     for (r, _), g in zip(jobs, got):
         assert g == want[r], r
+    st = abi.get_stats(reset=True)
+    # small batches take their anchor order from the device when no two anchors of a query share a target position, and from
+    # the host's replay of the reference's unstable sort otherwise (the rounds with repeats): both happen here
+    assert st["anchor_sort_device"] > 0 and st["anchor_sort_host"] > 0
 
 
 def test_mm_map_from_many_threads_sharing_one_index(ref):
