@@ -15,6 +15,7 @@
 #include "pgmm_cuda.h"
 
 #include <algorithm>
+#include <type_traits>
 #include <numeric>
 
 namespace pgmm {
@@ -296,13 +297,14 @@ struct LaneConsts {  // computed on the host, passed as a kernel parameter: the 
 
 // One anti-diagonal step of a pair.  In: x, v, x2 of the cells to the left (previous anti-diagonal), u, y, y2 of the
 // pair itself, the two target and the two query codes.  Out: the new state and the two traceback bytes (low byte =
-// low cell).  HAS_N is uniform per problem: sequences without ambiguous bases skip the third score.
-__device__ __forceinline__ uint32_t pair_step(const LaneConsts &c, bool has_n, uint32_t XT1, uint32_t VT1, uint32_t X2T1, uint32_t Uo,
+// low cell).  HAS_N: whether the two windows hold any ambiguous base (uniform per problem; the loops exist in both versions).
+template <bool HAS_N>
+__device__ __forceinline__ uint32_t pair_step(const LaneConsts &c, uint32_t XT1, uint32_t VT1, uint32_t X2T1, uint32_t Uo,
                                               uint32_t Yo, uint32_t Y2o, uint32_t tq, uint32_t qq, uint32_t &Un, uint32_t &Vn,
                                               uint32_t &Xn, uint32_t &Yn, uint32_t &X2n, uint32_t &Y2n) {
   const uint32_t ne = __vminu2(tq ^ qq, 0x00010001u);
   uint32_t Z = c.MCH7 - ne * c.DM8;  // halves stay positive: exact per half
-  if (has_n) {
+  if (HAS_N) {
     const uint32_t isn = __vminu2((tq | qq) & 0x00040004u, 0x00010001u) * 0xffffu;
     Z = (Z & ~isn) | (c.SCN7 & isn);
   }
@@ -313,10 +315,13 @@ __device__ __forceinline__ uint32_t pair_step(const LaneConsts &c, bool has_n, u
   const uint32_t Z8 = __vminu2(M, c.MCH7) & 0xfff8fff8u;  // z, offset 0x8000
   Un = Z8 - VT1, Vn = Z8 - Uo;                            // offset back to 0x4000
   const uint32_t A = XT1 - Un + c.CQ, B = Yo - Vn + c.CQ, A2 = X2T1 - Un + c.CQ2, B2 = Y2o - Vn + c.CQ2;
-  uint32_t acc = __vadd2(A, 0xcff8cff8u) & 0x10001000u;          // - 0x3008
-  acc |= __vadd2(B, 0xdff8dff8u) & 0x20002000u;                  // - 0x2008
-  acc |= __vadd2(A2, 0xfff8fff8u) & 0x40004000u;                 // - 8
-  acc |= (B2 + 0x3ff83ff8u) & 0x80008000u;                      // + 0x3ff8: no carry out of a half
+  // plain 32-bit adds (they can go to the FMA pipe; the kernel is bound by the ALU pipe): the three negative constants make
+  // the low half carry into the high one, always, which lifts the high half by one -- below the slack of the thresholds
+  // (the tags are at most 6, so 8a + tag + 1 >= 8 still means a >= 1)
+  uint32_t acc = (A + 0xcff8cff8u) & 0x10001000u;   // - 0x3008
+  acc |= (B + 0xdff8dff8u) & 0x20002000u;           // - 0x2008
+  acc |= (A2 + 0xfff8fff8u) & 0x40004000u;          // - 8
+  acc |= (B2 + 0x3ff83ff8u) & 0x80008000u;          // + 0x3ff8: no carry out of a half
   // max(a, 0) - (q + e): signed lanes here (the addend is negative, all three operands are far from the 16-bit limits)
   Xn = __viaddmax_s16x2(A, c.NQE, c.FLX), Yn = __viaddmax_s16x2(B, c.NQE, c.FLY);
   X2n = __viaddmax_s16x2(A2, c.NQE2, c.FLX2), Y2n = __viaddmax_s16x2(B2, c.NQE2, c.FLY2);
@@ -408,14 +413,20 @@ __global__ void __launch_bounds__(kFillWarps * 32, 7) ksw_fill_small_kernel(cons
   uint8_t *prow_l = P + 2 * lane;
   const bool last_lane = lane == 31;
 
+  // the loop exists twice: with and without the ambiguous-base score (decided once per problem)
+  const auto main_loop = [&](auto has_n_tag) {
+  constexpr bool HAS_N = decltype(has_n_tag)::value;
   for (int r = 0; r < n_row; ++r, prow_l += Tp) {
     const int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0, en0 = r < tlen - 1 ? r : tlen - 1;
     const uint32_t UF = lc.ufirst(r);
     const int p_lo = st0 >> 1, p_hi = en0 >> 1;  // active pairs
     const int qbase = 2 * kFillMaxT + (qlen - 1 - r);  // halfword index of the query base of target position 0
     // the copy in which (t=0, t=1) is an aligned 32-bit word: copy 1 is copy 0 shifted by one element
-    const uint32_t qaddr = ((qbase & 1) ? qa1 : qa0) + 4u * (uint32_t)(qbase >> 1);
-    const int fr_k = en0 == r ? r >> 6 : -1, fr_lane = (r >> 1) & 31;  // slot and lane of the first-row cell, if any
+    uint32_t qaddr = ((qbase & 1) ? qa1 : qa0) + 4u * (uint32_t)(qbase >> 1);
+    int fr_k = en0 == r ? r >> 6 : -1, fr_lane = (r >> 1) & 31;  // slot and lane of the first-row cell, if any
+    // opaque to the optimiser: left alone it re-derives all three in every slot (the shared-window base from %cluster_ctaid,
+    // the first-row test from r) -- 20 of ~80 instructions per slot
+    asm volatile("" : "+r"(qaddr), "+r"(fr_k), "+r"(fr_lane));
 #pragma unroll
     for (int k = 3; k >= 0; --k) {
       if (32 * k > p_hi || 32 * k + 31 < p_lo) continue;  // warp-uniform
@@ -437,7 +448,7 @@ __global__ void __launch_bounds__(kFillWarps * 32, 7) ksw_fill_small_kernel(cons
       }
       uint32_t qq;
       asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qq) : "r"(qaddr + 128u * k));
-      const uint32_t d16 = pair_step(lc, has_n, XT1, VT1, X2T1, Uo, Yo, Y2o, TQ[k], qq, U[k], V[k], X[k], Y[k], X2[k], Y2[k]);
+      const uint32_t d16 = pair_step<HAS_N>(lc, XT1, VT1, X2T1, Uo, Yo, Y2o, TQ[k], qq, U[k], V[k], X[k], Y[k], X2[k], Y2[k]);
       if (32 * k + lane <= p_hi) *(uint16_t *)(prow_l + 64 * k) = (uint16_t)d16;  // cells past the target end share the padded row
     }
     // The score (:367-379).  The reference walks a data-dependent staircase from (0,0) and adds v[last] or u[last+1] on
@@ -449,6 +460,9 @@ __global__ void __launch_bounds__(kFillWarps * 32, 7) ksw_fill_small_kernel(cons
       vsum += (w >> sh_end) & 0xffffu;
     }
   }
+  };
+  if (has_n) main_loop(std::true_type{});
+  else main_loop(std::false_type{});
   {
     const int gap1 = lc.q + lc.e * tlen, gap2 = lc.q2 + lc.e2 * tlen;
     const uint32_t tot = __shfl_sync(0xffffffffu, vsum, ((tlen - 1) >> 1) & 31);  // qlen halves of 8*v + 0x4000 each
@@ -584,7 +598,8 @@ __global__ void __launch_bounds__(NW * 32) ksw_fill_wide_kernel(const KswJob *__
       const int qi = qbase + 2 * p;
       const uint32_t qq = qi + 1 < qh_len ? ((uint32_t)QH[qi] | (uint32_t)QH[qi + 1] << 16) : 0u;
       uint32_t Un, Vn;
-      const uint32_t d16 = pair_step(lc, has_n, XT1, VT1, X2T1, Uo, Yo, Y2o, TQ[k], qq, Un, Vn, X[k], Y[k], X2[k], Y2[k]);
+      const uint32_t d16 = has_n ? pair_step<true>(lc, XT1, VT1, X2T1, Uo, Yo, Y2o, TQ[k], qq, Un, Vn, X[k], Y[k], X2[k], Y2[k])
+                                 : pair_step<false>(lc, XT1, VT1, X2T1, Uo, Yo, Y2o, TQ[k], qq, Un, Vn, X[k], Y[k], X2[k], Y2[k]);
       U[k] = Un, V[k] = Vn;
       if (p <= p_hi) *(uint16_t *)(prow + 2 * p) = (uint16_t)d16;
       const int t_lo = 2 * p, t_hi = 2 * p + 1;
