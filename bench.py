@@ -4,7 +4,7 @@
 One ROUND = one find_matches call of a guide-tree leaf merge: two related synthetic 5-Mbp genomes (1 % divergence,
 10 rearrangements each) are indexed and aligned all-vs-all, i.e. mm_idx_str + mm_mapopt_update + one
 mm_map per sequence in the reference, index kernels + pgmm_map_batch here.
-One STEP = `--rounds-per-step` (default 192) such rounds, `--workers` (default 64) of them in flight at any moment: sibling leaf merges of the guide tree are independent
+One STEP = `--rounds-per-step` (default 192) such rounds, `--workers` of them in flight at any moment (default: 6 per host core of the rank, 12..64): sibling leaf merges of the guide tree are independent
 (merge_graphs only reads its two children), so a rank keeps several of them in flight, one host thread and one CUDA
 stream each; their DP waves are merged across rounds by the library's DP service (dp_service.cu).  bp per step = total length of the genomes of its rounds.
 
@@ -458,7 +458,7 @@ def ours(args):
                                    f"at 1% divergence, 10 rearrangements (asm10, k=19 w=19)",
                        "l2": f"working set > L2: {n_pool} distinct genome pairs per rank ({n_pool * 2 * args.genome_len / 1e6:.0f} MB of bases), "
                              f"rounds in flight work on different pairs, > 1 GB of traceback written per round",
-                       "rounds_per_step": P, "rounds_in_flight": min(P, args.workers), "distinct_pairs_per_rank": n_pool,
+                       "rounds_per_step": P, "rounds_in_flight": min(P, args.workers), "host_cores_per_rank": (os.cpu_count() or 1) // max(1, env_int("LOCAL_WORLD_SIZE", world)), "distinct_pairs_per_rank": n_pool,
                        "steps_pipelined": "rounds of consecutive steps overlap inside the timed region (no drain between steps)",
                        "busy_host_cores": {"value": round(cpu_used.get("step_resident", 0), 1), "e2e": round(cpu_used.get("step_e2e", 0), 1)},
                        "hits_per_round": hits_res / max(1, rounds_timed), "host_threads": os.cpu_count(),
@@ -519,7 +519,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--rounds-per-step", type=int, default=192, help="independent leaf-merge rounds of one rank per step")
-    ap.add_argument("--workers", type=int, default=64, help="host threads driving rounds concurrently (one CUDA stream each)")
+    ap.add_argument("--workers", type=int, default=0, help="rounds in flight per rank (one host thread each); 0 = 6 per host core of the rank, at least 12, at most 64")
     ap.add_argument("--contexts", type=int, default=24, help="execution contexts of the library (PGMM_CONTEXTS)")
     ap.add_argument("--pool", type=int, default=32, help="distinct genome pairs generated per rank (rounds cycle through them)")
     ap.add_argument("--ref-rounds-per-step", type=int, default=0, help="reference arm / cpu_baseline: full-size rounds per step (0 = 2 per host thread)")
@@ -528,6 +528,15 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against oracle/_ref (profiling runs only)")
     ap.add_argument("--parity-all-ranks", action="store_true")
     args = ap.parse_args()
+    if args.workers <= 0:
+        # With few host cores per GPU (the 8-GPU boxes of this pool have 4) the host is the bound and more rounds in flight only
+        # add contention: 4 cores, 24 in flight 0.505 Gbp/s end to end against 0.421 with 64 (taskset on a one-GPU box).
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cores = os.cpu_count() or 1
+        per_rank = max(1, cores // max(1, env_int("LOCAL_WORLD_SIZE", env_int("WORLD_SIZE", 1))))
+        args.workers = max(12, min(64, 6 * per_rank))
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)
