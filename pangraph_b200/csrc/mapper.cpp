@@ -21,6 +21,7 @@
 #endif
 #include <functional>
 #include <thread>
+#include <memory_resource>
 #include <unordered_map>
 #include <ctime>
 
@@ -199,8 +200,7 @@ struct DpCached {
   int8_t zcode = -1;  // mm_test_zdrop's verdict on this result when it is a first-pass fill (-1 = not computed yet)
   int job = -1;  // >= 0: submitted in the current wave under this index, result not in yet
   KswOut ez;
-  std::shared_ptr<const KswBatchResult> keep;
-  const uint32_t *cigar = nullptr;
+  const uint32_t *cigar = nullptr;  // inside a wave result the query keeps alive (QCtx::wave_results)
 };
 
 struct DpCall {   // one DP window and, once its wave has run, its result
@@ -208,8 +208,9 @@ struct DpCall {   // one DP window and, once its wave has run, its result
   int wave = -1;  // the wave `job` belongs to
   struct DpCached *entry = nullptr;  // the query's result-cache entry of this problem (node addresses are stable), if it has one
   Ez ez = ez_reset();
-  // the CIGAR stays in the wave's result buffer (kept alive here) instead of being copied per problem
-  std::shared_ptr<const KswBatchResult> keep;
+  // the CIGAR stays in the wave's result buffer instead of being copied per problem; the buffer lives as long as the query
+  // (QCtx::wave_results holds one reference per wave -- a reference per problem was 70 000 atomic increments per round on a
+  // counter shared by every round of the merged wave)
   const uint32_t *cigar = nullptr;
 };
 
@@ -254,8 +255,12 @@ struct QCtx {
   std::vector<KswJob> jobs;  // this query's share of the next wave
   size_t job_base = 0;
   bool pending = false;
-  std::unordered_map<DpKey, DpCached, DpKeyHash> dp_cache;  // every DP result of this query so far
+  // every DP result of this query so far; its nodes come from a bump allocator that is released with the query (23 000
+  // windows per 5-Mbp query: one malloc and one free each otherwise)
+  std::pmr::monotonic_buffer_resource dp_pool{1 << 20};
+  std::pmr::unordered_map<DpKey, DpCached, DpKeyHash> dp_cache{&dp_pool};
   std::vector<DpCached *> wave_entries;                      // cache entry of jobs[i] of the wave being assembled / in flight
+  std::vector<std::shared_ptr<const KswBatchResult>> wave_results;  // every wave result this query's calls point into
   uint64_t dp_reused = 0;
   int wave_id = 0, done_wave = -1;  // the wave being assembled; the last one whose results are in
 };
@@ -655,7 +660,6 @@ struct Mapper {
               int zdrop, int end_bonus, int flag) const {
     c.ez = ez_reset();
     c.cigar = nullptr;
-    c.keep.reset();
     c.job = -1, c.entry = nullptr;
     if (opt.max_sw_mat > 0 && (int64_t)tl * ql > opt.max_sw_mat) {
       c.ez.zdropped = 1;
@@ -677,7 +681,7 @@ struct Mapper {
       if (!ins.second) {
         ++q.dp_reused;
         if (e.job >= 0) c.job = e.job, q.pending = true;  // asked for earlier in this very wave: share the slot
-        else c.ez = e.ez, c.keep = e.keep, c.cigar = e.cigar;
+        else c.ez = e.ez, c.cigar = e.cigar;
         return;
       }
       e.job = (int)q.jobs.size();
@@ -689,10 +693,11 @@ struct Mapper {
   }
   // the results of the wave that just ran become reusable (before any hit of the query looks at them)
   static void publish_wave(QCtx &q, const std::shared_ptr<const KswBatchResult> &res) {
+    q.wave_results.push_back(res);
     for (size_t k = 0; k < q.wave_entries.size(); ++k) {
       DpCached &e = *q.wave_entries[k];
       const size_t g = q.job_base + k;
-      e.job = -1, e.ez = res->out[g], e.keep = res, e.cigar = res->cigar.data() + res->cig_start[g];
+      e.job = -1, e.ez = res->out[g], e.cigar = res->cigar.data() + res->cig_start[g];
     }
     q.wave_entries.clear();
   }
@@ -797,7 +802,6 @@ struct Mapper {
     if (c.job < 0) return;
     const size_t g = q.job_base + (size_t)c.job;
     c.ez = res->out[g];
-    c.keep = res;
     c.cigar = res->cigar.data() + res->cig_start[g];
     c.job = -1;
   }
@@ -900,6 +904,16 @@ struct Mapper {
     }
     {  // gap fills between anchors (align.c:726-757): first pass of every fill, approximate max, effectively unbanded
       int32_t frs = rs, fqs = qs;
+      {  // how many fills there will be: the vector is sized once (a Fill is ~200 bytes)
+        size_t n_fill = 0;
+        int32_t crs = rs, cqs = qs;
+        for (int32_t i = 1; i < cnt1; ++i) {
+          if ((a[as1 + i].y & (SEED_IGNORE | SEED_TANDEM)) && i != cnt1 - 1) continue;
+          const int32_t fre = (int32_t)a[as1 + i].x - half_k, fqe = (int32_t)a[as1 + i].y - half_k;
+          if (i == cnt1 - 1 || (a[as1 + i].y & SEED_LONG_JOIN) || (fqe - cqs >= opt.min_ksw_len && fre - crs >= opt.min_ksw_len)) ++n_fill, crs = fre, cqs = fqe;
+        }
+        R.fills.reserve(n_fill);
+      }
       for (int32_t i = 1; i < cnt1; ++i) {
         if ((a[as1 + i].y & (SEED_IGNORE | SEED_TANDEM)) && i != cnt1 - 1) continue;
         const int32_t fre = (int32_t)a[as1 + i].x - half_k, fqe = (int32_t)a[as1 + i].y - half_k;
@@ -1093,7 +1107,6 @@ struct Mapper {
     if (R.has_p) update_extra(R, q.q0[r.rev] + qs1, tseq(R.rid, rs1));
     R.fills.clear();
     R.fills.shrink_to_fit();
-    R.left.keep.reset(), R.right.keep.reset();
     return r2;
   }
 
@@ -1151,7 +1164,6 @@ struct Mapper {
     ri.rs = Rinv.rs0 + Rinv.inv_t_off;
     ri.re = ri.rs + ez.max_t + 1;
     update_extra(Rinv, q.q0[Rinv.rev] + Rinv.qs0 + Rinv.inv_q_off, tseq(rid, Rinv.rs0 + Rinv.inv_t_off));
-    Rinv.inv.keep.reset();
     return true;
   }
 
