@@ -85,6 +85,7 @@ void encode_queries(QueryBatch &qb, const TargetSet &ts, int n_threads) {
   std::vector<uint64_t> vstart(qb.n + 1, 0);
   for (int i = 0; i < qb.n; ++i) qb.base[i] = tot, tot += 2ull * qb.lens[i], vstart[i + 1] = vstart[i] + (uint64_t)qb.lens[i];
   qb.codes.resize(tot + 16);
+  memset(qb.codes.data() + tot, 0, 16);  // (the buffer itself is not zero-filled: every base is written below)
   // forward codes and their reverse complement per query (align.c:969-975), chunked over all bases of the batch
   parallel_chunks(vstart[qb.n], n_threads, [&](uint64_t lo, uint64_t hi) {
     CpuScope cpu_scope(0);
@@ -93,9 +94,8 @@ void encode_queries(QueryBatch &qb, const TargetSet &ts, int n_threads) {
       while (vstart[i + 1] <= p) ++i;
       const uint64_t L = (uint64_t)qb.lens[i], j0 = p - vstart[i], j1 = std::min(L, hi - vstart[i]);
       uint8_t *f = qb.codes.data() + qb.base[i], *r = f + L;
-      if (qb.from_targets) {  // codes are there already: copy, and reverse-complement eight bases at a time
-        const uint8_t *s = ts.codes.data() + ts.offs[i];
-        memcpy(f + j0, s + j0, (size_t)(j1 - j0));
+      if (qb.from_targets) {  // codes are there already: only the reverse complement is built, eight bases at a time
+        const uint8_t *s = ts.codes.data() + ts.offs[i];  // (the forward strand is read in place: map_batch points q0[0] here)
         uint64_t j = j0;
         for (; j + 8 <= j1; j += 8) {
           uint64_t x;
@@ -1567,7 +1567,7 @@ void map_batch(Backend &be, const TargetSet &ts, QueryBatch &qb, const mm_mapopt
     CpuScope cpu_scope(2);
     QCtx &q = Q[i];
     q.qi = i, q.qlen = qb.lens[i], q.qname = qb.names[i], q.qbase = qb.base[i];
-    q.q0[0] = qb.codes.data() + q.qbase, q.q0[1] = q.q0[0] + q.qlen;
+    q.q0[0] = qb.from_targets ? ts.codes.data() + ts.offs[i] : qb.codes.data() + q.qbase, q.q0[1] = qb.codes.data() + q.qbase + q.qlen;
     if (q.qlen == 0) return;
     if (opt.max_qlen > 0 && q.qlen > opt.max_qlen) return;
     uint32_t h = q.qname && !(opt.flag & MM_F_NO_HASH_NAME) ? x31_hash(q.qname) : 0;  // map.c:246-248

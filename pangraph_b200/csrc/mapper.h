@@ -26,12 +26,26 @@ struct TargetSet {
 };
 
 // One batch of queries: ASCII in, coded forward and reverse-complement copies kept on both sides.
+// std::vector<uint8_t>::resize zero-fills; the 20 MB query buffer of a 5-Mbp pair is overwritten right away
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = DefaultInitAlloc<U>;
+  };
+  template <class U, class... Args>
+  void construct(U *p, Args &&...args) {
+    if constexpr (sizeof...(Args) == 0) ::new ((void *)p) U;
+    else ::new ((void *)p) U(std::forward<Args>(args)...);
+  }
+};
+
 struct QueryBatch {
   int n = 0;
   std::vector<const char *> seqs, names;
   std::vector<int> lens;
   std::vector<uint64_t> base;  // query i: forward codes at codes[base[i] .. +len), reverse complement right after
-  std::vector<uint8_t> codes;
+  std::vector<uint8_t, DefaultInitAlloc<uint8_t>> codes;
   bool from_targets = false;   // the queries ARE the indexed sequences (pangraph's all-vs-all round): seqs is unused and
                                // the device builds its query buffer from the resident target codes
 };

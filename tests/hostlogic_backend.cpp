@@ -210,8 +210,7 @@ extern "C" __attribute__((visibility("default"))) int pgmm_test_ll_score(int qle
   return ll_local_score(qlen, q, tlen, t, mat, gapo, gape, qe, te);
 }
 
-// encode_queries in its two modes: from ASCII, and from the resident target codes (pgmm_map_self); out gets both results
-// back to back (2 * total bases each).  Returns 0 when they agree.
+// encode_queries in its two modes: from ASCII, and from the resident target codes (pgmm_map_self).  Returns 0 when they agree.
 extern "C" __attribute__((visibility("default"))) int pgmm_test_encode_modes(int n, const char *const *seqs, const int *lens, int n_threads) {
   TargetSet ts;
   uint64_t sum = 0;
@@ -231,7 +230,13 @@ extern "C" __attribute__((visibility("default"))) int pgmm_test_encode_modes(int
   encode_queries(a, ts, n_threads);
   encode_queries(b, ts, n_threads);
   if (a.base != b.base) return 1;
-  return memcmp(a.codes.data(), b.codes.data(), 2 * sum) == 0 ? 0 : 2;
+  // from the resident codes only the reverse complements are built (the forward strand is read in place from ts.codes)
+  for (int i = 0; i < n; ++i) {
+    const uint64_t L = (uint64_t)lens[i];
+    if (memcmp(a.codes.data() + a.base[i], ts.codes.data() + ts.offs[i], L) != 0) return 3;                    // ASCII path, forward
+    if (memcmp(a.codes.data() + a.base[i] + L, b.codes.data() + b.base[i] + L, L) != 0) return 2;             // both paths, reverse
+  }
+  return 0;
 }
 
 // the product's host arbiter on every segment: f, p, v (n int32 each) of sorted anchors
