@@ -339,6 +339,39 @@ PGMM_API int pgmm_map_variations_batch(int n, const char *const *refs, const int
                                        int extra_band_width, int max_alignment_attempts, pgmm_edit_t **out, double *stats);
 PGMM_API void pgmm_edits_free(pgmm_edit_t *edits, int n);
 
+/* ===================== Part 5: the guide tree ===================== */
+
+/* mash_distance (packages/pangraph/src/distance/mash/mash_distance.rs:9-68) over minimizers_sketch
+ * (distance/mash/minimizer.rs:49-160): sketches of all sequences, the number of distinct minimizer values each pair shares
+ * (K7 on the GPU), dist[i][j] = 1 - shared(i, j) / distinct(min(i, j)).  seqs[i] = raw FASTA bytes of sequence i (any case;
+ * everything but ACGTU is an ambiguous base).  The reference always calls it with k = 15, w = 100 (MinimizersParams::default,
+ * tree/neighbor_joining.rs:42).  dist = n x n doubles, row-major.
+ * -> 0; 1 + i: sequence i has no minimizer (the reference panics: "no minimizer found for a sequence during mash distance
+ * evaluation"); -1: k outside 1..31 or w outside 1..255 (the reference's assert!s); -2: n < 1; -3: 2k + bits(n) > 64;
+ * -4: a sequence of 2^31 bases or more; -5: the incidence bitmap does not fit the device.
+ * stats (optional, 10 doubles): upload ms, sketch ms, sort ms, pair ms, bases, tiles, minimizers, distinct (value, sequence)
+ * keys, values shared by two or more sequences, kernel launches. */
+PGMM_API int pgmm_mash_distance(int n, const char *const *seqs, const int64_t *lens, int k, int w, double *dist, double *stats);
+
+/* build_tree_using_neighbor_joining (tree/neighbor_joining.rs:16-35, 46-101) on an n x n distance matrix; host code.
+ * Leaves are 0..n-1, the node made by the t-th join is n + t with children left[t], right[t] (n - 1 entries each), the root
+ * is 2n - 2.  -> 0; -1: n < 2 (the reference indexes nodes[1] and panics); -2: a NaN in the matrix. */
+PGMM_API int pgmm_nj_tree(int n, const double *dist, int32_t *left, int32_t *right);
+
+/* parse_newick (tree/newick.rs:43-62): *n_leaves leaves numbered in order of appearance, *names = their labels separated by
+ * '\0' (one malloc block), *left / *right = children of the nodes n, n + 1, ... (malloc, n - 1 entries, root last).
+ * -> 0, or -1 with the reference's message in err (truncated to err_cap).  Branch lengths and internal labels are read and
+ * dropped; only strictly bifurcating trees are accepted. */
+PGMM_API int pgmm_newick_parse(const char *text, int32_t *n_leaves, char **names, int64_t *names_bytes, int32_t **left, int32_t **right,
+                               char *err, int err_cap);
+/* Clade::to_newick (tree/newick.rs:11-38): -> malloc'd string (internal nodes unlabeled) */
+PGMM_API char *pgmm_newick_write(int n, const char *const *names, const int32_t *left, const int32_t *right);
+/* balance (tree/balance.rs:4-18): the same leaves left to right under a bisected tree */
+PGMM_API int pgmm_tree_balance(int n, const int32_t *left, const int32_t *right, int32_t *out_left, int32_t *out_right);
+/* postorder (tree/clade.rs:49-71): the 2n - 1 nodes in the order the reference's build loop visits them */
+PGMM_API int pgmm_tree_postorder(int n, const int32_t *left, const int32_t *right, int32_t *order);
+PGMM_API void pgmm_free(void *p);
+
 /* counters since the last reset: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells
  * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] kernel launches [11..16] wall ms of the phases of
  * pgmm_map_batch (encode, seeding, sort+chain+plan, DP waves, stitching between waves, final filters)

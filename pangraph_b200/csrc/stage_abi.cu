@@ -2,7 +2,9 @@
 // oracle in isolation.  Declared in include/pgmm_b200.h.
 #include "../../include/pgmm_b200.h"
 #include "chain_fill.h"
+#include "guide_tree.h"
 #include "ksw_extd2.h"
+#include "mash.h"
 #include "nextalign.h"
 #include "pgmm_cuda.h"
 
@@ -167,3 +169,72 @@ extern "C" void pgmm_edits_free(pgmm_edit_t *edits, int n) {
   }
   free(edits);
 }
+
+// ---------------- Part 5: the guide tree ----------------
+extern "C" int pgmm_mash_distance(int n, const char *const *seqs, const int64_t *lens, int k, int w, double *dist, double *stats) {
+  if (n < 1) return -2;
+  std::vector<uint32_t> counts((size_t)n * n);
+  mash::Stats st;
+  if (const int rc = mash::shared_counts(seqs, lens, n, k, w, counts.data(), &st)) return rc;
+  if (stats) {
+    stats[0] = st.upload_ms, stats[1] = st.sketch_ms, stats[2] = st.sort_ms, stats[3] = st.pair_ms, stats[4] = (double)st.bases;
+    stats[5] = (double)st.tiles, stats[6] = (double)st.minimizers, stats[7] = (double)st.unique_keys, stats[8] = (double)st.shared_values;
+    stats[9] = (double)st.launches;
+  }
+  return gt::distances_from_counts(counts.data(), n, dist);
+}
+
+extern "C" int pgmm_nj_tree(int n, const double *dist, int32_t *left, int32_t *right) {
+  gt::Tree t;
+  if (const int rc = gt::neighbor_joining(dist, n, t)) return rc;
+  std::copy(t.left.begin(), t.left.end(), left), std::copy(t.right.begin(), t.right.end(), right);
+  return 0;
+}
+
+extern "C" int pgmm_newick_parse(const char *text, int32_t *n_leaves, char **names, int64_t *names_bytes, int32_t **left, int32_t **right,
+                                 char *err, int err_cap) {
+  gt::Tree t;
+  std::vector<std::string> leaf_names;
+  std::string msg;
+  *n_leaves = 0, *names = nullptr, *names_bytes = 0, *left = nullptr, *right = nullptr;
+  if (!gt::parse_newick(text ? text : "", t, leaf_names, msg)) {
+    if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", msg.c_str());
+    return -1;
+  }
+  std::string joined;
+  for (const std::string &s : leaf_names) joined += s, joined.push_back('\0');
+  *n_leaves = t.n, *names_bytes = (int64_t)joined.size();
+  *names = dup_array(joined.data(), joined.size());
+  *left = dup_array(t.left.data(), t.left.size()), *right = dup_array(t.right.data(), t.right.size());
+  return 0;
+}
+
+static gt::Tree tree_of(int n, const int32_t *left, const int32_t *right) {
+  gt::Tree t;
+  t.n = n;
+  if (n > 1) t.left.assign(left, left + (n - 1)), t.right.assign(right, right + (n - 1));
+  return t;
+}
+
+extern "C" char *pgmm_newick_write(int n, const char *const *names, const int32_t *left, const int32_t *right) {
+  std::vector<std::string> leaf_names;
+  for (int i = 0; i < n; ++i) leaf_names.emplace_back(names[i]);
+  const std::string s = gt::to_newick(tree_of(n, left, right), leaf_names);
+  return dup_array(s.c_str(), s.size() + 1);
+}
+
+extern "C" int pgmm_tree_balance(int n, const int32_t *left, const int32_t *right, int32_t *out_left, int32_t *out_right) {
+  if (n < 1) return -1;
+  const gt::Tree b = gt::balance(tree_of(n, left, right));
+  std::copy(b.left.begin(), b.left.end(), out_left), std::copy(b.right.begin(), b.right.end(), out_right);
+  return 0;
+}
+
+extern "C" int pgmm_tree_postorder(int n, const int32_t *left, const int32_t *right, int32_t *order) {
+  if (n < 1) return -1;
+  const std::vector<int32_t> o = gt::postorder(tree_of(n, left, right));
+  std::copy(o.begin(), o.end(), order);
+  return (int)o.size();
+}
+
+extern "C" void pgmm_free(void *p) { free(p); }
