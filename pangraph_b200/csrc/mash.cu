@@ -1,6 +1,6 @@
 // K7: the counts behind pangraph's mash distance (mash.h), all of it streaming integer work:
-//   1. sketch    one CTA per tile of 4096 positions (mash_core.h: bases staged with 128-bit loads, rolling k-mers, per-position
-//                decisions from shared memory); run twice -- a counting pass, a scan of the tile counts, a writing pass -- so
+//   1. sketch    one CTA per tile of 4096 positions (mash_core.h: bases staged with 128-bit loads, rolling k-mers, block
+//                prefix / suffix minima, per-position decisions from shared memory); run twice -- a counting pass, a scan of the tile counts, a writing pass -- so
 //                that the key array has its exact size and no position-sized scratch exists.  A key is value << seq_bits | seq.
 //   2. sort      one radix sort of the 64-bit keys, then the distinct keys (a value once per sequence that holds it).
 //   3. incidence values held by two or more sequences get a dense rank; a bitmap row per sequence over those ranks.
@@ -27,10 +27,7 @@ struct MashTile {
   uint32_t seq, t0;  // sequence and first position of the tile inside it
 };
 
-inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
-inline size_t tile_smem(int w, int k) {
-  return (size_t)cap_ev(w) * 8 + align16((size_t)cap_ev(w) * 2) + align16((size_t)cap_ev(w)) + align16((size_t)cap_codes(w, k));
-}
+inline size_t tile_smem(int w, int k) { return layout_of(w, k).total; }
 
 // WRITE = false: counts[tile] = flagged positions of the tile.  WRITE = true: their keys, in position order, from
 // keys[prefix[tile]] on.
@@ -45,10 +42,10 @@ __global__ void __launch_bounds__(kTileThreads) mash_tile_kernel(const uint8_t *
   const uint64_t s0 = starts[tl.seq];
   const Tile t = tile_of((int64_t)(starts[tl.seq + 1] - s0), (int64_t)tl.t0, w, k);
   const int ce = cap_ev(w);
-  uint64_t *X = (uint64_t *)mash_smem;
-  uint16_t *EL = (uint16_t *)(mash_smem + (size_t)ce * 8);
-  uint8_t *F = mash_smem + (size_t)ce * 8 + ((size_t)ce * 2 + 15) / 16 * 16;
-  uint8_t *CDraw = F + ((size_t)ce + 15) / 16 * 16;
+  const Layout lay = layout_of(w, k);
+  uint64_t *X = (uint64_t *)(mash_smem + lay.x);
+  uint16_t *EL = (uint16_t *)(mash_smem + lay.el), *P = (uint16_t *)(mash_smem + lay.p), *S = (uint16_t *)(mash_smem + lay.s);
+  uint8_t *F = mash_smem + lay.f, *CDraw = mash_smem + lay.cd;
 
   // stage the bases with 128-bit loads from the 16-byte boundary at or before the first one needed (`bases` is a cudaMalloc
   // block, so that boundary lies inside it), then turn the bytes into codes in place; CD[i] = code of position c_lo + i
@@ -67,7 +64,9 @@ __global__ void __launch_bounds__(kTileThreads) mash_tile_kernel(const uint8_t *
   __syncthreads();
   roll(t, w, k, tid, kTileThreads, CD, X, EL);
   __syncthreads();
-  decide(t, w, k, tid, kTileThreads, X, EL, F);
+  scan_blocks(t, w, tid, kTileThreads, X, P, S);
+  __syncthreads();
+  decide(t, w, k, tid, kTileThreads, X, EL, P, S, F);
   __syncthreads();
 
   typedef cub::BlockScan<int, kTileThreads> Scan;

@@ -66,8 +66,21 @@ MASH_HD Tile tile_of(int64_t L, int64_t t0, int w, int k) {
   t.n_ev = (int)(t.e_hi - t.e_lo), t.n_codes = (int)(t.e_hi - t.c_lo);
   return t;
 }
-MASH_HD int cap_ev(int w) { return kTile + 2 * w; }                 // slots of X / EL / F
+MASH_HD int cap_ev(int w) { return kTile + 2 * w; }                 // slots of X / EL / P / S / F
 MASH_HD int cap_codes(int w, int k) { return kTile + 3 * w + k + 48; }  // staged bases (+ alignment slack)
+
+// The tile's working set in shared memory (byte offsets, every part on a 16-byte boundary): values X[u64], run length |
+// strand << 15 EL[u16], block-prefix / block-suffix minima P, S [u16], flags F[u8], staged bases CD[u8].
+struct Layout {
+  uint32_t x, el, p, s, f, cd, total;
+};
+MASH_HD Layout layout_of(int w, int k) {
+  const uint32_t ce = (uint32_t)cap_ev(w), r16 = (ce * 2 + 15) / 16 * 16;
+  Layout l;
+  l.x = 0, l.el = ce * 8, l.p = l.el + r16, l.s = l.p + r16, l.f = l.s + r16, l.cd = l.f + (ce + 15) / 16 * 16;
+  l.total = l.cd + ((uint32_t)cap_codes(w, k) + 15) / 16 * 16;
+  return l;
+}
 
 // Thread `tid` of `n_threads`: value (or kNone) and run length | strand << 15 of its stretch of the slots [0, n_ev).
 // CD[i] = code of position c_lo + i.
@@ -106,27 +119,79 @@ MASH_HD void roll(const Tile &t, int w, int k, int tid, int n_threads, const uin
   }
 }
 
+// Sliding-window minima in two steps (van Herk / Gil-Werman): the slots are cut into blocks of w; inside each block P[a] is
+// the oldest of the smallest over [block start, a] and S[a] over [a, block end].  A window of w slots is the tail of one block
+// plus the head of the next, so its minimum is one comparison (window_min) instead of a scan of the window.  One task per
+// (block, direction).  Slots need 13 bits (kTile + 2 kMaxW < 8192); the bits above carry what window_min would otherwise
+// have to recompute: kDup = the smallest value occurs more than once in the scanned range, kWhole (P only) = the window
+// ending at this slot lies inside the block (its last slot, or any slot of block 0, where windows are cut by the start).
+constexpr uint16_t kSlotMask = 0x1fff, kWhole = 0x4000, kDup = 0x8000;
+MASH_HD void scan_blocks(const Tile &t, int w, int tid, int n_threads, const uint64_t *X, uint16_t *P, uint16_t *S) {
+  const int nblk = (t.n_ev + w - 1) / w;
+  for (int task = tid; task < 2 * nblk; task += n_threads) {
+    const int lo = (task >> 1) * w, hi = lo + w < t.n_ev ? lo + w : t.n_ev;
+    if (task & 1) {  // from the block's newest slot down: an equal value further down is older and wins
+      int best = hi - 1;
+      uint64_t xb = X[best];
+      uint16_t dup = 0;
+      S[best] = (uint16_t)best;
+      for (int a = hi - 2; a >= lo; --a) {
+        const uint64_t x = X[a];
+        if (x <= xb) dup = x == xb ? kDup : 0, xb = x, best = a;
+        S[a] = (uint16_t)(best | dup);
+      }
+    } else {
+      int best = lo;
+      uint64_t xb = X[lo];
+      uint16_t dup = 0;
+      const uint16_t whole0 = lo == 0 ? kWhole : 0;
+      P[lo] = (uint16_t)(lo | whole0 | (w == 1 ? kWhole : 0));
+      for (int a = lo + 1; a < hi; ++a) {
+        const uint64_t x = X[a];
+        if (x < xb) xb = x, best = a, dup = 0;
+        else if (x == xb) dup = kDup;
+        P[a] = (uint16_t)(best | dup | whole0 | (a == lo + w - 1 ? kWhole : 0));
+      }
+    }
+  }
+}
+// Slot of the oldest of the smallest values over the w slots ending at a (fewer at the start of the sequence); `dup` =
+// that value occurs at another slot of the window as well.
+MASH_HD int window_min(int a, int w, const uint64_t *X, const uint16_t *P, const uint16_t *S, bool &dup) {
+  const uint16_t pa = P[a];
+  const int p = pa & kSlotMask;
+  if (pa & kWhole) {
+    dup = (pa & kDup) != 0;
+    return p;
+  }
+  const uint16_t sl = S[a - w + 1];  // the window starts in the block before
+  const int s = sl & kSlotMask;
+  const uint64_t xp = X[p], xs = X[s];
+  dup = xp == xs || (((xp < xs ? pa : sl) & kDup) != 0);
+  return xp < xs ? p : s;
+}
+
 // Thread `tid`: the decisions of its share of the deciding positions [t0, e_hi); F[slot] = 1 for every position the
 // reference's scan appends (several threads may set the same flag).
-MASH_HD void decide(const Tile &t, int w, int k, int tid, int n_threads, const uint64_t *X, const uint16_t *EL, uint8_t *F) {
+MASH_HD void decide(const Tile &t, int w, int k, int tid, int n_threads, const uint64_t *X, const uint16_t *EL, const uint16_t *P,
+                    const uint16_t *S, uint8_t *F) {
   const int n_dec = (int)(t.e_hi - t.t0);
   for (int q = tid; q < n_dec; q += n_threads) {
     const int64_t ee = t.t0 + q;             // the position
     const int a = (int)(ee - t.e_lo);        // its slot
-    const int lo_prev = (int)((ee - w > 0 ? ee - w : 0) - t.e_lo), lo_new = (int)((ee - w + 1 > 0 ? ee - w + 1 : 0) - t.e_lo);
+    const int lo_new = (int)((ee - w + 1 > 0 ? ee - w + 1 : 0) - t.e_lo);
     const int jm = (int)(ee - w - t.e_lo);   // slot of the position that leaves the window at this step (negative: none yet)
     // oldest of the smallest over [ee-w, ee-1] (the scan's minimum before this step) and over [ee-w+1, ee] (after it)
-    int pm = -1, nm = -1;
-    uint64_t xpm = kNone, xnm = kNone;
-    for (int j = lo_prev; j < a; ++j) {
-      const uint64_t x = X[j];
-      if (x < xpm) xpm = x, pm = j;
-      if (j > jm && x < xnm) xnm = x, nm = j;
-    }
-    const uint64_t xe = X[a];
-    if (xe < xnm) xnm = xe, nm = a;
+    int pm = -1;
+    uint64_t xpm = kNone;
+    bool dup_pm = false, dup_nm = false;
+    if (a > 0) pm = window_min(a - 1, w, X, P, S, dup_pm), xpm = X[pm];
+    const int nm = window_min(a, w, X, P, S, dup_nm);
+    const uint64_t xnm = X[nm], xe = X[a];
     const int le = EL[a] & 0x7fff;
-    if (le == w + k - 1 && xpm != kNone)  // first full window: the other positions holding the minimum's value
+    // first full window: the other positions holding the minimum's value (the slot that just left the window held no
+    // value -- the run was k - 1 long there -- so there are none unless the old window had the value twice or this slot has it)
+    if (le == w + k - 1 && xpm != kNone && (dup_pm || xe == xpm))
       for (int j = lo_new; j <= a; ++j)
         if (X[j] == xpm && j != pm) F[j] = 1;
     if (xe < xpm) {  // a smaller value displaces the minimum
@@ -134,7 +199,7 @@ MASH_HD void decide(const Tile &t, int w, int k, int tid, int n_threads, const u
     } else if (xpm != kNone && pm == jm) {  // the minimum leaves the window
       if (le >= w + k - 1) {
         F[pm] = 1;
-        if (xnm != kNone)
+        if (xnm != kNone && dup_nm)  // (the scan below finds nothing unless the value occurs twice in the window)
           for (int j = lo_new; j <= a; ++j)
             if (X[j] == xnm && j != nm) F[j] = 1;
       }

@@ -13,24 +13,29 @@ using namespace pgmm::mash;
 extern "C" __attribute__((visibility("default"))) int64_t mash_emul_sketch(const char *seq, int64_t L, uint64_t id, int k, int w,
                                                                            uint64_t *value, uint64_t *position, int64_t cap) {
   if (k < 1 || k > kMaxK || w < 1 || w > kMaxW) return -1;
-  std::vector<uint64_t> X((size_t)cap_ev(w));
-  std::vector<uint16_t> EL((size_t)cap_ev(w));
-  std::vector<uint8_t> F((size_t)cap_ev(w)), CD((size_t)cap_codes(w, k));
+  const Layout lay = layout_of(w, k);
+  std::vector<uint64_t> smem((size_t)lay.total / 8 + 1);  // the kernel's shared memory, same offsets
+  uint8_t *sm = (uint8_t *)smem.data();
+  uint64_t *X = (uint64_t *)(sm + lay.x);
+  uint16_t *EL = (uint16_t *)(sm + lay.el), *P = (uint16_t *)(sm + lay.p), *S = (uint16_t *)(sm + lay.s);
+  uint8_t *F = sm + lay.f, *CD = sm + lay.cd;
   int64_t n = 0;
   for (int64_t t0 = 0; t0 < L; t0 += kTile) {
     const Tile t = tile_of(L, t0, w, k);
     if (t.n_ev > cap_ev(w) || t.n_codes > cap_codes(w, k)) return -2;
-    for (int i = 0; i < t.n_codes; ++i) CD[(size_t)i] = (uint8_t)code((uint8_t)seq[t.c_lo + i]);
-    std::fill(F.begin(), F.end(), 0);
-    std::fill(X.begin(), X.end(), 0x5555555555555555ull);  // slots past n_ev must never be read
-    for (int tid = 0; tid < kTileThreads; ++tid) roll(t, w, k, tid, kTileThreads, CD.data(), X.data(), EL.data());
-    for (int tid = 0; tid < kTileThreads; ++tid) decide(t, w, k, tid, kTileThreads, X.data(), EL.data(), F.data());
+    memset(sm, 0x55, lay.total);  // nothing may depend on what an earlier tile left behind
+    const int pre = (int)(t.c_lo & 15);  // the kernel's staging starts at a 16-byte boundary of the source
+    for (int i = 0; i < t.n_codes; ++i) CD[(size_t)(pre + i)] = (uint8_t)code((uint8_t)seq[t.c_lo + i]);
+    memset(F, 0, (size_t)cap_ev(w));
+    for (int tid = 0; tid < kTileThreads; ++tid) roll(t, w, k, tid, kTileThreads, CD + pre, X, EL);
+    for (int tid = 0; tid < kTileThreads; ++tid) scan_blocks(t, w, tid, kTileThreads, X, P, S);
+    for (int tid = 0; tid < kTileThreads; ++tid) decide(t, w, k, tid, kTileThreads, X, EL, P, S, F);
     const int base = (int)(t.t0 - t.e_lo);
     for (int j = 0; j < (int)(t.t1 - t.t0); ++j)
-      if (F[(size_t)(base + j)]) {
+      if (F[base + j]) {
         if (n < cap) {
-          value[n] = X[(size_t)(base + j)];
-          position[n] = id << 32 | (uint64_t)(t.t0 + j + 1) << 1 | (uint64_t)(EL[(size_t)(base + j)] >> 15);
+          value[n] = X[base + j];
+          position[n] = id << 32 | (uint64_t)(t.t0 + j + 1) << 1 | (uint64_t)(EL[base + j] >> 15);
         }
         ++n;
       }
