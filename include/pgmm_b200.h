@@ -372,6 +372,27 @@ PGMM_API int pgmm_tree_balance(int n, const int32_t *left, const int32_t *right,
 PGMM_API int pgmm_tree_postorder(int n, const int32_t *left, const int32_t *right, int32_t *order);
 PGMM_API void pgmm_free(void *p);
 
+/* ===================== Part 6: FASTA input ===================== */
+
+/* FastaRecord (packages/pangraph/src/io/fasta.rs:17-24).  desc == NULL where the reference has None.  seq is upper-cased and
+ * NUL-terminated; len = its length. */
+typedef struct pgmm_fasta_record_s {
+  char *name, *desc, *seq;
+  int64_t len, index;
+} pgmm_fasta_record_t;
+
+/* FastaReader::from_paths(paths).read_many() (io/fasta.rs:92-129, 131-225): the files one after the other (".gz" inflated;
+ * ".bz2" / ".xz" / ".zst" refused: this build links zlib only).  alphabet = accepted characters after upper-casing, NULL = the
+ * reference's default "ACGTYRWSKMDVHBN" (no gap).  *recs = malloc array of *n_recs records (pgmm_fasta_free).
+ * -> 0, or -1 with the reference's message in err ("FASTA input is incorrectly formatted: ...", "When processing sequence
+ * #i: \">name\": FASTA input is incorrect: character \"c\" is not in the alphabet"). */
+PGMM_API int pgmm_fasta_read_files(int n_paths, const char *const *paths, const char *alphabet, pgmm_fasta_record_t **recs,
+                                   int64_t *n_recs, char *err, int err_cap);
+/* the same over one buffer (FastaReader::from_str) */
+PGMM_API int pgmm_fasta_read_buffer(const char *data, int64_t n, const char *alphabet, pgmm_fasta_record_t **recs, int64_t *n_recs,
+                                    char *err, int err_cap);
+PGMM_API void pgmm_fasta_free(pgmm_fasta_record_t *recs, int64_t n_recs);
+
 /* counters since the last reset: [0] total_ms [1] seed_ms [2] dp_kernel_ms [3] index_ms [4] dp_jobs [5] dp_cells
  * [6] dp_waves [7] bases_mapped [8] bases_indexed [9] batches [10] kernel launches [11..16] wall ms of the phases of
  * pgmm_map_batch (encode, seeding, sort+chain+plan, DP waves, stitching between waves, final filters)

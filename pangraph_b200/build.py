@@ -46,7 +46,7 @@ def build(verbose=False, force=False):
             if r.returncode != 0:
                 raise RuntimeError(f"compiler failed on {s}")
     if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xlinker", "-Bsymbolic", "-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lz"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -4,6 +4,8 @@
 #include <cstring>
 #include <limits>
 
+#include "text_util.h"
+
 namespace pgmm {
 namespace gt {
 
@@ -211,25 +213,9 @@ struct Newick {
   Newick(const std::string &s, std::vector<std::string> &n, Tree &t) : in(s), names(n), tree(t) {}
   bool eof() const { return pos >= in.size(); }
   // the reference walks chars of a UTF-8 string; positions in its messages are byte offsets and every character it tests
-  // for is ASCII, so bytes behave the same except for non-ASCII whitespace (char::is_whitespace), handled in ws_len
-  size_t ws_len() const {
-    const unsigned char c = (unsigned char)in[pos];
-    if (c == ' ' || (c >= 0x09 && c <= 0x0d)) return 1;
-    if (c == 0xc2 && pos + 1 < in.size() && ((unsigned char)in[pos + 1] == 0x85 || (unsigned char)in[pos + 1] == 0xa0)) return 2;
-    if (c == 0xe1 && pos + 2 < in.size() && (unsigned char)in[pos + 1] == 0x9a && (unsigned char)in[pos + 2] == 0x80) return 3;
-    if (c == 0xe2 && pos + 2 < in.size()) {
-      const unsigned char d = (unsigned char)in[pos + 1], e = (unsigned char)in[pos + 2];
-      if (d == 0x80 && ((e >= 0x80 && e <= 0x8a) || e == 0xa8 || e == 0xa9 || e == 0xaf)) return 3;
-      if (d == 0x81 && e == 0x9f) return 3;
-    }
-    if (c == 0xe3 && pos + 2 < in.size() && (unsigned char)in[pos + 1] == 0x80 && (unsigned char)in[pos + 2] == 0x80) return 3;
-    return 0;
-  }
-  size_t char_len() const {  // bytes of the UTF-8 character at pos
-    const unsigned char c = (unsigned char)in[pos];
-    const size_t n = c < 0x80 ? 1 : c < 0xe0 ? 2 : c < 0xf0 ? 3 : 4;
-    return pos + n <= in.size() ? n : in.size() - pos;
-  }
+  // for is ASCII, so bytes behave the same except for non-ASCII whitespace (char::is_whitespace, text_util.h)
+  size_t ws_len() const { return text::ws_len(in.data(), pos, in.size()); }
+  size_t char_len() const { return text::char_len(in.data(), pos, in.size()); }
   void skip_ws() {
     while (!eof()) {
       const size_t n = ws_len();

@@ -2,6 +2,7 @@
 // oracle in isolation.  Declared in include/pgmm_b200.h.
 #include "../../include/pgmm_b200.h"
 #include "chain_fill.h"
+#include "fasta.h"
 #include "guide_tree.h"
 #include "ksw_extd2.h"
 #include "mash.h"
@@ -238,3 +239,46 @@ extern "C" int pgmm_tree_postorder(int n, const int32_t *left, const int32_t *ri
 }
 
 extern "C" void pgmm_free(void *p) { free(p); }
+
+// ---------------- Part 6: FASTA input ----------------
+static int fasta_out(bool ok, const std::vector<fasta::Record> &rs, const std::string &msg, pgmm_fasta_record_t **recs, int64_t *n_recs,
+                     char *err, int err_cap) {
+  *recs = nullptr, *n_recs = 0;
+  if (!ok) {
+    if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", msg.c_str());
+    return -1;
+  }
+  pgmm_fasta_record_t *out = (pgmm_fasta_record_t *)calloc(std::max<size_t>(1, rs.size()), sizeof(pgmm_fasta_record_t));
+  for (size_t i = 0; i < rs.size(); ++i) {
+    out[i].name = dup_array(rs[i].name.c_str(), rs[i].name.size() + 1);
+    out[i].desc = rs[i].has_desc ? dup_array(rs[i].desc.c_str(), rs[i].desc.size() + 1) : nullptr;
+    out[i].seq = dup_array(rs[i].seq.c_str(), rs[i].seq.size() + 1);
+    out[i].len = (int64_t)rs[i].seq.size(), out[i].index = rs[i].index;
+  }
+  *recs = out, *n_recs = (int64_t)rs.size();
+  return 0;
+}
+
+extern "C" int pgmm_fasta_read_files(int n_paths, const char *const *paths, const char *alphabet, pgmm_fasta_record_t **recs,
+                                     int64_t *n_recs, char *err, int err_cap) {
+  std::vector<std::string> ps;
+  for (int i = 0; i < n_paths; ++i) ps.emplace_back(paths[i]);
+  std::vector<fasta::Record> rs;
+  std::string msg;
+  const bool ok = fasta::read_files(ps, alphabet, rs, msg);
+  return fasta_out(ok, rs, msg, recs, n_recs, err, err_cap);
+}
+
+extern "C" int pgmm_fasta_read_buffer(const char *data, int64_t n, const char *alphabet, pgmm_fasta_record_t **recs, int64_t *n_recs,
+                                      char *err, int err_cap) {
+  std::vector<fasta::Record> rs;
+  std::string msg;
+  const bool ok = fasta::read_buffer(data, (size_t)std::max<int64_t>(0, n), alphabet, rs, msg);
+  return fasta_out(ok, rs, msg, recs, n_recs, err, err_cap);
+}
+
+extern "C" void pgmm_fasta_free(pgmm_fasta_record_t *recs, int64_t n_recs) {
+  if (!recs) return;
+  for (int64_t i = 0; i < n_recs; ++i) free(recs[i].name), free(recs[i].desc), free(recs[i].seq);
+  free(recs);
+}
