@@ -155,3 +155,32 @@ def build_tree_from_newick(text, seq_names):
     m = t.n
     ren = lambda v: leaf_of[v] if v < m else v
     return GuideTree(m, [ren(v) for v in t.left], [ren(v) for v in t.right], list(seq_names))
+
+
+def main(argv=None):
+    """`python -m pangraph_b200.guide_tree a.fa [b.fa.gz ...]`: the guide tree `pangraph build` would use for these genomes
+    (FASTA in as the reference reads it, mash distance on the GPU, neighbour joining), printed as the Newick line the
+    reference logs (`Guide tree (newick): ...`, commands/build/build_run.rs:102); `--balance` prints the bisected tree too."""
+    import argparse
+    import sys
+    from . import fasta
+    ap = argparse.ArgumentParser(prog="python -m pangraph_b200.guide_tree", description=main.__doc__)
+    ap.add_argument("fasta", nargs="+")
+    ap.add_argument("--balance", action="store_true")
+    ap.add_argument("--distances", action="store_true", help="print the mash distance matrix as well")
+    args = ap.parse_args(argv)
+    recs = fasta.read_many(args.fasta)
+    names = [r.seq_name for r in recs]
+    D = mash_distance([r.seq for r in recs])
+    if args.distances:
+        for name, row in zip(names, D):
+            print(name, " ".join(f"{v:.6f}" for v in row), file=sys.stderr)
+    tree = neighbor_joining(D, names)
+    print(tree.to_newick())
+    if args.balance:
+        print(tree.balance().to_newick())
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
