@@ -108,3 +108,13 @@ def test_distance_from_sets(emul):
         for j in range(i + 1, n):
             got[i, j] = got[j, i] = 1.0 - len(sets[i] & sets[j]) / len(sets[i])
     assert np.array_equal(got, want)
+
+
+def test_window_and_kmer_size_sweep(emul):
+    """window sizes around 1, the warp width and the block boundaries of the window-minimum scans, k from 1 to 31, on random,
+    two-letter (many equal values per window), one-letter and N-rich sequences, the last two longer than a tile"""
+    rng = np.random.default_rng(5)
+    for w in (1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 254, 255):
+        for k in (1, 2, 3, 8, 15, 16, 31):
+            for alphabet, n in ((b"ACGT", 700), (b"AC", 900), (b"A", 300), (b"ACGTN", 800), (b"ACGT", 4096 + w + 3), (b"AC", 8192 + 5)):
+                check(emul, rand_seq(rng, n, alphabet=alphabet), k, w, sid=2)
